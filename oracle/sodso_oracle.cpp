@@ -1,0 +1,695 @@
+// =============================================================================
+//  ORACLE — TEST INFRASTRUCTURE ONLY.  NOT PART OF THE PRODUCT.
+//
+//  CPU restatement (C++17, no Eigen) of the descriptor generate + match hot
+//  path of IRVLab/so_dso_place_recognition.  Only tests/, __graft_entry__.smoke()
+//  and bench.py's cpu_baseline / --impl reference legs may load this library.
+//
+//  PARITY STATUS: **parity unpinned** for descriptor values / distances / top-1.
+//  The reference ships no golden signatures (history_*.txt is git-ignored,
+//  /root/reference/.gitignore:1) and cannot be compiled here (needs Eigen, ROS:
+//  PosesPts.h:1, test_sc.cpp:4).  What IS pinned: frame selection
+//  (incoming_id_file.txt of all 13 committed sequences, reproduced exactly by
+//  orc_stage_* below; see tests/test_oracle_golden.py).
+//
+//  Third-party arithmetic not in /root/reference: Eigen3 (unpinned version,
+//  CMakeLists.txt:7) SelfAdjointEigenSolver / JacobiSVD.  Restated here by a
+//  cyclic Jacobi symmetric eigen-solver and a one-sided Jacobi SVD with the
+//  sign conventions documented at orc_sym_eig3 / orc_svd_dominant.
+//
+//  Compiled with -ffp-contract=off: every fp64 op is a separately rounded
+//  IEEE operation in source order.
+// =============================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+constexpr int SC_NUM_S = 60;   // SC.h:7
+constexpr int SC_NUM_R = 20;   // SC.h:8
+constexpr int SC_SIZE = SC_NUM_S * SC_NUM_R;
+constexpr int M2DP_NUM_S = 16; // M2DP.h:7  (theta)
+constexpr int M2DP_NUM_R = 8;  // M2DP.h:8  (rho)
+constexpr int M2DP_NUM_P = 4;  // M2DP.h:9
+constexpr int M2DP_NUM_Q = 16; // M2DP.h:10
+constexpr int M2DP_PQ = M2DP_NUM_P * M2DP_NUM_Q;   // 64
+constexpr int M2DP_SR = M2DP_NUM_S * M2DP_NUM_R;   // 128
+constexpr int M2DP_SIG = M2DP_PQ + M2DP_SR;        // 192, M2DP.cpp:36
+
+// -----------------------------------------------------------------------------
+// Symmetric 3x3 eigen-decomposition, eigenvalues ascending (stands in for
+// Eigen::SelfAdjointEigenSolver, pts_align.h:31-34).  Cyclic Jacobi.
+// SIGN CONVENTION (ours; Eigen's is implementation-defined): each eigenvector
+// is scaled so that its largest-magnitude component is positive (ties -> lowest
+// index).
+// a: row-major 3x3 symmetric.  w[3] ascending, v column k = (v[0*3+k],v[1*3+k],v[2*3+k]).
+// -----------------------------------------------------------------------------
+void sym_eig3(const double a_in[9], double w[3], double v[9]) {
+  double a[3][3], q[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      a[i][j] = a_in[i * 3 + j];
+      q[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+  for (int sweep = 0; sweep < 64; sweep++) {
+    double off = std::fabs(a[0][1]) + std::fabs(a[0][2]) + std::fabs(a[1][2]);
+    if (off == 0.0) break;
+    for (int p = 0; p < 2; p++) {
+      for (int r = p + 1; r < 3; r++) {
+        double apq = a[p][r];
+        if (apq == 0.0) continue;
+        double theta = (a[r][r] - a[p][p]) / (2.0 * apq);
+        double t = 1.0 / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        if (theta < 0.0) t = -t;
+        double c = 1.0 / std::sqrt(t * t + 1.0);
+        double s = t * c;
+        // A <- J^T A J  with J = [[c, s], [-s, c]] on (p, r)
+        for (int k = 0; k < 3; k++) {
+          double akp = a[k][p], akr = a[k][r];
+          a[k][p] = c * akp - s * akr;
+          a[k][r] = s * akp + c * akr;
+        }
+        for (int k = 0; k < 3; k++) {
+          double apk = a[p][k], ark = a[r][k];
+          a[p][k] = c * apk - s * ark;
+          a[r][k] = s * apk + c * ark;
+        }
+        a[p][r] = 0.0;
+        a[r][p] = 0.0;
+        for (int k = 0; k < 3; k++) {
+          double qkp = q[k][p], qkr = q[k][r];
+          q[k][p] = c * qkp - s * qkr;
+          q[k][r] = s * qkp + c * qkr;
+        }
+      }
+    }
+  }
+  int order[3] = {0, 1, 2};
+  double d[3] = {a[0][0], a[1][1], a[2][2]};
+  // stable insertion sort ascending
+  for (int i = 1; i < 3; i++) {
+    int oi = order[i];
+    int j = i - 1;
+    while (j >= 0 && d[order[j]] > d[oi]) {
+      order[j + 1] = order[j];
+      j--;
+    }
+    order[j + 1] = oi;
+  }
+  for (int k = 0; k < 3; k++) {
+    int src = order[k];
+    w[k] = d[src];
+    double col[3] = {q[0][src], q[1][src], q[2][src]};
+    int big = 0;
+    for (int i = 1; i < 3; i++)
+      if (std::fabs(col[i]) > std::fabs(col[big])) big = i;
+    double sgn = (col[big] < 0.0) ? -1.0 : 1.0;
+    for (int i = 0; i < 3; i++) v[i * 3 + k] = sgn * col[i];
+  }
+}
+
+// pts_align.h:7-46.  xyz AoS n x 3 -> out AoS n x 3 in the PCA frame
+// (x: least variance "up", y: middle, z: largest).  evec (optional) = 3x3
+// row-major, column k = k-th eigenvector.
+void align_pca(const double* xyz, int n, double* out, double* evec, double* mean_out) {
+  double mx = 0, my = 0, mz = 0;                       // pts_align.h:10-15 (sequential)
+  for (int i = 0; i < n; i++) {
+    mx += xyz[3 * i + 0];
+    my += xyz[3 * i + 1];
+    mz += xyz[3 * i + 2];
+  }
+  mx /= (double)n;                                     // pts_align.h:16-18
+  my /= (double)n;
+  mz /= (double)n;
+  // cov = P^T P of the centred points, NOT divided by n (pts_align.h:21-30).
+  // Eigen's product order is unspecified; we sum sequentially over points.
+  double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+  for (int i = 0; i < n; i++) {
+    double x = xyz[3 * i + 0] - mx, y = xyz[3 * i + 1] - my, z = xyz[3 * i + 2] - mz;
+    c00 += x * x; c01 += x * y; c02 += x * z;
+    c11 += y * y; c12 += y * z; c22 += z * z;
+  }
+  double cov[9] = {c00, c01, c02, c01, c11, c12, c02, c12, c22};
+  double w[3], v[9];
+  sym_eig3(cov, w, v);                                 // pts_align.h:31-34
+  for (int i = 0; i < n; i++) {                        // pts_align.h:37-45
+    double x = xyz[3 * i + 0] - mx, y = xyz[3 * i + 1] - my, z = xyz[3 * i + 2] - mz;
+    out[3 * i + 0] = (x * v[0] + y * v[3]) + z * v[6];
+    out[3 * i + 1] = (x * v[1] + y * v[4]) + z * v[7];
+    out[3 * i + 2] = (x * v[2] + y * v[5]) + z * v[8];
+  }
+  if (evec) std::memcpy(evec, v, sizeof(v));
+  if (mean_out) { mean_out[0] = mx; mean_out[1] = my; mean_out[2] = mz; }
+}
+
+// SC.cpp:12-76
+void sc_signature(const double* xyz, const float* inten, int n, double max_rho,
+                  double* structure, double* intensity) {
+  const double S_res_inv = SC_NUM_S / (2.0 * M_PI);    // SC.cpp:6
+  const double R_res_inv = SC_NUM_R / max_rho;         // SC.cpp:7
+  std::vector<double> al((size_t)3 * std::max(n, 1));
+  align_pca(xyz, n, al.data(), nullptr, nullptr);      // SC.cpp:17
+  std::vector<double> cnt(SC_SIZE, 0.0), lo(SC_SIZE, 0.0), hi(SC_SIZE, 0.0), isum(SC_SIZE, 0.0);
+  for (int i = 0; i < n; i++) {                        // SC.cpp:29-57
+    double yp = al[3 * i + 1];
+    double zp = al[3 * i + 2];
+    int si = static_cast<int>(std::floor((std::atan2(zp, yp) + M_PI) * S_res_inv));
+    int ri = static_cast<int>(std::floor(std::sqrt(yp * yp + zp * zp) * R_res_inv));
+    int idx = si * SC_NUM_R + ri;
+    // SC.cpp:42: `idx >= getSignatureSize()` is int-vs-unsigned: negative idx is dropped too.
+    if ((unsigned int)idx >= (unsigned int)SC_SIZE) continue;
+    if (cnt[idx] == 0) {
+      isum[idx] = inten[i];
+      lo[idx] = al[3 * i + 0];
+      hi[idx] = al[3 * i + 0];
+    } else {
+      isum[idx] += double(inten[i]);
+      lo[idx] = std::min(lo[idx], al[3 * i + 0]);
+      hi[idx] = std::max(hi[idx], al[3 * i + 0]);
+    }
+    cnt[idx]++;
+  }
+  float ave = 0;                                       // SC.cpp:60-64 (float, sequential)
+  for (int i = 0; i < n; i++) ave += inten[i];
+  ave = ave / n;
+  for (int i = 0; i < SC_SIZE; i++) {                  // SC.cpp:67-72
+    if (cnt[i]) {
+      isum[i] = isum[i] / cnt[i];
+      isum[i] = isum[i] > ave ? 1 : 0;
+    }
+  }
+  for (int i = 0; i < SC_SIZE; i++) {                  // SC.cpp:74-75
+    structure[i] = hi[i] - lo[i];
+    intensity[i] = isum[i];
+  }
+}
+
+// M2DP.cpp:4-34.  Tables are 3 x 64, stored [k*3 + c] (column k = plane p*16+q).
+void m2dp_tables(double* xproj, double* yproj) {
+  for (int p = 0; p < M2DP_NUM_P; p++) {
+    float azm = -M_PI / 2.0 + (M_PI / M2DP_NUM_P) * p;             // M2DP.cpp:10 (float)
+    for (int q = 0; q < M2DP_NUM_Q; q++) {
+      float elv = (M_PI / 2.0 / M2DP_NUM_Q) * q;                   // M2DP.cpp:14 (float)
+      // std::cos(float) -> float; product of floats -> float; stored in double (M2DP.cpp:17-18)
+      double n0 = std::cos(elv) * std::cos(azm);
+      double n1 = std::cos(elv) * std::sin(azm);
+      double n2 = std::sin(elv);
+      // xProj = e_x - (e_x . n) n    (M2DP.cpp:21-22)
+      double d = (1.0 * n0 + 0.0 * n1) + 0.0 * n2;
+      double x0 = 1.0 - d * n0, x1 = 0.0 - d * n1, x2 = 0.0 - d * n2;
+      // yProj = n x xProj            (M2DP.cpp:25)
+      double y0 = n1 * x2 - n2 * x1;
+      double y1 = n2 * x0 - n0 * x2;
+      double y2 = n0 * x1 - n1 * x0;
+      int k = p * M2DP_NUM_Q + q;
+      xproj[3 * k + 0] = x0; xproj[3 * k + 1] = x1; xproj[3 * k + 2] = x2;
+      yproj[3 * k + 0] = y0; yproj[3 * k + 1] = y1; yproj[3 * k + 2] = y2;
+    }
+  }
+}
+
+// Dominant singular pair of a rows x cols (rows <= cols) row-major matrix A,
+// standing in for Eigen::JacobiSVD thin U/V column 0 (M2DP.cpp:94-103).
+// One-sided (Hestenes) Jacobi on the `rows` row-vectors of A:  A^T J = W with
+// orthogonal columns; U = J, sigma_k = |W_k|, V_k = W_k / sigma_k.
+// SIGN CONVENTION (ours; Eigen's is unobservable here): the pair (u1, v1) is
+// oriented so that sum(u1) >= 0 (Perron vector of a non-negative matrix).
+void svd_dominant(const double* A, int rows, int cols, double* u1, double* v1, double* sigma_out) {
+  std::vector<double> W((size_t)rows * cols);   // row i = current i-th vector (length cols)
+  std::vector<double> J((size_t)rows * rows, 0.0);
+  std::memcpy(W.data(), A, sizeof(double) * rows * cols);
+  for (int i = 0; i < rows; i++) J[(size_t)i * rows + i] = 1.0;
+  const double eps = 1e-15;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    bool rotated = false;
+    for (int p = 0; p < rows - 1; p++) {
+      for (int q = p + 1; q < rows; q++) {
+        double* wp = &W[(size_t)p * cols];
+        double* wq = &W[(size_t)q * cols];
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int k = 0; k < cols; k++) {
+          alpha += wp[k] * wp[k];
+          beta += wq[k] * wq[k];
+          gamma += wp[k] * wq[k];
+        }
+        if (gamma == 0.0 || std::fabs(gamma) <= eps * std::sqrt(alpha * beta)) continue;
+        rotated = true;
+        double zeta = (beta - alpha) / (2.0 * gamma);
+        double t = 1.0 / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        if (zeta < 0.0) t = -t;
+        double c = 1.0 / std::sqrt(1.0 + t * t);
+        double s = c * t;
+        for (int k = 0; k < cols; k++) {
+          double a = wp[k], b = wq[k];
+          wp[k] = c * a - s * b;
+          wq[k] = s * a + c * b;
+        }
+        // J columns p, q (J stored so that column p is J[k*rows + p])
+        for (int k = 0; k < rows; k++) {
+          double a = J[(size_t)k * rows + p], b = J[(size_t)k * rows + q];
+          J[(size_t)k * rows + p] = c * a - s * b;
+          J[(size_t)k * rows + q] = s * a + c * b;
+        }
+      }
+    }
+    if (!rotated) break;
+  }
+  int best = 0;
+  double best_n2 = -1.0;
+  for (int i = 0; i < rows; i++) {
+    double n2 = 0;
+    for (int k = 0; k < cols; k++) n2 += W[(size_t)i * cols + k] * W[(size_t)i * cols + k];
+    if (n2 > best_n2) { best_n2 = n2; best = i; }
+  }
+  double sigma = std::sqrt(best_n2);
+  double su = 0;
+  for (int k = 0; k < rows; k++) su += J[(size_t)k * rows + best];
+  double sgn = (su < 0.0) ? -1.0 : 1.0;
+  for (int k = 0; k < rows; k++) u1[k] = sgn * J[(size_t)k * rows + best];
+  for (int k = 0; k < cols; k++)
+    v1[k] = (sigma > 0.0) ? sgn * W[(size_t)best * cols + k] / sigma : 0.0;
+  if (sigma_out) *sigma_out = sigma;
+}
+
+// M2DP.cpp:38-109.  Input is already PCA-aligned + sign-flipped (test_m2dp.cpp:44-57).
+void m2dp_signature(const double* pts, const float* inten, int n, double max_rho,
+                    const double* xproj, const double* yproj,
+                    double* count_out, double* inten_out, double* A_cnt_out, double* A_int_out) {
+  const double S_res_inv = M2DP_NUM_S / (2.0 * M_PI);  // M2DP.cpp:32
+  const double R_res_inv = M2DP_NUM_R / max_rho;       // M2DP.cpp:33
+  std::vector<double> cnt((size_t)M2DP_PQ * M2DP_SR, 0.0), isum((size_t)M2DP_PQ * M2DP_SR, 0.0);
+  for (int pq = 0; pq < M2DP_PQ; pq++) {               // M2DP.cpp:47-74
+    const double* xP = &xproj[3 * pq];
+    const double* yP = &yproj[3 * pq];
+    for (int i = 0; i < n; i++) {
+      const double* pt = &pts[3 * i];
+      double xp = (xP[0] * pt[0] + xP[1] * pt[1]) + xP[2] * pt[2];   // Eigen dot, M2DP.cpp:56
+      double yp = (yP[0] * pt[0] + yP[1] * pt[1]) + yP[2] * pt[2];   // M2DP.cpp:57
+      int si = static_cast<int>(std::floor((std::atan2(yp, xp) + M_PI) * S_res_inv));
+      int ri = static_cast<int>(std::floor(std::sqrt(xp * xp + yp * yp) * R_res_inv));
+      int idx_sr = ri * M2DP_NUM_S + si;                             // M2DP.cpp:63
+      if (idx_sr >= M2DP_SR) continue;                               // M2DP.cpp:66 (signed compare)
+      if (idx_sr < 0) continue;  // unreachable for finite input (si,ri >= 0); guards NaN -> INT_MIN
+      cnt[(size_t)pq * M2DP_SR + idx_sr]++;
+      isum[(size_t)pq * M2DP_SR + idx_sr] += inten[i];
+    }
+  }
+  float ave = 0;                                       // M2DP.cpp:77-81
+  for (int i = 0; i < n; i++) ave += inten[i];
+  ave = ave / n;
+  for (size_t k = 0; k < cnt.size(); k++) {            // M2DP.cpp:84-91
+    if (cnt[k]) {
+      isum[k] = isum[k] / cnt[k];
+      isum[k] = isum[k] > ave ? 1 : 0;
+    }
+  }
+  svd_dominant(cnt.data(), M2DP_PQ, M2DP_SR, count_out, count_out + M2DP_PQ, nullptr);   // :94-98,107
+  svd_dominant(isum.data(), M2DP_PQ, M2DP_SR, inten_out, inten_out + M2DP_PQ, nullptr);  // :100-108
+  if (A_cnt_out) std::memcpy(A_cnt_out, cnt.data(), sizeof(double) * cnt.size());
+  if (A_int_out) std::memcpy(A_int_out, isum.data(), sizeof(double) * isum.size());
+}
+
+}  // namespace
+
+extern "C" {
+
+int orc_sc_size() { return SC_SIZE; }
+int orc_m2dp_size() { return M2DP_SIG; }
+
+void orc_sym_eig3(const double* a, double* w, double* v) { sym_eig3(a, w, v); }
+
+void orc_align_pca(const double* xyz, int n, double* out, double* evec, double* mean) {
+  align_pca(xyz, n, out, evec, mean);
+}
+
+void orc_sc_signature(const double* xyz, const float* inten, int n, double max_rho,
+                      double* structure, double* intensity) {
+  sc_signature(xyz, inten, n, max_rho, structure, intensity);
+}
+
+// test_sc.cpp:36-57 — rows of history_sc: [structure(1200), intensity(1200)].
+void orc_sc_generate(const double* xyz, const float* inten, const int64_t* off, int nscan,
+                     double max_rho, double* hist /* nscan x 2400 */, int nthreads) {
+#pragma omp parallel for schedule(dynamic) num_threads(nthreads > 0 ? nthreads : 1)
+  for (int s = 0; s < nscan; s++) {
+    int64_t b = off[s];
+    int n = (int)(off[s + 1] - off[s]);
+    sc_signature(xyz + 3 * b, inten + b, n, max_rho, hist + (size_t)s * 2 * SC_SIZE,
+                 hist + (size_t)s * 2 * SC_SIZE + SC_SIZE);
+  }
+}
+
+void orc_m2dp_tables(double* xproj, double* yproj) { m2dp_tables(xproj, yproj); }
+
+void orc_svd_dominant(const double* A, int rows, int cols, double* u1, double* v1, double* sigma) {
+  svd_dominant(A, rows, cols, u1, v1, sigma);
+}
+
+void orc_m2dp_signature(const double* pts, const float* inten, int n, double max_rho,
+                        double* count_out, double* inten_out, double* A_cnt, double* A_int) {
+  double xp[3 * M2DP_PQ], yp[3 * M2DP_PQ];
+  m2dp_tables(xp, yp);
+  m2dp_signature(pts, inten, n, max_rho, xp, yp, count_out, inten_out, A_cnt, A_int);
+}
+
+// test_m2dp.cpp:41-67 — PCA once, 4 sign variants (dx outer, dy inner), rows 4i..4i+3 =
+// [count(192), intensity(192)].
+void orc_m2dp_frame(const double* xyz, const float* inten, int n, double max_rho, double* out) {
+  double xp[3 * M2DP_PQ], yp[3 * M2DP_PQ];
+  m2dp_tables(xp, yp);
+  std::vector<double> al((size_t)3 * std::max(n, 1)), var((size_t)3 * std::max(n, 1));
+  align_pca(xyz, n, al.data(), nullptr, nullptr);
+  int sub = 0;
+  for (int dx = -1; dx < 2; dx += 2) {
+    for (int dy = -1; dy < 2; dy += 2) {
+      for (int i = 0; i < n; i++) {
+        var[3 * i + 0] = dx * al[3 * i + 0];
+        var[3 * i + 1] = dy * al[3 * i + 1];
+        var[3 * i + 2] = (dx * dy) * al[3 * i + 2];
+      }
+      double* row = out + (size_t)sub * 2 * M2DP_SIG;
+      m2dp_signature(var.data(), inten, n, max_rho, xp, yp, row, row + M2DP_SIG, nullptr, nullptr);
+      sub++;
+    }
+  }
+}
+
+void orc_m2dp_generate(const double* xyz, const float* inten, const int64_t* off, int nscan,
+                       double max_rho, double* hist /* 4*nscan x 384 */, int nthreads) {
+#pragma omp parallel for schedule(dynamic) num_threads(nthreads > 0 ? nthreads : 1)
+  for (int s = 0; s < nscan; s++) {
+    int64_t b = off[s];
+    int n = (int)(off[s + 1] - off[s]);
+    orc_m2dp_frame(xyz + 3 * b, inten + b, n, max_rho, hist + (size_t)s * 4 * 2 * M2DP_SIG);
+  }
+}
+
+// -----------------------------------------------------------------------------
+// processSC.m:12-45 for ONE channel.  h1: m x 1200, h2: n x 1200 (row-major,
+// element s*20+r as written by SC.cpp:39).  res: m x n.
+// MATLAB `min` ignores NaN unless all are NaN; x/0 -> NaN rows propagate.
+// -----------------------------------------------------------------------------
+static void sc_match_channel(const double* h1, int m, const double* h2, int n, double* res,
+                             int nthreads) {
+  std::vector<double> a((size_t)m * SC_SIZE), b((size_t)n * SC_SIZE);
+  auto normalise = [](const double* src, double* dst, int rows) {   // processSC.m:15-20
+    for (int i = 0; i < rows; i++) {
+      double ss = 0;
+      for (int k = 0; k < SC_SIZE; k++) ss += src[(size_t)i * SC_SIZE + k] * src[(size_t)i * SC_SIZE + k];
+      double nrm = std::sqrt(ss);
+      for (int k = 0; k < SC_SIZE; k++) dst[(size_t)i * SC_SIZE + k] = src[(size_t)i * SC_SIZE + k] / nrm;
+    }
+  };
+  normalise(h1, a.data(), m);
+  normalise(h2, b.data(), n);
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+  {
+    std::vector<double> sig((size_t)120 * SC_SIZE);
+#pragma omp for schedule(dynamic)
+    for (int i = 0; i < m; i++) {
+      const double* q = &a[(size_t)i * SC_SIZE];
+      // permute_sc (processSC.m:37-45): h_img = reshape(row,[20,60]) -> column s is sector s.
+      for (int k = 1; k <= 60; k++) {
+        double* fwd = &sig[(size_t)(2 * k - 2) * SC_SIZE];   // row 2k-1 (1-based)
+        double* rev = &sig[(size_t)(2 * k - 1) * SC_SIZE];   // row 2k
+        for (int c = 0; c < 60; c++) {
+          // forward: columns [k..60, 1..k-1]  -> c-th output column = sector (k-1+c) mod 60
+          int sf = (k - 1 + c) % 60;
+          // reverse: columns [k,k-1..1, 60..k+1] -> c-th output column = sector (k-1-c) mod 60
+          int sr = ((k - 1 - c) % 60 + 60) % 60;
+          std::memcpy(fwd + c * 20, q + sf * 20, 20 * sizeof(double));
+          std::memcpy(rev + c * 20, q + sr * 20, 20 * sizeof(double));
+        }
+      }
+      for (int j = 0; j < n; j++) {
+        const double* h = &b[(size_t)j * SC_SIZE];
+        double best = std::numeric_limits<double>::quiet_NaN();
+        for (int v = 0; v < 120; v++) {
+          const double* s = &sig[(size_t)v * SC_SIZE];
+          double dot = 0;
+          for (int k = 0; k < SC_SIZE; k++) dot += s[k] * h[k];
+          double d = (1.0 - dot) / 2.0;                         // processSC.m:30
+          if (!(d != d)) {                                       // min skipping NaN (:31)
+            if (best != best || d < best) best = d;
+          }
+        }
+        res[(size_t)i * n + j] = best;
+      }
+    }
+  }
+}
+
+// processSC.m:1-10.  hist rows = [structure(1200), intensity(1200)].
+void orc_sc_match(const double* hist1, int m, const double* hist2, int n, double* d_p, double* d_i,
+                  int nthreads) {
+  std::vector<double> a((size_t)m * SC_SIZE), b((size_t)n * SC_SIZE);
+  for (int ch = 0; ch < 2; ch++) {
+    for (int i = 0; i < m; i++)
+      std::memcpy(&a[(size_t)i * SC_SIZE], hist1 + (size_t)i * 2 * SC_SIZE + ch * SC_SIZE, SC_SIZE * sizeof(double));
+    for (int i = 0; i < n; i++)
+      std::memcpy(&b[(size_t)i * SC_SIZE], hist2 + (size_t)i * 2 * SC_SIZE + ch * SC_SIZE, SC_SIZE * sizeof(double));
+    sc_match_channel(a.data(), m, b.data(), n, ch == 0 ? d_p : d_i, nthreads);
+  }
+}
+
+// processM2DP.m:1-22.  hist1: 4m x 384, hist2: 4n x 384; outputs m x n.
+void orc_m2dp_match(const double* hist1, int m, const double* hist2, int n, double* d_p, double* d_i,
+                    int nthreads) {
+  for (int ch = 0; ch < 2; ch++) {
+    double* out = ch == 0 ? d_p : d_i;
+#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
+    for (int i = 0; i < m; i++) {
+      for (int j = 0; j < n; j++) {
+        double best = std::numeric_limits<double>::quiet_NaN();
+        for (int a = 0; a < 4; a++) {
+          const double* r1 = hist1 + (size_t)(4 * i + a) * 2 * M2DP_SIG + ch * M2DP_SIG;
+          for (int b = 0; b < 4; b++) {
+            const double* r2 = hist2 + (size_t)(4 * j + b) * 2 * M2DP_SIG + ch * M2DP_SIG;
+            double dot = 0;
+            for (int k = 0; k < M2DP_SIG; k++) dot += r1[k] * r2[k];
+            double d = (1.0 - dot) / 2.0;                       // processM2DP.m:15
+            if (!(d != d)) {
+              if (best != best || d < best) best = d;           // :19
+            }
+          }
+        }
+        out[(size_t)i * n + j] = best;
+      }
+    }
+  }
+}
+
+// run_test.m:38-57.  fused = p_weight*zscore_row(d_p) + zscore_row(d_i) (std with N-1,
+// over the UNMASKED row), then |i-j| < mask_width -> Inf, then first-index argmin.
+// idx is 0-based (MATLAB's is 1-based).  fused_out optional (m x n, after masking).
+void orc_fuse_top1(const double* d_p, const double* d_i, int m, int n, int mask_width,
+                   double p_weight, int* idx, double* score, double* fused_out) {
+  std::vector<double> row(n);
+  for (int i = 0; i < m; i++) {
+    const double* chans[2] = {d_p + (size_t)i * n, d_i + (size_t)i * n};
+    double mu[2], sd[2];
+    for (int c = 0; c < 2; c++) {
+      double s = 0;
+      for (int j = 0; j < n; j++) s += chans[c][j];
+      mu[c] = s / n;
+      double v = 0;
+      for (int j = 0; j < n; j++) {
+        double d = chans[c][j] - mu[c];
+        v += d * d;
+      }
+      sd[c] = std::sqrt(v / (n - 1));
+    }
+    for (int j = 0; j < n; j++)
+      row[j] = p_weight * ((chans[0][j] - mu[0]) / sd[0]) + (chans[1][j] - mu[1]) / sd[1];
+    for (int j = 0; j < n; j++)                                  // run_test.m:47-53
+      if (std::abs(i - j) < mask_width) row[j] = std::numeric_limits<double>::infinity();
+    int bi = 0;                                                  // run_test.m:57 (first min; NaN skipped)
+    double bv = std::numeric_limits<double>::quiet_NaN();
+    for (int j = 0; j < n; j++) {
+      double v = row[j];
+      if (v != v) continue;
+      if (bv != bv || v < bv) { bv = v; bi = j; }
+    }
+    idx[i] = bi;
+    score[i] = bv;
+    if (fused_out) std::memcpy(fused_out + (size_t)i * n, row.data(), sizeof(double) * n);
+  }
+}
+
+// =============================================================================
+// Staging: PosesPts.h + pts_preprocess.h restated with the very
+// same std::unordered_map<int,...> so that libstdc++ iteration order (T16) is
+// reproduced.  Result is kept in a handle and copied out by orc_stage_get_*.
+// =============================================================================
+struct StageResult {
+  std::vector<int> incoming_ids;
+  std::vector<int64_t> off;           // nscan + 1
+  std::vector<double> xyz;            // total x 3
+  std::vector<float> inten;
+  int n_poses = 0;
+  int64_t n_pts = 0;
+};
+
+struct PtI { int id; double p[3]; float it; };
+struct PoseI { int id; double w[12]; };
+
+static void filter_grid(const std::vector<PtI>& in, double lidar_range, const double resolution[3],
+                        std::vector<double>& oxyz, std::vector<float>& oint) {
+  // pts_preprocess.h:51-94
+  double res_xyz[3] = {lidar_range / resolution[0], lidar_range / resolution[1], lidar_range / resolution[2]};
+  double steps[3] = {1.0 / res_xyz[0], 1.0 / res_xyz[1], 1.0 / res_xyz[2]};
+  int voxel_size[3] = {static_cast<int>(std::floor(2 * lidar_range * steps[0]) + 1),
+                       static_cast<int>(std::floor(2 * lidar_range * steps[1]) + 1),
+                       static_cast<int>(std::floor(2 * lidar_range * steps[2]) + 1)};
+  int loc_step[3] = {1, voxel_size[0], voxel_size[0] * voxel_size[1]};
+  struct V { int idx; double p[3]; };
+  std::unordered_map<int, V> loc2;
+  for (size_t idx = 0; idx < in.size(); idx++) {
+    const double* pt = in[idx].p;
+    int xi = static_cast<int>(std::floor((pt[0] + lidar_range) * steps[0]));
+    int yi = static_cast<int>(std::floor((pt[1] + lidar_range) * steps[1]));
+    int zi = static_cast<int>(std::floor((pt[2] + lidar_range) * steps[2]));
+    int loc = xi * loc_step[0] + yi * loc_step[1] + zi * loc_step[2];
+    auto it = loc2.find(loc);
+    if (it == loc2.end() || -it->second.p[1] < -pt[1]) {
+      V v; v.idx = (int)idx; v.p[0] = pt[0]; v.p[1] = pt[1]; v.p[2] = pt[2];
+      loc2[loc] = v;
+    }
+  }
+  for (auto& kv : loc2) {
+    oxyz.push_back(kv.second.p[0]); oxyz.push_back(kv.second.p[1]); oxyz.push_back(kv.second.p[2]);
+    oint.push_back(in[kv.second.idx].it);
+  }
+}
+
+static void filter_polar(const std::vector<PtI>& in, const double resolution[3],
+                         std::vector<double>& oxyz, std::vector<float>& oint) {
+  // pts_preprocess.h:96-133
+  double azi_res_inv = 1.0 / resolution[0];
+  double ele_res_inv = 1.0 / resolution[1];
+  int azi_bins = static_cast<int>(std::floor(2 * M_PI * azi_res_inv) + 1);
+  struct V { int idx; double p[3]; };
+  std::unordered_map<int, V> loc2;
+  auto norm3 = [](const double* p) { return std::sqrt((p[0] * p[0] + p[1] * p[1]) + p[2] * p[2]); };
+  for (int idx = 0; idx < (int)in.size(); idx++) {
+    const double* pt = in[idx].p;
+    double xz = std::sqrt(pt[0] * pt[0] + pt[2] * pt[2]);
+    int azi = static_cast<int>(std::floor((std::atan2(pt[2], pt[0]) + M_PI) * azi_res_inv));
+    int ele = static_cast<int>(std::floor((std::atan2(pt[1], xz) + M_PI / 2) * ele_res_inv));
+    int loc = azi + ele * azi_bins;
+    auto it = loc2.find(loc);
+    if (it == loc2.end() || norm3(it->second.p) > norm3(pt)) {
+      V v; v.idx = idx; v.p[0] = pt[0]; v.p[1] = pt[1]; v.p[2] = pt[2];
+      loc2[loc] = v;
+    }
+  }
+  for (auto& kv : loc2) {
+    oxyz.push_back(kv.second.p[0]); oxyz.push_back(kv.second.p[1]); oxyz.push_back(kv.second.p[2]);
+    oint.push_back(in[kv.second.idx].it);
+  }
+}
+
+void* orc_stage_run(const char* poses_file, const char* pts_file, double lidar_range, int polar_filter) {
+  constexpr int INIT_FRAME = 30;                       // pts_preprocess.h:13
+  constexpr double RES_GRID = 30;                      // :14
+  const double RES_POLAR = 1.0 / 180.0 * M_PI;         // :15
+  auto* R = new StageResult();
+  std::vector<PoseI> poses;
+  std::vector<PtI> pts;
+  {                                                    // read_poses_pts, :17-49
+    std::ifstream f(poses_file);
+    while (true) {
+      PoseI p;
+      if (!(f >> p.id)) break;
+      for (int k = 0; k < 12; k++)
+        if (!(f >> p.w[k])) break;
+      poses.push_back(p);
+    }
+    std::ifstream g(pts_file);
+    while (true) {
+      PtI p;
+      if (!(g >> p.id >> p.p[0] >> p.p[1] >> p.p[2] >> p.it)) break;
+      pts.push_back(p);
+    }
+  }
+  R->n_poses = (int)poses.size();
+  R->n_pts = (int64_t)pts.size();
+  R->off.push_back(0);
+  std::vector<const PtI*> nearby;
+  size_t pts_idx = 0;
+  int frame_from_reset = 0;
+  for (auto& pose : poses) {                           // :187-216
+    const double* w = pose.w;                          // row-major 3x4
+    double tn = std::sqrt((w[3] * w[3] + w[7] * w[7]) + w[11] * w[11]);
+    if (tn < 1.0) {                                    // :189-193
+      frame_from_reset = 0;
+      nearby.clear();
+    }
+    while (pts_idx < pts.size() && pts[pts_idx].id <= pose.id) {   // :196-200
+      nearby.push_back(&pts[pts_idx]);
+      pts_idx++;
+    }
+    if (frame_from_reset < INIT_FRAME) {               // :203-206
+      frame_from_reset++;
+      continue;
+    }
+    // generate_spherical_points, :135-167
+    std::vector<const PtI*> keep;
+    std::vector<PtI> raw;
+    for (auto* p : nearby) {
+      PtI l;
+      l.id = p->id;
+      l.it = p->it;
+      for (int r = 0; r < 3; r++)   // Eigen 3x4 * 4-vector: sequential sum over the 4 columns
+        l.p[r] = ((w[4 * r + 0] * p->p[0] + w[4 * r + 1] * p->p[1]) + w[4 * r + 2] * p->p[2]) + w[4 * r + 3] * 1.0;
+      double nrm = std::sqrt((l.p[0] * l.p[0] + l.p[1] * l.p[1]) + l.p[2] * l.p[2]);
+      if (nrm < lidar_range) {
+        raw.push_back(l);
+        keep.push_back(p);
+      }
+    }
+    std::vector<double> oxyz;
+    std::vector<float> oint;
+    if (polar_filter) {
+      double res[3] = {RES_POLAR, RES_POLAR, RES_POLAR};
+      filter_polar(raw, res, oxyz, oint);
+    } else {
+      double res[3] = {RES_GRID, 2 * RES_GRID, RES_GRID};
+      filter_grid(raw, lidar_range, res, oxyz, oint);
+    }
+    nearby.swap(keep);
+    R->xyz.insert(R->xyz.end(), oxyz.begin(), oxyz.end());
+    R->inten.insert(R->inten.end(), oint.begin(), oint.end());
+    R->off.push_back((int64_t)R->inten.size());
+    R->incoming_ids.push_back(pose.id);                // :215
+  }
+  return R;
+}
+
+int orc_stage_num_scans(void* h) { return (int)((StageResult*)h)->incoming_ids.size(); }
+int64_t orc_stage_num_points(void* h) { return (int64_t)((StageResult*)h)->inten.size(); }
+int orc_stage_num_poses(void* h) { return ((StageResult*)h)->n_poses; }
+void orc_stage_copy(void* h, int* ids, int64_t* off, double* xyz, float* inten) {
+  auto* R = (StageResult*)h;
+  if (ids) std::memcpy(ids, R->incoming_ids.data(), sizeof(int) * R->incoming_ids.size());
+  if (off) std::memcpy(off, R->off.data(), sizeof(int64_t) * R->off.size());
+  if (xyz) std::memcpy(xyz, R->xyz.data(), sizeof(double) * R->xyz.size());
+  if (inten) std::memcpy(inten, R->inten.data(), sizeof(float) * R->inten.size());
+}
+void orc_stage_free(void* h) { delete (StageResult*)h; }
+
+}  // extern "C"
