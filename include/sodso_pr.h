@@ -1,0 +1,156 @@
+/*
+ * sodso_pr.h — C ABI of libsodso_pr.so: the B200 (sm_100a) implementation of the
+ * descriptor generate + match hot path of IRVLab/so_dso_place_recognition.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * reference repository root).  The reference has no FFI of its own: its seams are two
+ * C++ classes + one free function (generation) and two MATLAB functions + one script
+ * section (matching / fusion); see INTEGRATION.md for the bindings a maintainer adds.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all matrices are row-major.
+ *  - every data pointer may be a HOST pointer or a DEVICE pointer (same device as the
+ *    context); the library detects which (cudaPointerGetAttributes) and stages host
+ *    buffers through its own pinned/HBM workspaces.  Nothing is ever freed for the caller.
+ *  - return value: 0 = ok, negative = error (SODSO_E_*); sodso_last_error() gives the text.
+ *  - there is NO CPU fallback: without a usable CUDA device every compute call fails.
+ *  - calls on one context are stream-ordered on the context's stream and synchronous
+ *    towards the host for host-pointer outputs; a context is not thread-safe, use one
+ *    per thread / per GPU.
+ */
+#ifndef SODSO_PR_H
+#define SODSO_PR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SODSO_OK 0
+#define SODSO_E_ARG (-1)     /* bad argument */
+#define SODSO_E_CUDA (-2)    /* CUDA runtime / driver error */
+#define SODSO_E_NODEV (-3)   /* no usable sm_100 device */
+#define SODSO_E_STATE (-4)   /* call sequence error (e.g. topk before match) */
+
+#define SODSO_SC_SIZE 1200   /* SC.h:7-8   numS*numR = 60*20 */
+#define SODSO_M2DP_SIZE 192  /* M2DP.cpp:36 numS*numR + numP*numQ = 128 + 64 */
+
+#define SODSO_TYPE_SC 0      /* run_test.m:29 'sc'   */
+#define SODSO_TYPE_M2DP 1    /* run_test.m:27 'm2dp' */
+
+/* match algorithms (sodso_ctx_set_match_algo).  TC is the product path; SIMT is a plain
+ * fp32 CUDA-core kernel kept as an on-GPU cross-check for the tensor-core path. */
+#define SODSO_ALGO_TC 0
+#define SODSO_ALGO_SIMT 1
+
+typedef struct sodso_ctx sodso_ctx;
+typedef struct sodso_db sodso_db;
+
+/* ---- context ---------------------------------------------------------------------- */
+int sodso_ctx_create(int device, sodso_ctx **out);
+void sodso_ctx_destroy(sodso_ctx *ctx);
+/* The context's stream as a cudaStream_t (void* to keep this header CUDA-free). */
+void *sodso_ctx_stream(sodso_ctx *ctx);
+/* Use an external stream (e.g. torch's current stream); NULL restores the own stream. */
+int sodso_ctx_set_stream(sodso_ctx *ctx, void *cuda_stream);
+int sodso_ctx_set_match_algo(sodso_ctx *ctx, int algo);
+const char *sodso_last_error(void);
+const char *sodso_version(void);
+/* Number of kernels of this library launched on the context so far. */
+int64_t sodso_ctx_launch_count(sodso_ctx *ctx);
+/* Device time (ms, CUDA events on the context's stream) of the dominant kernel of the last
+ * generate / match call, and its name. */
+double sodso_ctx_last_kernel_ms(sodso_ctx *ctx);
+const char *sodso_ctx_last_kernel_name(sodso_ctx *ctx);
+
+/* ---- signature sizes:  SC::getSignatureSize (SC.cpp:10), M2DP::getSignatureSize (M2DP.cpp:36) */
+int sodso_sc_signature_size(void);
+int sodso_m2dp_signature_size(void);
+
+/* ---- generation ------------------------------------------------------------------- */
+/* pts_align.h:7-46  align_points_PCA for a batch of scans.
+ * xyz: sum(n) x 3 doubles (AoS), scan_off: nscan+1 offsets (in points).  out_xyz same shape.
+ * evec (optional): nscan x 9, row-major 3x3, column k = k-th eigenvector (ascending eigenvalue). */
+int sodso_align_pca(sodso_ctx *ctx, const double *xyz, const int64_t *scan_off, int nscan,
+                    double *out_xyz, double *evec);
+
+/* SC::getSignature (SC.cpp:12-76) over a batch, output in the history_sc layout of
+ * test_sc.cpp:52-54: hist row s = [structure(1200), intensity(1200)], nscan x 2400 doubles.
+ * inten: sum(n) floats.  max_rho: SC::SC argument (lidarRange, test_sc.cpp:28,35). */
+int sodso_sc_generate(sodso_ctx *ctx, const double *xyz, const float *inten,
+                      const int64_t *scan_off, int nscan, double max_rho, double *hist);
+
+/* test_m2dp.cpp:41-67 over a batch: PCA once per scan (pts_align.h), the 4 sign variants
+ * (dx outer, dy inner), M2DP::getSignature (M2DP.cpp:38-109) for each; output in the
+ * history_m2dp layout: rows 4s..4s+3 = [count(192), intensity(192)], 4*nscan x 384 doubles. */
+int sodso_m2dp_generate(sodso_ctx *ctx, const double *xyz, const float *inten,
+                        const int64_t *scan_off, int nscan, double max_rho, double *hist);
+
+/* M2DP::getSignature (M2DP.cpp:38-109) on ALREADY aligned + sign-flipped points (the class
+ * contract, M2DP.h:18-20): sig row s = [count(192), intensity(192)], nscan x 384. */
+int sodso_m2dp_signature(sodso_ctx *ctx, const double *xyz_aligned, const float *inten,
+                         const int64_t *scan_off, int nscan, double max_rho, double *sig);
+
+/* ---- matching --------------------------------------------------------------------- */
+/* [d_p, d_i] = processSC(hist1, hist2)   (processSC.m:1-45).
+ * hist1: m x 2400, hist2: n x 2400 doubles; d_p, d_i: m x n (either may be NULL). */
+int sodso_sc_match(sodso_ctx *ctx, const double *hist1, int m, const double *hist2, int n,
+                   double *d_p, double *d_i);
+int sodso_sc_match_f32(sodso_ctx *ctx, const double *hist1, int m, const double *hist2, int n,
+                       float *d_p, float *d_i);
+
+/* [d_p, d_i] = processM2DP(hist1, hist2) (processM2DP.m:1-22).
+ * hist1: 4m x 384, hist2: 4n x 384 doubles; d_p, d_i: m x n. */
+int sodso_m2dp_match(sodso_ctx *ctx, const double *hist1, int m, const double *hist2, int n,
+                     double *d_p, double *d_i);
+int sodso_m2dp_match_f32(sodso_ctx *ctx, const double *hist1, int m, const double *hist2, int n,
+                         float *d_p, float *d_i);
+
+/* run_test.m:38-57 on given distance matrices: fused = p_weight*zscore_row(d_p) +
+ * zscore_row(d_i) (std with N-1 over the UNMASKED row), |i-j| < mask_width -> Inf,
+ * first-index argmin.  idx: m int32 (0-BASED; MATLAB's diff_idx is 1-based), score: m doubles. */
+int sodso_fuse_top1(sodso_ctx *ctx, const double *d_p, const double *d_i, int m, int n,
+                    int mask_width, double p_weight, int32_t *idx, double *score);
+
+/* run_test.m:25-57 without materialising the matrices on the host: match (type = SODSO_TYPE_SC
+ * -> processSC, SODSO_TYPE_M2DP -> processM2DP), fuse, mask, argmin.  hist1 has m (SC) or 4m
+ * (M2DP) rows.  Optional outputs (may be NULL): d_p_at / d_i_at = the two channel distances
+ * of the chosen candidate. */
+int sodso_loop_top1(sodso_ctx *ctx, int type, const double *hist1, int m, const double *hist2,
+                    int n, int mask_width, double p_weight, int32_t *idx, double *score,
+                    double *d_p_at, double *d_i_at);
+
+/* ---- resident, row-sharded signature database ------------------------ */
+/* A shard holds n_local consecutive DB signatures whose first row has global index
+ * global_row0; the signatures stay resident in HBM in MMA operand format. */
+int sodso_db_create(sodso_ctx *ctx, int type, const double *hist2, int n_local,
+                    int64_t global_row0, sodso_db **out);
+void sodso_db_destroy(sodso_db *db);
+int sodso_db_size(sodso_db *db);
+/* Distances of m queries against the shard (kept on the device inside the handle). */
+int sodso_db_match(sodso_db *db, const double *hist1, int m);
+/* Per-query partial row sums over this shard, m x 4 doubles:
+ * [sum(d_p-c), sum((d_p-c)^2), sum(d_i-c), sum((d_i-c)^2)] with c = 0.25; NaN propagates.
+ * Summed over shards (allreduce) they give the row mean / std of run_test.m:40. */
+int sodso_db_partial_stats(sodso_db *db, double *stats);
+/* Fuse with the GLOBAL stats, mask |q_global - j_global| < mask_width, emit the k best
+ * (ascending score, lowest global index first on ties) of this shard:
+ * idx (m x k, int64 global; -1 when fewer than k valid), score, d_p, d_i (m x k doubles).
+ * q_global_row0: global index of query 0 (run_test.m:47-53 compares row and column numbers). */
+int sodso_db_topk(sodso_db *db, const double *global_stats, int64_t n_global,
+                  int64_t q_global_row0, int mask_width, double p_weight, int k, int64_t *idx,
+                  double *score, double *d_p, double *d_i);
+/* Merge R gathered per-shard top-k lists (R x m x k, as produced by an allgather of
+ * sodso_db_topk outputs) into the global top-k per query (m x k).  Host-side helper. */
+int sodso_topk_merge(const int64_t *idx, const double *score, const double *d_p,
+                     const double *d_i, int nshards, int m, int k, int64_t *out_idx,
+                     double *out_score, double *out_d_p, double *out_d_i);
+/* Copy the last sodso_db_match result (fp32, m x n_local each; either may be NULL) out. */
+int sodso_db_get_distances(sodso_db *db, float *d_p, float *d_i);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SODSO_PR_H */

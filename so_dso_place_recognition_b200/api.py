@@ -1,0 +1,344 @@
+"""Host-side mirror of the reference interface for the descriptor hot path, over the C ABI.
+
+Names, argument meaning and results follow the reference:
+  SC / M2DP classes      <- place_recognition/generate_signatures/src/SC/SC.h:10-23, M2DP/M2DP.h:12-30
+  align_points_PCA       <- .../src/utils/pts_align.h:7-9
+  sc_generate / m2dp_generate (batch drivers) <- SC/test_sc.cpp:36-57, M2DP/test_m2dp.cpp:37-67
+  processSC / processM2DP <- place_recognition/match_signatures/processSC.m:1, processM2DP.m:1
+  run_test (lines 25-57 only: match, fuse, mask, argmin) <- match_signatures/run_test.m
+
+Arrays may be numpy arrays (host) or torch CUDA tensors (device; outputs are then torch CUDA
+tensors too).  Every call goes to libsodso_pr.so; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _native as N
+from ._native import SC_SIZE, M2DP_SIZE, SODSO_TYPE_SC, SODSO_TYPE_M2DP, SODSO_ALGO_TC, SODSO_ALGO_SIMT
+
+_ctx_lock = threading.Lock()
+_ctxs: dict[int, "Context"] = {}
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_torch(a):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+def _prep(a, dtype_np, dtype_name):
+    """contiguous array of the right dtype, numpy or torch-cuda"""
+    if a is None:
+        return None
+    if _is_torch(a):
+        import torch
+
+        dt = getattr(torch, dtype_name)
+        if a.dtype != dt:
+            a = a.to(dt)
+        return a.contiguous()
+    return np.ascontiguousarray(a, dtype=dtype_np)
+
+
+def _empty_like_kind(ref, shape, dtype_np, dtype_name):
+    if _is_torch(ref):
+        import torch
+
+        return torch.empty(shape, dtype=getattr(torch, dtype_name), device=ref.device)
+    return np.empty(shape, dtype=dtype_np)
+
+
+class Context:
+    """One per GPU (sodso_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        N.check(N.lib().sodso_ctx_create(int(device), C.byref(self._h)))
+        self.device = int(device)
+
+    def close(self):
+        if self._h:
+            N.lib().sodso_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_match_algo(self, algo: int):
+        N.check(N.lib().sodso_ctx_set_match_algo(self._h, int(algo)))
+
+    def set_stream(self, cuda_stream_ptr):
+        N.check(N.lib().sodso_ctx_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    @property
+    def stream(self):
+        return N.lib().sodso_ctx_stream(self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(N.lib().sodso_ctx_launch_count(self._h))
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return float(N.lib().sodso_ctx_last_kernel_ms(self._h))
+
+    @property
+    def last_kernel_name(self) -> str:
+        return N.lib().sodso_ctx_last_kernel_name(self._h).decode()
+
+
+def default_context(device: int | None = None) -> Context:
+    if device is None:
+        device = 0
+    with _ctx_lock:
+        c = _ctxs.get(device)
+        if c is None:
+            c = Context(device)
+            _ctxs[device] = c
+        return c
+
+
+def _ctx_for(*arrays, ctx=None):
+    if ctx is not None:
+        return ctx
+    for a in arrays:
+        if a is not None and _is_torch(a) and a.is_cuda:
+            return default_context(a.device.index or 0)
+    return default_context(0)
+
+
+# ----------------------------------------------------------------------------------------------
+# generation
+# ----------------------------------------------------------------------------------------------
+def align_points_PCA(xyz, off=None, want_evec=False, ctx=None):
+    """pts_align.h:7-46.  xyz: (n,3) [+ off for a batch].  -> aligned (n,3) [, evec (nscan,3,3)]"""
+    xyz = _prep(xyz, np.float64, "float64")
+    n = xyz.shape[0]
+    if off is None:
+        off = np.array([0, n], dtype=np.int64)
+    off = _prep(off, np.int64, "int64")
+    nscan = off.shape[0] - 1
+    c = _ctx_for(xyz, ctx=ctx)
+    out = _empty_like_kind(xyz, (n, 3), np.float64, "float64")
+    ev = _empty_like_kind(xyz, (nscan, 3, 3), np.float64, "float64") if want_evec else None
+    N.check(N.lib().sodso_align_pca(c.handle, _ptr(xyz), _ptr(off), nscan, _ptr(out), _ptr(ev)))
+    return (out, ev) if want_evec else out
+
+
+def sc_generate(xyz, inten, off, max_rho=45.0, ctx=None):
+    """test_sc.cpp:36-57: history_sc (nscan x 2400) = rows [structure(1200), intensity(1200)]."""
+    xyz = _prep(xyz, np.float64, "float64")
+    inten = _prep(inten, np.float32, "float32")
+    off = _prep(off, np.int64, "int64")
+    nscan = off.shape[0] - 1
+    c = _ctx_for(xyz, ctx=ctx)
+    hist = _empty_like_kind(xyz, (nscan, 2 * SC_SIZE), np.float64, "float64")
+    N.check(N.lib().sodso_sc_generate(c.handle, _ptr(xyz), _ptr(inten), _ptr(off), nscan, float(max_rho), _ptr(hist)))
+    return hist
+
+
+def m2dp_generate(xyz, inten, off, max_rho=45.0, ctx=None):
+    """test_m2dp.cpp:37-67: history_m2dp (4*nscan x 384)."""
+    xyz = _prep(xyz, np.float64, "float64")
+    inten = _prep(inten, np.float32, "float32")
+    off = _prep(off, np.int64, "int64")
+    nscan = off.shape[0] - 1
+    c = _ctx_for(xyz, ctx=ctx)
+    hist = _empty_like_kind(xyz, (4 * nscan, 2 * M2DP_SIZE), np.float64, "float64")
+    N.check(N.lib().sodso_m2dp_generate(c.handle, _ptr(xyz), _ptr(inten), _ptr(off), nscan, float(max_rho), _ptr(hist)))
+    return hist
+
+
+class SC:
+    """SC.h:10-23.  getSignature takes the points of ONE scan (n x 3 doubles, n floats)."""
+
+    def __init__(self, max_rho: float, ctx=None):
+        self.max_rho = float(max_rho)
+        self._ctx = ctx
+
+    def getSignatureSize(self) -> int:
+        return int(N.lib().sodso_sc_signature_size())
+
+    def getSignature(self, pts, inten):
+        pts = _prep(pts, np.float64, "float64")
+        n = pts.shape[0]
+        h = sc_generate(pts, inten, np.array([0, n], dtype=np.int64), self.max_rho, ctx=self._ctx)
+        return h[0, :SC_SIZE], h[0, SC_SIZE:]
+
+
+class M2DP:
+    """M2DP.h:12-30.  getSignature expects ALREADY aligned (+ sign-flipped) points, like the class."""
+
+    def __init__(self, max_rho: float, ctx=None):
+        self.max_rho = float(max_rho)
+        self._ctx = ctx
+
+    def getSignatureSize(self) -> int:
+        return int(N.lib().sodso_m2dp_signature_size())
+
+    def getSignature(self, pts_aligned, inten):
+        pts = _prep(pts_aligned, np.float64, "float64")
+        inten = _prep(inten, np.float32, "float32")
+        n = pts.shape[0]
+        off = np.array([0, n], dtype=np.int64)
+        c = _ctx_for(pts, ctx=self._ctx)
+        sig = _empty_like_kind(pts, (1, 2 * M2DP_SIZE), np.float64, "float64")
+        N.check(N.lib().sodso_m2dp_signature(c.handle, _ptr(pts), _ptr(inten), _ptr(off), 1, self.max_rho, _ptr(sig)))
+        return sig[0, :M2DP_SIZE], sig[0, M2DP_SIZE:]
+
+
+# ----------------------------------------------------------------------------------------------
+# matching
+# ----------------------------------------------------------------------------------------------
+def _match(fn64, fn32, hist1, hist2, rows_per_sig, f32, ctx):
+    hist1 = _prep(hist1, np.float64, "float64")
+    hist2 = _prep(hist2, np.float64, "float64")
+    m, n = hist1.shape[0] // rows_per_sig, hist2.shape[0] // rows_per_sig
+    c = _ctx_for(hist1, hist2, ctx=ctx)
+    ref = hist1 if _is_torch(hist1) else hist2
+    if f32:
+        dp = _empty_like_kind(ref, (m, n), np.float32, "float32")
+        di = _empty_like_kind(ref, (m, n), np.float32, "float32")
+        N.check(fn32(c.handle, _ptr(hist1), m, _ptr(hist2), n, _ptr(dp), _ptr(di)))
+    else:
+        dp = _empty_like_kind(ref, (m, n), np.float64, "float64")
+        di = _empty_like_kind(ref, (m, n), np.float64, "float64")
+        N.check(fn64(c.handle, _ptr(hist1), m, _ptr(hist2), n, _ptr(dp), _ptr(di)))
+    return dp, di
+
+
+def processSC(hist1, hist2, f32=False, ctx=None):
+    """[diff_m_p, diff_m_i] = processSC(hist1, hist2)  (processSC.m:1-45)."""
+    L = N.lib()
+    return _match(L.sodso_sc_match, L.sodso_sc_match_f32, hist1, hist2, 1, f32, ctx)
+
+
+def processM2DP(hist1, hist2, f32=False, ctx=None):
+    """[diff_m_p, diff_m_i] = processM2DP(hist1, hist2)  (processM2DP.m:1-22)."""
+    L = N.lib()
+    return _match(L.sodso_m2dp_match, L.sodso_m2dp_match_f32, hist1, hist2, 4, f32, ctx)
+
+
+def fuse_top1(d_p, d_i, mask_width, p_weight=2.0, ctx=None):
+    """run_test.m:38-57 on given matrices -> (idx 0-based int32[m], score[m])."""
+    d_p = _prep(d_p, np.float64, "float64")
+    d_i = _prep(d_i, np.float64, "float64")
+    m, n = d_p.shape
+    c = _ctx_for(d_p, d_i, ctx=ctx)
+    idx = _empty_like_kind(d_p, (m,), np.int32, "int32")
+    score = _empty_like_kind(d_p, (m,), np.float64, "float64")
+    N.check(N.lib().sodso_fuse_top1(c.handle, _ptr(d_p), _ptr(d_i), m, n, int(mask_width), float(p_weight),
+                                    _ptr(idx), _ptr(score)))
+    return idx, score
+
+
+def run_test(type, hist1, hist2, mask_width, p_weight=2.0, want_channels=False, ctx=None):
+    """The timed + decision part of run_test(type, hist1, hist2, gt1, gt2, loop_diff, mask_width)
+    (run_test.m:25-57): -> (diff_idx 0-based int32[m], diff_v[m] [, d_p_at, d_i_at])."""
+    t = {"sc": SODSO_TYPE_SC, "m2dp": SODSO_TYPE_M2DP}[type]
+    rows = 1 if t == SODSO_TYPE_SC else 4
+    hist1 = _prep(hist1, np.float64, "float64")
+    hist2 = _prep(hist2, np.float64, "float64")
+    m, n = hist1.shape[0] // rows, hist2.shape[0] // rows
+    c = _ctx_for(hist1, hist2, ctx=ctx)
+    ref = hist1 if _is_torch(hist1) else hist2
+    idx = _empty_like_kind(ref, (m,), np.int32, "int32")
+    score = _empty_like_kind(ref, (m,), np.float64, "float64")
+    dpa = _empty_like_kind(ref, (m,), np.float64, "float64") if want_channels else None
+    dia = _empty_like_kind(ref, (m,), np.float64, "float64") if want_channels else None
+    N.check(N.lib().sodso_loop_top1(c.handle, t, _ptr(hist1), m, _ptr(hist2), n, int(mask_width), float(p_weight),
+                                    _ptr(idx), _ptr(score), _ptr(dpa), _ptr(dia)))
+    return (idx, score, dpa, dia) if want_channels else (idx, score)
+
+
+# ----------------------------------------------------------------------------------------------
+# resident, row-sharded database
+# ----------------------------------------------------------------------------------------------
+class SignatureDB:
+    """A shard of the signature database resident in HBM (sodso_db)."""
+
+    def __init__(self, type, hist2, global_row0=0, ctx=None):
+        self.type = {"sc": SODSO_TYPE_SC, "m2dp": SODSO_TYPE_M2DP}[type]
+        rows = 1 if self.type == SODSO_TYPE_SC else 4
+        hist2 = _prep(hist2, np.float64, "float64")
+        self.n = hist2.shape[0] // rows
+        self.row0 = int(global_row0)
+        self.ctx = _ctx_for(hist2, ctx=ctx)
+        self._h = C.c_void_p()
+        self._rows = rows
+        self.m = 0
+        N.check(N.lib().sodso_db_create(self.ctx.handle, self.type, _ptr(hist2), self.n, self.row0, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            N.lib().sodso_db_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def match(self, hist1):
+        hist1 = _prep(hist1, np.float64, "float64")
+        self.m = hist1.shape[0] // self._rows
+        self._ref = hist1
+        N.check(N.lib().sodso_db_match(self._h, _ptr(hist1), self.m))
+
+    def partial_stats(self, like=None):
+        ref = like if like is not None else self._ref
+        st = _empty_like_kind(ref, (self.m, 4), np.float64, "float64")
+        N.check(N.lib().sodso_db_partial_stats(self._h, _ptr(st)))
+        return st
+
+    def topk(self, global_stats, n_global, q_global_row0, mask_width, p_weight=2.0, k=8):
+        gs = _prep(global_stats, np.float64, "float64")
+        idx = _empty_like_kind(gs, (self.m, k), np.int64, "int64")
+        score = _empty_like_kind(gs, (self.m, k), np.float64, "float64")
+        dp = _empty_like_kind(gs, (self.m, k), np.float64, "float64")
+        di = _empty_like_kind(gs, (self.m, k), np.float64, "float64")
+        N.check(N.lib().sodso_db_topk(self._h, _ptr(gs), int(n_global), int(q_global_row0), int(mask_width),
+                                      float(p_weight), int(k), _ptr(idx), _ptr(score), _ptr(dp), _ptr(di)))
+        return idx, score, dp, di
+
+    def distances(self, like=None):
+        """fp32 (m x n_local) copies of the last match result (numpy, or torch if `like` is a CUDA tensor)."""
+        ref = like if like is not None else np.empty(0)
+        dp = _empty_like_kind(ref, (self.m, self.n), np.float32, "float32")
+        di = _empty_like_kind(ref, (self.m, self.n), np.float32, "float32")
+        N.check(N.lib().sodso_db_get_distances(self._h, _ptr(dp), _ptr(di)))
+        return dp, di
+
+
+def topk_merge(idx, score, d_p, d_i):
+    """Merge gathered per-shard top-k lists (R x m x k numpy arrays) -> (m x k) each."""
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    score = np.ascontiguousarray(score, dtype=np.float64)
+    d_p = np.ascontiguousarray(d_p, dtype=np.float64)
+    d_i = np.ascontiguousarray(d_i, dtype=np.float64)
+    R, m, k = idx.shape
+    oi = np.empty((m, k), dtype=np.int64)
+    os_ = np.empty((m, k))
+    op = np.empty((m, k))
+    od = np.empty((m, k))
+    N.check(N.lib().sodso_topk_merge(_ptr(idx), _ptr(score), _ptr(d_p), _ptr(d_i), R, m, k, _ptr(oi), _ptr(os_),
+                                     _ptr(op), _ptr(od)))
+    return oi, os_, op, od

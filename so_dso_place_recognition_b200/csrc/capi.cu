@@ -1,0 +1,741 @@
+// extern "C" surface of libsodso_pr.so (include/sodso_pr.h): context, host<->HBM staging,
+// call sequencing.  All compute is in the kernel translation units; there is no CPU path.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sodso_pr.h"
+#include "common.cuh"
+
+namespace sodso {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+
+struct Buf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+static bool is_device_ptr(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace sodso
+
+using namespace sodso;
+
+struct sodso_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  int algo = SODSO_ALGO_TC;
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  std::string kname;
+  // workspaces
+  Buf in_xyz, in_inten, in_off, out_hist, out_xyz, out_evec;
+  Buf h1, h2, q_op, db_op, dp32, di32, dp64, di64;
+  Buf stats, idx64, idx32, score, dpat, diat, gen_ws, m2dp_ws;
+};
+
+struct sodso_db {
+  sodso_ctx *ctx = nullptr;
+  int type = 0;
+  int n = 0;
+  int64_t row0 = 0;
+  Buf op;        // SC: MMA operand (TC) or normalised K-major fp32 (SIMT); M2DP: raw fp64 rows
+  int op_algo = 0;
+  Buf q_in, q_op, dp, di, stats, gstats, idx, score, dpat, diat, ws;
+  int m = 0;     // rows of the last match
+  bool matched = false;
+};
+
+namespace {
+
+#define CTX_CHECK(ctx)                                   \
+  if (!(ctx)) {                                          \
+    set_error("null context");                           \
+    return SODSO_E_ARG;                                  \
+  }                                                      \
+  SODSO_CUDA_CHECK(cudaSetDevice((ctx)->device))
+
+// host-or-device input -> device pointer (copies through `ws` if host)
+template <class T>
+int stage_in(sodso_ctx *c, const T *src, size_t count, Buf &ws, const T **out) {
+  if (count == 0 || is_device_ptr(src)) {
+    *out = src;
+    return SODSO_OK;
+  }
+  SODSO_CUDA_CHECK(ws.reserve(count * sizeof(T)));
+  SODSO_CUDA_CHECK(cudaMemcpyAsync(ws.p, src, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  *out = ws.as<T>();
+  return SODSO_OK;
+}
+
+// host-or-device output -> device pointer to write to
+template <class T>
+int stage_out(sodso_ctx *c, T *dst, size_t count, Buf &ws, T **out) {
+  if (!dst) {
+    *out = nullptr;
+    return SODSO_OK;
+  }
+  if (is_device_ptr(dst)) {
+    *out = dst;
+    return SODSO_OK;
+  }
+  SODSO_CUDA_CHECK(ws.reserve(count * sizeof(T) + 16));
+  *out = ws.as<T>();
+  return SODSO_OK;
+}
+
+template <class T>
+int finish_out(sodso_ctx *c, T *dst, size_t count, const T *dev) {
+  if (!dst || dst == dev) return SODSO_OK;
+  SODSO_CUDA_CHECK(cudaMemcpyAsync(dst, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+  return SODSO_OK;
+}
+
+int sync_ctx(sodso_ctx *c) {
+  SODSO_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return SODSO_OK;
+}
+
+struct TimedRegion {
+  sodso_ctx *c;
+  TimedRegion(sodso_ctx *ctx, const char *name) : c(ctx) {
+    c->kname = name;
+    c->ev_valid = cudaEventRecord(c->ev0, c->stream) == cudaSuccess;
+  }
+  ~TimedRegion() {
+    if (c->ev_valid) c->ev_valid = cudaEventRecord(c->ev1, c->stream) == cudaSuccess;
+  }
+};
+
+int check_offsets_host(const int64_t *off, int nscan, int64_t *total) {
+  // off may be host or device; fetch the last element
+  int64_t last = 0, first = 0;
+  if (is_device_ptr(off)) {
+    SODSO_CUDA_CHECK(cudaMemcpy(&last, off + nscan, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    SODSO_CUDA_CHECK(cudaMemcpy(&first, off, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  } else {
+    last = off[nscan];
+    first = off[0];
+    for (int s = 0; s < nscan; s++)
+      if (off[s + 1] < off[s] || off[s + 1] - off[s] > INT32_MAX) {
+        set_error("scan_off must be non-decreasing with < 2^31 points per scan");
+        return SODSO_E_ARG;
+      }
+  }
+  if (first != 0 || last < 0) {
+    set_error("scan_off[0] must be 0");
+    return SODSO_E_ARG;
+  }
+  *total = last;
+  return SODSO_OK;
+}
+
+// SC operands for `rows` signatures in the format of the selected algorithm
+int sc_prepare(sodso_ctx *c, int algo, const double *hist_dev, int rows, Buf &op, bool is_db) {
+  if (algo == SODSO_ALGO_SIMT) {
+    int ld = (rows + 31) & ~31;
+    SODSO_CUDA_CHECK(op.reserve((size_t)2 * SC_SIZE * ld * sizeof(float)));
+    SODSO_CUDA_CHECK(launch_sc_prep_simt(hist_dev, rows, op.as<float>(), ld, c->stream, &c->launches));
+  } else {
+    size_t bytes = is_db ? sc_tc_db_bytes(rows) : sc_tc_query_bytes(rows);
+    SODSO_CUDA_CHECK(op.reserve(bytes));
+    if (is_db)
+      SODSO_CUDA_CHECK(launch_sc_tc_prep_db(hist_dev, rows, op.p, c->stream, &c->launches));
+    else
+      SODSO_CUDA_CHECK(launch_sc_tc_prep_query(hist_dev, rows, op.p, c->stream, &c->launches));
+  }
+  return SODSO_OK;
+}
+
+int sc_match_core(sodso_ctx *c, int algo, const Buf &q_op, int m, const Buf &db_op, int n, float *dp,
+                  float *di, int ldd) {
+  TimedRegion tr(c, algo == SODSO_ALGO_SIMT ? "sc_match_simt_kernel" : "sc_match_tc_kernel");
+  if (algo == SODSO_ALGO_SIMT) {
+    int ldq = (m + 31) & ~31, ldh = (n + 31) & ~31;
+    SODSO_CUDA_CHECK(launch_sc_match_simt(q_op.as<float>(), m, ldq, db_op.as<float>(), n, ldh, dp, di,
+                                          ldd, c->stream, &c->launches));
+  } else {
+    SODSO_CUDA_CHECK(launch_sc_match_tc(q_op.p, m, db_op.p, n, dp, di, ldd, c->num_sms, c->stream,
+                                        &c->launches));
+  }
+  return SODSO_OK;
+}
+
+// distances (fp32, device, ld = n) of hist1 vs hist2 for either descriptor type
+int match_to_device(sodso_ctx *c, int type, const double *hist1, int m, const double *hist2, int n,
+                    float *dp, float *di) {
+  const size_t w = type == SODSO_TYPE_SC ? 2 * SC_SIZE : 2 * M2DP_SIG;
+  const size_t r1 = type == SODSO_TYPE_SC ? m : 4 * (size_t)m, r2 = type == SODSO_TYPE_SC ? n : 4 * (size_t)n;
+  const double *h1d, *h2d;
+  int rc;
+  if ((rc = stage_in(c, hist1, r1 * w, c->h1, &h1d))) return rc;
+  if ((rc = stage_in(c, hist2, r2 * w, c->h2, &h2d))) return rc;
+  if (type == SODSO_TYPE_SC) {
+    if ((rc = sc_prepare(c, c->algo, h2d, n, c->db_op, true))) return rc;
+    if ((rc = sc_prepare(c, c->algo, h1d, m, c->q_op, false))) return rc;
+    return sc_match_core(c, c->algo, c->q_op, m, c->db_op, n, dp, di, n);
+  }
+  SODSO_CUDA_CHECK(c->m2dp_ws.reserve(m2dp_match_workspace_bytes(m, n)));
+  TimedRegion tr(c, "m2dp_match_kernel");
+  SODSO_CUDA_CHECK(launch_m2dp_match(h1d, m, h2d, n, dp, di, n, c->m2dp_ws.p, c->stream, &c->launches));
+  return SODSO_OK;
+}
+
+template <class T>
+int match_api(sodso_ctx *c, int type, const double *hist1, int m, const double *hist2, int n, T *d_p,
+              T *d_i) {
+  CTX_CHECK(c);
+  if (m < 0 || n < 0 || (m > 0 && !hist1) || (n > 0 && !hist2)) {
+    set_error("bad match arguments");
+    return SODSO_E_ARG;
+  }
+  if (m == 0 || n == 0) return SODSO_OK;
+  const size_t cnt = (size_t)m * n;
+  int rc;
+  float *dp32, *di32;
+  constexpr bool is_f32 = sizeof(T) == 4;
+  const bool direct_p = is_f32 && is_device_ptr(d_p), direct_i = is_f32 && is_device_ptr(d_i);
+  if (direct_p)
+    dp32 = reinterpret_cast<float *>(d_p);
+  else {
+    SODSO_CUDA_CHECK(c->dp32.reserve(cnt * 4));
+    dp32 = c->dp32.as<float>();
+  }
+  if (direct_i)
+    di32 = reinterpret_cast<float *>(d_i);
+  else {
+    SODSO_CUDA_CHECK(c->di32.reserve(cnt * 4));
+    di32 = c->di32.as<float>();
+  }
+  if ((rc = match_to_device(c, type, hist1, m, hist2, n, dp32, di32))) return rc;
+  if constexpr (is_f32) {
+    if (d_p && !direct_p && (rc = finish_out(c, reinterpret_cast<float *>(d_p), cnt, dp32))) return rc;
+    if (d_i && !direct_i && (rc = finish_out(c, reinterpret_cast<float *>(d_i), cnt, di32))) return rc;
+  } else {
+    double *o;
+    if (d_p) {
+      if ((rc = stage_out(c, reinterpret_cast<double *>(d_p), cnt, c->dp64, &o))) return rc;
+      SODSO_CUDA_CHECK(launch_f32_to_f64(dp32, m, n, n, o, c->stream, &c->launches));
+      if ((rc = finish_out(c, reinterpret_cast<double *>(d_p), cnt, o))) return rc;
+    }
+    if (d_i) {
+      if ((rc = stage_out(c, reinterpret_cast<double *>(d_i), cnt, c->di64, &o))) return rc;
+      SODSO_CUDA_CHECK(launch_f32_to_f64(di32, m, n, n, o, c->stream, &c->launches));
+      if ((rc = finish_out(c, reinterpret_cast<double *>(d_i), cnt, o))) return rc;
+    }
+  }
+  return sync_ctx(c);
+}
+
+int generate_common(sodso_ctx *c, const double *xyz, const float *inten, const int64_t *off, int nscan,
+                    const double **xd, const float **id, const int64_t **od) {
+  if (nscan < 0 || !off || (nscan > 0 && !xyz)) {
+    set_error("bad generate arguments");
+    return SODSO_E_ARG;
+  }
+  int64_t total = 0;
+  int rc;
+  if ((rc = check_offsets_host(off, nscan, &total))) return rc;
+  if ((rc = stage_in(c, xyz, (size_t)total * 3, c->in_xyz, xd))) return rc;
+  if (inten && (rc = stage_in(c, inten, (size_t)total, c->in_inten, id))) return rc;
+  if ((rc = stage_in(c, off, (size_t)nscan + 1, c->in_off, od))) return rc;
+  return SODSO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *sodso_last_error(void) { return g_err.c_str(); }
+const char *sodso_version(void) { return "sodso_pr 0.1 (sm_100a)"; }
+int sodso_sc_signature_size(void) { return SC_SIZE; }
+int sodso_m2dp_signature_size(void) { return M2DP_SIG; }
+
+int sodso_ctx_create(int device, sodso_ctx **out) {
+  if (!out) {
+    set_error("out is null");
+    return SODSO_E_ARG;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    set_error(std::string("no CUDA device: ") + cudaGetErrorString(e) +
+              " — libsodso_pr has no CPU fallback");
+    return SODSO_E_NODEV;
+  }
+  if (device < 0 || device >= ndev) {
+    set_error("device index out of range");
+    return SODSO_E_ARG;
+  }
+  cudaDeviceProp prop;
+  SODSO_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error(std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+              "; libsodso_pr is built for sm_100a only");
+    return SODSO_E_NODEV;
+  }
+  SODSO_CUDA_CHECK(cudaSetDevice(device));
+  sodso_ctx *c = new sodso_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  SODSO_CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  SODSO_CUDA_CHECK(cudaEventCreate(&c->ev0));
+  SODSO_CUDA_CHECK(cudaEventCreate(&c->ev1));
+  *out = c;
+  return SODSO_OK;
+}
+
+void sodso_ctx_destroy(sodso_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (Buf *b : {&c->in_xyz, &c->in_inten, &c->in_off, &c->out_hist, &c->out_xyz, &c->out_evec, &c->h1,
+                 &c->h2, &c->q_op, &c->db_op, &c->dp32, &c->di32, &c->dp64, &c->di64, &c->stats,
+                 &c->idx64, &c->idx32, &c->score, &c->dpat, &c->diat, &c->gen_ws, &c->m2dp_ws})
+    b->release();
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+void *sodso_ctx_stream(sodso_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int sodso_ctx_set_stream(sodso_ctx *c, void *s) {
+  if (!c) return SODSO_E_ARG;
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return SODSO_OK;
+}
+
+int sodso_ctx_set_match_algo(sodso_ctx *c, int algo) {
+  if (!c || (algo != SODSO_ALGO_TC && algo != SODSO_ALGO_SIMT)) {
+    set_error("bad algo");
+    return SODSO_E_ARG;
+  }
+  c->algo = algo;
+  return SODSO_OK;
+}
+
+int64_t sodso_ctx_launch_count(sodso_ctx *c) { return c ? c->launches : 0; }
+
+double sodso_ctx_last_kernel_ms(sodso_ctx *c) {
+  if (!c || !c->ev_valid) return -1.0;
+  cudaSetDevice(c->device);
+  if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+const char *sodso_ctx_last_kernel_name(sodso_ctx *c) { return c ? c->kname.c_str() : ""; }
+
+int sodso_align_pca(sodso_ctx *c, const double *xyz, const int64_t *off, int nscan, double *out_xyz,
+                    double *evec) {
+  CTX_CHECK(c);
+  const double *xd;
+  const float *id = nullptr;
+  const int64_t *od;
+  int rc;
+  if ((rc = generate_common(c, xyz, nullptr, off, nscan, &xd, &id, &od))) return rc;
+  if (nscan == 0) return SODSO_OK;
+  int64_t total = 0;
+  if ((rc = check_offsets_host(off, nscan, &total))) return rc;
+  double *o, *ev;
+  if ((rc = stage_out(c, out_xyz, (size_t)total * 3, c->out_xyz, &o))) return rc;
+  if ((rc = stage_out(c, evec, (size_t)nscan * 9, c->out_evec, &ev))) return rc;
+  if (!o) {
+    set_error("out_xyz is null");
+    return SODSO_E_ARG;
+  }
+  {
+    TimedRegion tr(c, "align_pca_kernel");
+    SODSO_CUDA_CHECK(launch_align_pca(xd, od, nscan, o, ev, c->num_sms, c->stream, &c->launches));
+  }
+  if ((rc = finish_out(c, out_xyz, (size_t)total * 3, o))) return rc;
+  if ((rc = finish_out(c, evec, (size_t)nscan * 9, ev))) return rc;
+  return sync_ctx(c);
+}
+
+int sodso_sc_generate(sodso_ctx *c, const double *xyz, const float *inten, const int64_t *off,
+                      int nscan, double max_rho, double *hist) {
+  CTX_CHECK(c);
+  const double *xd;
+  const float *id = nullptr;
+  const int64_t *od;
+  int rc;
+  if (nscan > 0 && (!inten || !hist)) {
+    set_error("inten / hist is null");
+    return SODSO_E_ARG;
+  }
+  if ((rc = generate_common(c, xyz, inten, off, nscan, &xd, &id, &od))) return rc;
+  if (nscan == 0) return SODSO_OK;
+  double *h;
+  const size_t cnt = (size_t)nscan * 2 * SC_SIZE;
+  if ((rc = stage_out(c, hist, cnt, c->out_hist, &h))) return rc;
+  {
+    TimedRegion tr(c, "sc_generate_kernel");
+    SODSO_CUDA_CHECK(launch_sc_generate(xd, id, od, nscan, max_rho, h, c->num_sms, c->stream, &c->launches));
+  }
+  if ((rc = finish_out(c, hist, cnt, h))) return rc;
+  return sync_ctx(c);
+}
+
+static int m2dp_generate_impl(sodso_ctx *c, const double *xyz, const float *inten, const int64_t *off,
+                              int nscan, double max_rho, double *hist, bool variants) {
+  CTX_CHECK(c);
+  const double *xd;
+  const float *id = nullptr;
+  const int64_t *od;
+  int rc;
+  if (nscan > 0 && (!inten || !hist)) {
+    set_error("inten / hist is null");
+    return SODSO_E_ARG;
+  }
+  if ((rc = generate_common(c, xyz, inten, off, nscan, &xd, &id, &od))) return rc;
+  if (nscan == 0) return SODSO_OK;
+  double *h;
+  const size_t cnt = (size_t)nscan * (variants ? 4 : 1) * 2 * M2DP_SIG;
+  if ((rc = stage_out(c, hist, cnt, c->out_hist, &h))) return rc;
+  const size_t wsb = m2dp_generate_workspace_bytes(nscan, variants);
+  SODSO_CUDA_CHECK(c->gen_ws.reserve(wsb));
+  {
+    TimedRegion tr(c, "m2dp_hist_kernel");
+    SODSO_CUDA_CHECK(launch_m2dp_generate(xd, id, od, nscan, max_rho, variants, h, c->gen_ws.p, wsb,
+                                          c->num_sms, c->stream, &c->launches));
+  }
+  if ((rc = finish_out(c, hist, cnt, h))) return rc;
+  return sync_ctx(c);
+}
+
+int sodso_m2dp_generate(sodso_ctx *c, const double *xyz, const float *inten, const int64_t *off,
+                        int nscan, double max_rho, double *hist) {
+  return m2dp_generate_impl(c, xyz, inten, off, nscan, max_rho, hist, true);
+}
+
+int sodso_m2dp_signature(sodso_ctx *c, const double *xyz, const float *inten, const int64_t *off,
+                         int nscan, double max_rho, double *sig) {
+  return m2dp_generate_impl(c, xyz, inten, off, nscan, max_rho, sig, false);
+}
+
+int sodso_sc_match(sodso_ctx *c, const double *h1, int m, const double *h2, int n, double *d_p,
+                   double *d_i) {
+  return match_api<double>(c, SODSO_TYPE_SC, h1, m, h2, n, d_p, d_i);
+}
+int sodso_sc_match_f32(sodso_ctx *c, const double *h1, int m, const double *h2, int n, float *d_p,
+                       float *d_i) {
+  return match_api<float>(c, SODSO_TYPE_SC, h1, m, h2, n, d_p, d_i);
+}
+int sodso_m2dp_match(sodso_ctx *c, const double *h1, int m, const double *h2, int n, double *d_p,
+                     double *d_i) {
+  return match_api<double>(c, SODSO_TYPE_M2DP, h1, m, h2, n, d_p, d_i);
+}
+int sodso_m2dp_match_f32(sodso_ctx *c, const double *h1, int m, const double *h2, int n, float *d_p,
+                         float *d_i) {
+  return match_api<float>(c, SODSO_TYPE_M2DP, h1, m, h2, n, d_p, d_i);
+}
+
+int sodso_fuse_top1(sodso_ctx *c, const double *d_p, const double *d_i, int m, int n, int mask_width,
+                    double p_weight, int32_t *idx, double *score) {
+  CTX_CHECK(c);
+  if (m < 0 || n <= 0 || !d_p || !d_i || !idx || !score) {
+    set_error("bad fuse_top1 arguments");
+    return SODSO_E_ARG;
+  }
+  if (m == 0) return SODSO_OK;
+  const double *pd, *qd;
+  int rc;
+  const size_t cnt = (size_t)m * n;
+  if ((rc = stage_in(c, d_p, cnt, c->dp64, &pd))) return rc;
+  if ((rc = stage_in(c, d_i, cnt, c->di64, &qd))) return rc;
+  int32_t *id;
+  double *sd;
+  if ((rc = stage_out(c, idx, (size_t)m, c->idx32, &id))) return rc;
+  if ((rc = stage_out(c, score, (size_t)m, c->score, &sd))) return rc;
+  {
+    TimedRegion tr(c, "fuse_top1_f64_kernel");
+    SODSO_CUDA_CHECK(launch_fuse_top1_f64(pd, qd, m, n, mask_width, p_weight, id, sd, c->stream, &c->launches));
+  }
+  if ((rc = finish_out(c, idx, (size_t)m, id))) return rc;
+  if ((rc = finish_out(c, score, (size_t)m, sd))) return rc;
+  return sync_ctx(c);
+}
+
+int sodso_loop_top1(sodso_ctx *c, int type, const double *hist1, int m, const double *hist2, int n,
+                    int mask_width, double p_weight, int32_t *idx, double *score, double *d_p_at,
+                    double *d_i_at) {
+  CTX_CHECK(c);
+  if ((type != SODSO_TYPE_SC && type != SODSO_TYPE_M2DP) || m < 0 || n <= 0 || !hist1 || !hist2 || !idx ||
+      !score) {
+    set_error("bad loop_top1 arguments");
+    return SODSO_E_ARG;
+  }
+  if (m == 0) return SODSO_OK;
+  const size_t cnt = (size_t)m * n;
+  int rc;
+  SODSO_CUDA_CHECK(c->dp32.reserve(cnt * 4));
+  SODSO_CUDA_CHECK(c->di32.reserve(cnt * 4));
+  if ((rc = match_to_device(c, type, hist1, m, hist2, n, c->dp32.as<float>(), c->di32.as<float>()))) return rc;
+  SODSO_CUDA_CHECK(c->stats.reserve((size_t)m * 4 * sizeof(double)));
+  SODSO_CUDA_CHECK(launch_row_stats(c->dp32.as<float>(), c->di32.as<float>(), m, n, n, c->stats.as<double>(),
+                                    c->stream, &c->launches));
+  SODSO_CUDA_CHECK(c->idx64.reserve((size_t)m * sizeof(int64_t)));
+  double *sd, *pa, *ia;
+  if ((rc = stage_out(c, score, (size_t)m, c->score, &sd))) return rc;
+  if ((rc = stage_out(c, d_p_at, (size_t)m, c->dpat, &pa))) return rc;
+  if ((rc = stage_out(c, d_i_at, (size_t)m, c->diat, &ia))) return rc;
+  SODSO_CUDA_CHECK(launch_fuse_topk(c->dp32.as<float>(), c->di32.as<float>(), m, n, n, c->stats.as<double>(), n,
+                                    0, 0, mask_width, p_weight, 1, c->idx64.as<int64_t>(), sd, pa, ia,
+                                    c->stream, &c->launches));
+  // idx: int64 (-1 = none) -> int32 0-based (MATLAB returns the first index for an all-NaN row)
+  std::vector<int64_t> tmp((size_t)m);
+  SODSO_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), c->idx64.p, (size_t)m * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                   c->stream));
+  if ((rc = finish_out(c, score, (size_t)m, sd))) return rc;
+  if ((rc = finish_out(c, d_p_at, (size_t)m, pa))) return rc;
+  if ((rc = finish_out(c, d_i_at, (size_t)m, ia))) return rc;
+  if ((rc = sync_ctx(c))) return rc;
+  std::vector<int32_t> t32((size_t)m);
+  for (int i = 0; i < m; i++) t32[i] = tmp[i] < 0 ? 0 : (int32_t)tmp[i];
+  if (is_device_ptr(idx))
+    SODSO_CUDA_CHECK(cudaMemcpy(idx, t32.data(), (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice));
+  else
+    std::memcpy(idx, t32.data(), (size_t)m * sizeof(int32_t));
+  return SODSO_OK;
+}
+
+// ---- resident row-sharded database ---------------------------------------------------------
+int sodso_db_create(sodso_ctx *c, int type, const double *hist2, int n_local, int64_t global_row0,
+                    sodso_db **out) {
+  CTX_CHECK(c);
+  if (!out || (type != SODSO_TYPE_SC && type != SODSO_TYPE_M2DP) || n_local <= 0 || !hist2) {
+    set_error("bad db_create arguments");
+    return SODSO_E_ARG;
+  }
+  *out = nullptr;
+  sodso_db *db = new sodso_db();
+  db->ctx = c;
+  db->type = type;
+  db->n = n_local;
+  db->row0 = global_row0;
+  db->op_algo = c->algo;
+  const size_t w = type == SODSO_TYPE_SC ? 2 * SC_SIZE : 2 * M2DP_SIG;
+  const size_t rows = type == SODSO_TYPE_SC ? n_local : 4 * (size_t)n_local;
+  const double *hd;
+  int rc = stage_in(c, hist2, rows * w, c->h2, &hd);
+  if (!rc) {
+    if (type == SODSO_TYPE_SC)
+      rc = sc_prepare(c, db->op_algo, hd, n_local, db->op, true);
+    else {
+      cudaError_t e = db->op.reserve(rows * w * sizeof(double));
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(db->op.p, hd, rows * w * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+      if (e != cudaSuccess) {
+        set_error(std::string("db_create: ") + cudaGetErrorString(e));
+        rc = SODSO_E_CUDA;
+      }
+    }
+  }
+  if (!rc) rc = sync_ctx(c);
+  if (rc) {
+    sodso_db_destroy(db);
+    return rc;
+  }
+  *out = db;
+  return SODSO_OK;
+}
+
+void sodso_db_destroy(sodso_db *db) {
+  if (!db) return;
+  cudaSetDevice(db->ctx->device);
+  cudaStreamSynchronize(db->ctx->stream);
+  for (Buf *b : {&db->op, &db->q_in, &db->q_op, &db->dp, &db->di, &db->stats, &db->gstats, &db->idx,
+                 &db->score, &db->dpat, &db->diat, &db->ws})
+    b->release();
+  delete db;
+}
+
+int sodso_db_size(sodso_db *db) { return db ? db->n : 0; }
+
+int sodso_db_match(sodso_db *db, const double *hist1, int m) {
+  if (!db) {
+    set_error("null db");
+    return SODSO_E_ARG;
+  }
+  sodso_ctx *c = db->ctx;
+  CTX_CHECK(c);
+  if (m <= 0 || !hist1) {
+    set_error("bad db_match arguments");
+    return SODSO_E_ARG;
+  }
+  db->matched = false;
+  const size_t w = db->type == SODSO_TYPE_SC ? 2 * SC_SIZE : 2 * M2DP_SIG;
+  const size_t rows = db->type == SODSO_TYPE_SC ? m : 4 * (size_t)m;
+  const double *hd;
+  int rc;
+  if ((rc = stage_in(c, hist1, rows * w, db->q_in, &hd))) return rc;
+  const size_t cnt = (size_t)m * db->n;
+  SODSO_CUDA_CHECK(db->dp.reserve(cnt * 4));
+  SODSO_CUDA_CHECK(db->di.reserve(cnt * 4));
+  if (db->type == SODSO_TYPE_SC) {
+    if ((rc = sc_prepare(c, db->op_algo, hd, m, db->q_op, false))) return rc;
+    if ((rc = sc_match_core(c, db->op_algo, db->q_op, m, db->op, db->n, db->dp.as<float>(), db->di.as<float>(),
+                            db->n)))
+      return rc;
+  } else {
+    SODSO_CUDA_CHECK(db->ws.reserve(m2dp_match_workspace_bytes(m, db->n)));
+    TimedRegion tr(c, "m2dp_match_kernel");
+    SODSO_CUDA_CHECK(launch_m2dp_match(hd, m, db->op.as<double>(), db->n, db->dp.as<float>(),
+                                       db->di.as<float>(), db->n, db->ws.p, c->stream, &c->launches));
+  }
+  db->m = m;
+  db->matched = true;
+  return SODSO_OK;
+}
+
+int sodso_db_partial_stats(sodso_db *db, double *stats) {
+  if (!db || !stats) {
+    set_error("bad db_partial_stats arguments");
+    return SODSO_E_ARG;
+  }
+  sodso_ctx *c = db->ctx;
+  CTX_CHECK(c);
+  if (!db->matched) {
+    set_error("db_partial_stats before db_match");
+    return SODSO_E_STATE;
+  }
+  double *sd;
+  int rc;
+  const size_t cnt = (size_t)db->m * 4;
+  if ((rc = stage_out(c, stats, cnt, db->stats, &sd))) return rc;
+  SODSO_CUDA_CHECK(launch_row_stats(db->dp.as<float>(), db->di.as<float>(), db->m, db->n, db->n, sd, c->stream,
+                                    &c->launches));
+  if ((rc = finish_out(c, stats, cnt, sd))) return rc;
+  return sync_ctx(c);
+}
+
+int sodso_db_topk(sodso_db *db, const double *global_stats, int64_t n_global, int64_t q_global_row0,
+                  int mask_width, double p_weight, int k, int64_t *idx, double *score, double *d_p,
+                  double *d_i) {
+  if (!db || !global_stats || !idx || !score || k <= 0 || n_global < db->n) {
+    set_error("bad db_topk arguments");
+    return SODSO_E_ARG;
+  }
+  sodso_ctx *c = db->ctx;
+  CTX_CHECK(c);
+  if (!db->matched) {
+    set_error("db_topk before db_match");
+    return SODSO_E_STATE;
+  }
+  const double *gs;
+  int rc;
+  const size_t cnt = (size_t)db->m * k;
+  if ((rc = stage_in(c, global_stats, (size_t)db->m * 4, db->gstats, &gs))) return rc;
+  int64_t *id;
+  double *sd, *pa, *ia;
+  if ((rc = stage_out(c, idx, cnt, db->idx, &id))) return rc;
+  if ((rc = stage_out(c, score, cnt, db->score, &sd))) return rc;
+  if ((rc = stage_out(c, d_p, cnt, db->dpat, &pa))) return rc;
+  if ((rc = stage_out(c, d_i, cnt, db->diat, &ia))) return rc;
+  SODSO_CUDA_CHECK(launch_fuse_topk(db->dp.as<float>(), db->di.as<float>(), db->m, db->n, db->n, gs, n_global,
+                                    q_global_row0, db->row0, mask_width, p_weight, k, id, sd, pa, ia,
+                                    c->stream, &c->launches));
+  if ((rc = finish_out(c, idx, cnt, id))) return rc;
+  if ((rc = finish_out(c, score, cnt, sd))) return rc;
+  if ((rc = finish_out(c, d_p, cnt, pa))) return rc;
+  if ((rc = finish_out(c, d_i, cnt, ia))) return rc;
+  return sync_ctx(c);
+}
+
+int sodso_topk_merge(const int64_t *idx, const double *score, const double *d_p, const double *d_i,
+                     int nshards, int m, int k, int64_t *out_idx, double *out_score, double *out_d_p,
+                     double *out_d_i) {
+  if (!idx || !score || !out_idx || !out_score || nshards <= 0 || m < 0 || k <= 0) {
+    set_error("bad topk_merge arguments");
+    return SODSO_E_ARG;
+  }
+  std::vector<int> cur((size_t)nshards);
+  for (int q = 0; q < m; q++) {
+    std::fill(cur.begin(), cur.end(), 0);
+    for (int r = 0; r < k; r++) {
+      int best = -1;
+      size_t bo = 0;
+      for (int s = 0; s < nshards; s++) {
+        if (cur[s] >= k) continue;
+        size_t o = ((size_t)s * m + q) * k + cur[s];
+        if (idx[o] < 0) continue;
+        if (best < 0 || score[o] < score[bo] || (score[o] == score[bo] && idx[o] < idx[bo])) {
+          best = s;
+          bo = o;
+        }
+      }
+      size_t oo = (size_t)q * k + r;
+      if (best < 0) {
+        out_idx[oo] = -1;
+        out_score[oo] = NAN;
+        if (out_d_p) out_d_p[oo] = NAN;
+        if (out_d_i) out_d_i[oo] = NAN;
+      } else {
+        out_idx[oo] = idx[bo];
+        out_score[oo] = score[bo];
+        if (out_d_p) out_d_p[oo] = d_p ? d_p[bo] : NAN;
+        if (out_d_i) out_d_i[oo] = d_i ? d_i[bo] : NAN;
+        cur[best]++;
+      }
+    }
+  }
+  return SODSO_OK;
+}
+
+int sodso_db_get_distances(sodso_db *db, float *d_p, float *d_i) {
+  if (!db) {
+    set_error("null db");
+    return SODSO_E_ARG;
+  }
+  sodso_ctx *c = db->ctx;
+  CTX_CHECK(c);
+  if (!db->matched) {
+    set_error("db_get_distances before db_match");
+    return SODSO_E_STATE;
+  }
+  const size_t bytes = (size_t)db->m * db->n * sizeof(float);
+  if (d_p) SODSO_CUDA_CHECK(cudaMemcpyAsync(d_p, db->dp.p, bytes, cudaMemcpyDefault, c->stream));
+  if (d_i) SODSO_CUDA_CHECK(cudaMemcpyAsync(d_i, db->di.p, bytes, cudaMemcpyDefault, c->stream));
+  return sync_ctx(c);
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+// Shared declarations of libsodso_pr (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace sodso {
+
+constexpr int SC_NUM_S = 60;   // SC.h:7
+constexpr int SC_NUM_R = 20;   // SC.h:8
+constexpr int SC_SIZE = SC_NUM_S * SC_NUM_R;
+constexpr int M2DP_NUM_S = 16; // M2DP.h:7 (theta)
+constexpr int M2DP_NUM_R = 8;  // M2DP.h:8 (rho)
+constexpr int M2DP_NUM_P = 4;  // M2DP.h:9
+constexpr int M2DP_NUM_Q = 16; // M2DP.h:10
+constexpr int M2DP_PQ = M2DP_NUM_P * M2DP_NUM_Q;  // 64
+constexpr int M2DP_SR = M2DP_NUM_S * M2DP_NUM_R;  // 128
+constexpr int M2DP_SIG = M2DP_PQ + M2DP_SR;       // 192
+
+constexpr double STAT_SHIFT = 0.25;  // centre of the [0, 0.5] distance range, see sodso_db_partial_stats
+
+void set_error(const std::string &msg);
+
+struct KernelTimer;  // capi.cu
+
+#define SODSO_CUDA_CHECK(expr)                                                              \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      ::sodso::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +        \
+                         __FILE__ + ":" + std::to_string(__LINE__) + ")");                  \
+      return SODSO_E_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+// ---- launchers implemented in the kernel translation units ----------------------------
+// Each returns a cudaError_t from the launch (cudaGetLastError) and counts into *launches.
+
+// sc_generate.cu
+cudaError_t launch_sc_generate(const double *xyz, const float *inten, const int64_t *off, int nscan,
+                               double max_rho, double *hist, int num_sms, cudaStream_t st,
+                               int64_t *launches);
+cudaError_t launch_align_pca(const double *xyz, const int64_t *off, int nscan, double *out_xyz,
+                             double *evec, int num_sms, cudaStream_t st, int64_t *launches);
+
+// m2dp_generate.cu
+cudaError_t launch_m2dp_generate(const double *xyz, const float *inten, const int64_t *off, int nscan,
+                                 double max_rho, bool do_align_and_variants, double *hist,
+                                 void *workspace, size_t workspace_bytes, int num_sms,
+                                 cudaStream_t st, int64_t *launches);
+size_t m2dp_generate_workspace_bytes(int nscan, bool variants);
+
+// sc_match_simt.cu : fp32 CUDA-core cross-check path
+// prep: hist (rows x 2400 fp64) -> per channel, row-normalised fp32, K-major [ch][1200][ld]
+cudaError_t launch_sc_prep_simt(const double *hist, int rows, float *out_t, int ld, cudaStream_t st,
+                                int64_t *launches);
+cudaError_t launch_sc_match_simt(const float *q_t, int m, int ldq, const float *h_t, int n, int ldh,
+                                 float *d_p, float *d_i, int ldd, cudaStream_t st, int64_t *launches);
+
+// sc_match_tc.cu : tcgen05 path
+struct ScTcDb;     // resident DB operand (device)
+struct ScTcQuery;  // query operand (device)
+size_t sc_tc_db_bytes(int n);
+size_t sc_tc_query_bytes(int m);
+cudaError_t launch_sc_tc_prep_db(const double *hist, int n, void *db_buf, cudaStream_t st,
+                                 int64_t *launches);
+cudaError_t launch_sc_tc_prep_query(const double *hist, int m, void *q_buf, cudaStream_t st,
+                                    int64_t *launches);
+// d_p / d_i: fp32 m x ldd.  Returns cudaErrorNotSupported if tensor maps cannot be encoded.
+cudaError_t launch_sc_match_tc(const void *q_buf, int m, const void *db_buf, int n, float *d_p,
+                               float *d_i, int ldd, int num_sms, cudaStream_t st, int64_t *launches);
+
+// m2dp_match.cu
+cudaError_t launch_m2dp_match(const double *hist1, int m, const double *hist2, int n, float *d_p,
+                              float *d_i, int ldd, void *workspace, cudaStream_t st,
+                              int64_t *launches);
+size_t m2dp_match_workspace_bytes(int m, int n);
+
+// fuse_topk.cu
+cudaError_t launch_row_stats(const float *d_p, const float *d_i, int m, int n, int ldd, double *stats,
+                             cudaStream_t st, int64_t *launches);
+cudaError_t launch_fuse_topk(const float *d_p, const float *d_i, int m, int n, int ldd,
+                             const double *global_stats, int64_t n_global, int64_t q_row0,
+                             int64_t db_row0, int mask_width, double p_weight, int k, int64_t *idx,
+                             double *score, double *dp_at, double *di_at, cudaStream_t st,
+                             int64_t *launches);
+// fp64 variants for sodso_fuse_top1 (inputs are caller-supplied fp64 matrices; exact two-pass
+// statistics like run_test.m:40)
+cudaError_t launch_fuse_top1_f64(const double *d_p, const double *d_i, int m, int n, int mask_width,
+                                 double p_weight, int32_t *idx, double *score, cudaStream_t st,
+                                 int64_t *launches);
+cudaError_t launch_f32_to_f64(const float *src, int rows, int cols, int ld, double *dst,
+                              cudaStream_t st, int64_t *launches);
+
+}  // namespace sodso

@@ -1,0 +1,263 @@
+// Channel fusion + decision, run_test.m:38-57: row z-score of both distance matrices (std with
+// N-1 over the UNMASKED row), fused = p_weight * z_p + z_i, temporal mask |i-j| < mask_width ->
+// Inf, first-index argmin (generalised to the k best for the row-sharded database).
+// One CTA per query row; all statistics in fp64 with a fixed reduction tree.
+#include <cmath>
+
+#include "../../include/sodso_pr.h"
+#include "common.cuh"
+
+namespace sodso {
+namespace {
+
+constexpr int FUSE_THREADS = 256;
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int NV>
+__device__ __forceinline__ void block_sum_d(double (&v)[NV], double *scratch /* NV*32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    double s = warp_sum_d(v[k]);
+    if (lane == 0) scratch[k * 32 + warp] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      double s = lane < nwarp ? scratch[k * 32 + lane] : 0.0;
+      s = warp_sum_d(s);
+      if (lane == 0) scratch[k * 32] = s;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; k++) v[k] = scratch[k * 32];
+  __syncthreads();
+}
+
+// (score, idx) lexicographic "less" with NaN never winning; idx < 0 means "none".
+__device__ __forceinline__ bool cand_less(double sa, long long ia, double sb, long long ib) {
+  if (ia < 0) return false;
+  if (ib < 0) return true;
+  return sa < sb || (sa == sb && ia < ib);
+}
+
+__device__ __forceinline__ void block_argmin(double &s, long long &i, double *ss, long long *si) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double s2 = __shfl_down_sync(0xffffffffu, s, o);
+    long long i2 = __shfl_down_sync(0xffffffffu, i, o);
+    if (cand_less(s2, i2, s, i)) {
+      s = s2;
+      i = i2;
+    }
+  }
+  if (lane == 0) {
+    ss[warp] = s;
+    si[warp] = i;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    s = lane < nwarp ? ss[lane] : 0.0;
+    i = lane < nwarp ? si[lane] : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double s2 = __shfl_down_sync(0xffffffffu, s, o);
+      long long i2 = __shfl_down_sync(0xffffffffu, i, o);
+      if (cand_less(s2, i2, s, i)) {
+        s = s2;
+        i = i2;
+      }
+    }
+    if (lane == 0) {
+      ss[0] = s;
+      si[0] = i;
+    }
+  }
+  __syncthreads();
+  s = ss[0];
+  i = si[0];
+  __syncthreads();
+}
+
+// stats[row] = [sum(dp-c), sum((dp-c)^2), sum(di-c), sum((di-c)^2)], c = STAT_SHIFT
+__global__ void __launch_bounds__(FUSE_THREADS)
+row_stats_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, int n, int ldd,
+                 double *__restrict__ stats) {
+  __shared__ double scratch[4 * 32];
+  const int row = blockIdx.x;
+  const float *p = d_p + (size_t)row * ldd, *q = d_i + (size_t)row * ldd;
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
+    double a = (double)p[j] - STAT_SHIFT, b = (double)q[j] - STAT_SHIFT;
+    v[0] += a;
+    v[1] += a * a;
+    v[2] += b;
+    v[3] += b * b;
+  }
+  block_sum_d<4>(v, scratch);
+  if (threadIdx.x < 4) stats[(size_t)row * 4 + threadIdx.x] = v[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(FUSE_THREADS)
+fuse_topk_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, int n, int ldd,
+                 const double *__restrict__ gstats, long long n_global, long long q_row0,
+                 long long db_row0, int mask_width, double p_weight, int k, int64_t *__restrict__ idx,
+                 double *__restrict__ score, double *__restrict__ dp_at, double *__restrict__ di_at) {
+  __shared__ double ss[32];
+  __shared__ long long si[32];
+  const int row = blockIdx.x;
+  const float *p = d_p + (size_t)row * ldd, *q = d_i + (size_t)row * ldd;
+  const double *st = gstats + (size_t)row * 4;
+  const double N = (double)n_global;
+  const double mu_p = STAT_SHIFT + st[0] / N, mu_i = STAT_SHIFT + st[2] / N;
+  const double sd_p = sqrt((st[1] - st[0] * st[0] / N) / (N - 1.0));
+  const double sd_i = sqrt((st[3] - st[2] * st[2] / N) / (N - 1.0));
+  const long long qg = q_row0 + row;
+  double last_s = 0.0;
+  long long last_i = -1;  // nothing selected yet
+  for (int r = 0; r < k; r++) {
+    double bs = 0.0;
+    long long bi = -1;
+    for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
+      const long long jg = db_row0 + j;
+      double f = p_weight * (((double)p[j] - mu_p) / sd_p) + ((double)q[j] - mu_i) / sd_i;
+      long long dist = qg - jg;
+      if (dist < 0) dist = -dist;
+      if (dist < (long long)mask_width) f = INFINITY;  // run_test.m:47-53
+      if (f != f) continue;                              // min skips NaN (run_test.m:57)
+      if (last_i >= 0 && !cand_less(last_s, last_i, f, jg)) continue;  // already emitted
+      if (cand_less(f, jg, bs, bi)) {
+        bs = f;
+        bi = jg;
+      }
+    }
+    block_argmin(bs, bi, ss, si);
+    if (threadIdx.x == 0) {
+      const size_t o = (size_t)row * k + r;
+      idx[o] = bi;
+      score[o] = bi >= 0 ? bs : NAN;
+      if (dp_at) dp_at[o] = bi >= 0 ? (double)p[bi - db_row0] : NAN;
+      if (di_at) di_at[o] = bi >= 0 ? (double)q[bi - db_row0] : NAN;
+    }
+    if (bi < 0) {  // exhausted: fill the rest
+      if (threadIdx.x == 0)
+        for (int r2 = r + 1; r2 < k; r2++) {
+          const size_t o = (size_t)row * k + r2;
+          idx[o] = -1;
+          score[o] = NAN;
+          if (dp_at) dp_at[o] = NAN;
+          if (di_at) di_at[o] = NAN;
+        }
+      break;
+    }
+    last_s = bs;
+    last_i = bi;
+  }
+}
+
+// run_test.m:38-57 on caller-supplied fp64 matrices, two-pass statistics like MATLAB normalize.
+__global__ void __launch_bounds__(FUSE_THREADS)
+fuse_top1_f64_kernel(const double *__restrict__ d_p, const double *__restrict__ d_i, int n,
+                     int mask_width, double p_weight, int32_t *__restrict__ idx,
+                     double *__restrict__ score) {
+  __shared__ double scratch[2 * 32];
+  __shared__ double ss[32];
+  __shared__ long long si[32];
+  const int row = blockIdx.x;
+  const double *p = d_p + (size_t)row * n, *q = d_i + (size_t)row * n;
+  double s[2] = {0.0, 0.0};
+  for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
+    s[0] += p[j];
+    s[1] += q[j];
+  }
+  block_sum_d<2>(s, scratch);
+  const double mu_p = s[0] / n, mu_i = s[1] / n;
+  double v[2] = {0.0, 0.0};
+  for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
+    double a = p[j] - mu_p, b = q[j] - mu_i;
+    v[0] += a * a;
+    v[1] += b * b;
+  }
+  block_sum_d<2>(v, scratch);
+  const double sd_p = sqrt(v[0] / (n - 1)), sd_i = sqrt(v[1] / (n - 1));
+  double bs = 0.0;
+  long long bi = -1;
+  for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
+    double f = p_weight * ((p[j] - mu_p) / sd_p) + (q[j] - mu_i) / sd_i;
+    int dist = row - j;
+    if (dist < 0) dist = -dist;
+    if (dist < mask_width) f = INFINITY;
+    if (f != f) continue;
+    if (cand_less(f, j, bs, bi)) {
+      bs = f;
+      bi = j;
+    }
+  }
+  block_argmin(bs, bi, ss, si);
+  if (threadIdx.x == 0) {
+    idx[row] = bi >= 0 ? (int32_t)bi : 0;  // MATLAB min of an all-NaN row returns index 1
+    score[row] = bi >= 0 ? bs : NAN;
+  }
+}
+
+__global__ void f32_to_f64_kernel(const float *__restrict__ src, int rows, int cols, int ld,
+                                  double *__restrict__ dst) {
+  const size_t total = (size_t)rows * cols;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total;
+       t += (size_t)gridDim.x * blockDim.x) {
+    size_t r = t / cols, c = t - r * cols;
+    dst[t] = (double)src[r * ld + c];
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_row_stats(const float *d_p, const float *d_i, int m, int n, int ldd, double *stats,
+                             cudaStream_t st, int64_t *launches) {
+  if (m <= 0) return cudaSuccess;
+  row_stats_kernel<<<m, FUSE_THREADS, 0, st>>>(d_p, d_i, n, ldd, stats);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fuse_topk(const float *d_p, const float *d_i, int m, int n, int ldd,
+                             const double *global_stats, int64_t n_global, int64_t q_row0,
+                             int64_t db_row0, int mask_width, double p_weight, int k, int64_t *idx,
+                             double *score, double *dp_at, double *di_at, cudaStream_t st,
+                             int64_t *launches) {
+  if (m <= 0) return cudaSuccess;
+  fuse_topk_kernel<<<m, FUSE_THREADS, 0, st>>>(d_p, d_i, n, ldd, global_stats, n_global, q_row0,
+                                               db_row0, mask_width, p_weight, k, idx, score, dp_at,
+                                               di_at);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fuse_top1_f64(const double *d_p, const double *d_i, int m, int n, int mask_width,
+                                 double p_weight, int32_t *idx, double *score, cudaStream_t st,
+                                 int64_t *launches) {
+  if (m <= 0) return cudaSuccess;
+  fuse_top1_f64_kernel<<<m, FUSE_THREADS, 0, st>>>(d_p, d_i, n, mask_width, p_weight, idx, score);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_f32_to_f64(const float *src, int rows, int cols, int ld, double *dst,
+                              cudaStream_t st, int64_t *launches) {
+  if (rows <= 0 || cols <= 0) return cudaSuccess;
+  size_t total = (size_t)rows * cols;
+  int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  f32_to_f64_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld, dst);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+}  // namespace sodso

@@ -1,0 +1,70 @@
+"""Generates the committed fixtures under tests/golden/ from the reference's own data files.
+
+Run HERE (the container that has /root/reference); the GPU box only sees the .npz outputs.
+
+  incoming_id_kat.npz   for each of the 13 sequences under place_recognition/results/: the pose
+                        ids + w2c translation columns parsed from poses_history_file.txt and the
+                        reference's own committed incoming_id_file.txt (an OUTPUT of pts_preprocess,
+                        pts_preprocess.h:181-182,215) -- the only golden vector the reference ships.
+  real_scans_seq06.npz  a few real SO-DSO scans of KITTI seq06 as staged by the oracle's restatement of
+                        pts_preprocess (grid filter for SC, polar filter for M2DP) and the ORACLE's
+                        signatures for them (parity unpinned: the reference ships no signatures).
+"""
+import glob
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+
+RES = "/root/reference/place_recognition/results"
+
+
+def main():
+    kat = {}
+    names = []
+    for d in sorted(glob.glob(RES + "/*/*/")):
+        name = "/".join(d.rstrip("/").split("/")[-2:])
+        poses = np.loadtxt(d + "poses_history_file.txt")
+        ids = np.loadtxt(d + "incoming_id_file.txt", dtype=np.int64)
+        key = name.replace("/", "__")
+        kat[key + "__pose_id"] = poses[:, 0].astype(np.int64)
+        kat[key + "__t"] = poses[:, [4, 8, 12]].astype(np.float64)
+        kat[key + "__ids"] = ids
+        names.append(name)
+        print(name, poses.shape[0], "poses ->", ids.shape[0], "ids")
+    kat["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "incoming_id_kat.npz"), **kat)
+
+    d = RES + "/KITTI/seq06/"
+    out = {}
+    pick = [0, 100, 400, 879]
+    for tag, polar in (("sc", False), ("m2dp", True)):
+        st = O.stage(d + "poses_history_file.txt", d + "pts_history_file.txt", 45.0, polar)
+        xs, its, off = [], [], [0]
+        for s in pick:
+            a, b = st["off"][s], st["off"][s + 1]
+            xs.append(st["xyz"][a:b])
+            its.append(st["inten"][a:b])
+            off.append(off[-1] + (b - a))
+        xyz = np.concatenate(xs)
+        inten = np.concatenate(its)
+        off = np.array(off, dtype=np.int64)
+        out[tag + "_xyz"] = xyz
+        out[tag + "_inten"] = inten
+        out[tag + "_off"] = off
+        if tag == "sc":
+            out["sc_hist"] = O.sc_generate(xyz, inten, off)
+        else:
+            out["m2dp_hist"] = O.m2dp_generate(xyz, inten, off)
+        print(tag, "scans", pick, "points", np.diff(off))
+    out["pick"] = np.array(pick)
+    np.savez_compressed(os.path.join(HERE, "real_scans_seq06.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()
