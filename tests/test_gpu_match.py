@@ -95,7 +95,10 @@ def test_fuse_top1_given_matrices(gpu_ctx, oracle):
             ridx, rsc = oracle.fuse_top1(dp, di, mw)
         np.testing.assert_array_equal(idx, ridx)
         np.testing.assert_allclose(sc, rsc, rtol=1e-10, equal_nan=True)
-    assert idx[3] == 0 and np.isnan(sc[3])          # NaN row: MATLAB min returns the first index
+        if mw == 0:                                     # NaN row: MATLAB min returns the first index
+            assert idx[3] == 0 and np.isnan(sc[3])
+        else:                                           # ... but the mask overwrites NaN with Inf (run_test.m:47-53)
+            assert idx[3] == 0 and np.isinf(sc[3])
 
 
 def test_tc_equals_simt_at_scale(gpu_ctx, oracle):
