@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Headline benchmark: query x DB pair-distances/s of the Scan Context hot path
+(generate_signatures + match_signatures + fusion/top-1) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W          (torchrun for N > 1)
+  python bench.py --impl reference ...                   (the CPU restatement on the host cores)
+
+Workload (BASELINE.json configs[2], `config.workload`): a 5 000-scan synthetic set (4 096 points per
+scan, planted loops), Scan Context signatures, all-pairs match over the 120 shift/reversal variants,
+two-channel z-score fusion, temporal mask 100, top-1 loop candidate.  One step = one pass of that
+hot path: sc_generate of the rank's scans -> match of all queries against the rank's DB shard ->
+row statistics -> (N > 1: all-reduce of the statistics, all-gather of the per-shard top-k) ->
+top-1.  For N > 1 the DB is row-sharded, 5 000 scans per GPU (weak scaling), the 5 000 queries
+are replicated.
+
+`value` is measured with the points resident in HBM; `e2e` with the points in pinned host memory,
+copied in every step, and the top-1 result copied out every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SCANS = 5000
+N_PTS = 4096
+MASK_WIDTH = 100          # test_kitti.m:19
+P_WEIGHT = 2.0            # run_test.m:39
+TOPK = 8
+FLOP_PER_PAIR = 576000    # 2 channels x 120 variants x 1200 x 2
+SC_BYTES_PER_SCAN = 133888
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained"), src="measured")
+    return dict(hbm=6650.0, tf=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.lines = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        load = [s for s in sm if s > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement timed the way the reference times itself
+# ---------------------------------------------------------------------------------------------------
+def cpu_sample(nq: int, hist_db: np.ndarray, xyz, inten, off, threads: int):
+    """One bounded sample of the hot path on the host: SC generation of nq scans (test_sc.cpp:40-57),
+    match of those nq queries against the whole DB (processSC.m:22-33, one BLAS dgemm per query like
+    MATLAB), fusion + top-1 (run_test.m:38-57).  -> seconds"""
+    from oracle import oracle as O
+
+    t0 = time.perf_counter()
+    sub_off = off[:nq + 1]
+    q = O.sc_generate(xyz[:sub_off[-1]], inten[:sub_off[-1]], sub_off, nthreads=threads)
+    dp, di = O.sc_match_numpy(q, hist_db)
+    O.fuse_top1_numpy(dp, di, MASK_WIDTH, P_WEIGHT)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from so_dso_place_recognition_b200 import synth
+
+    threads = os.cpu_count() or 1
+    nq = args.ref_queries
+    xyz, inten, off = synth.make_scan_set(N_SCANS, N_PTS, planted_loops=True)
+    hist = O.sc_generate(xyz, inten, off, nthreads=threads)     # DB signatures (untimed set-up)
+    for _ in range(args.warmup):
+        cpu_sample(nq, hist, xyz, inten, off, threads)
+    t = [cpu_sample(nq, hist, xyz, inten, off, threads) for _ in range(args.steps)]
+    dt = float(np.sum(t))
+    value = nq * N_SCANS * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "query x DB pair-distances/s (Scan Context generate+match+fuse)",
+        "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "5k-scan DB all-pairs ScanContext match, 4096 pts/scan (BASELINE configs[2])",
+                   "n_db": N_SCANS, "pts_per_scan": N_PTS, "mask_width": MASK_WIDTH,
+                   "sample": f"{nq} queries x {N_SCANS} DB per step"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
+                         "sample": f"{nq} queries (generated + matched + fused) x {N_SCANS} DB per step, "
+                                   f"numpy/OpenBLAS dgemm per query as MATLAB does, {threads} threads"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from so_dso_place_recognition_b200 import api, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = api.default_context(local_rank)
+    peaks = load_peaks()
+
+    # ---- synthetic scans: queries = set 0 (planted loops inside it); rank r's DB shard = set r
+    n_local = N_SCANS
+    xyz_q, inten_q, off_q = synth.make_scan_set(N_SCANS, N_PTS, planted_loops=True, first=0)
+    if rank == 0:
+        xyz_d, inten_d, off_d = xyz_q, inten_q, off_q
+    else:
+        xyz_d, inten_d, off_d = synth.make_scan_set(N_SCANS, N_PTS, planted_loops=False, first=1_000_000 * rank)
+    n_global = n_local * world
+    row0 = rank * n_local
+
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    h_xyz, h_inten, h_off = pin(xyz_d), pin(inten_d), pin(off_d)
+    d_xyz, d_inten, d_off = h_xyz.to(dev), h_inten.to(dev), h_off.to(dev)
+    if rank == 0:
+        hq_xyz, hq_inten, dq_xyz, dq_inten = h_xyz, h_inten, d_xyz, d_inten
+    else:
+        hq_xyz, hq_inten = pin(xyz_q), pin(inten_q)
+        dq_xyz, dq_inten = hq_xyz.to(dev), hq_inten.to(dev)
+    h2d_bytes = (h_xyz.numel() * 8 + h_inten.numel() * 4 + h_off.numel() * 8)
+    if rank != 0:
+        h2d_bytes *= 2
+
+    kern_ms = []
+
+    def step(host_inputs: bool):
+        """one pass of the hot path; returns (idx, score) of the top-1 on the host"""
+        if host_inputs:
+            # C-ABI call with HOST point buffers (copied in by the library), signatures stay in HBM
+            hist_db = torch.empty((n_local, 2400), dtype=torch.float64, device=dev)
+            api.N.check(api.N.lib().sodso_sc_generate(ctx.handle, h_xyz.data_ptr(), h_inten.data_ptr(),
+                                                      h_off.data_ptr(), n_local, 45.0, hist_db.data_ptr()))
+            if rank == 0:
+                hist_q = hist_db
+            else:
+                hist_q = torch.empty((N_SCANS, 2400), dtype=torch.float64, device=dev)
+                api.N.check(api.N.lib().sodso_sc_generate(ctx.handle, hq_xyz.data_ptr(), hq_inten.data_ptr(),
+                                                          h_off.data_ptr(), N_SCANS, 45.0, hist_q.data_ptr()))
+        else:
+            hist_db = api.sc_generate(d_xyz, d_inten, d_off)
+            hist_q = hist_db if rank == 0 else api.sc_generate(dq_xyz, dq_inten, d_off)
+        if world == 1:
+            idx, score = api.run_test("sc", hist_q, hist_db, MASK_WIDTH, P_WEIGHT)
+            kern_ms.append(ctx.last_kernel_ms)
+            return idx.cpu(), score.cpu()
+        db = api.SignatureDB("sc", hist_db, global_row0=row0, ctx=ctx)
+        db.match(hist_q)
+        kern_ms.append(ctx.last_kernel_ms)
+        stats = db.partial_stats(like=hist_q)
+        dist.all_reduce(stats)                                    # row sums over all shards (run_test.m:40)
+        idx, score, dp, di = db.topk(stats, n_global, 0, MASK_WIDTH, P_WEIGHT, TOPK)
+        pack = torch.stack([idx.double(), score, dp, di], dim=0).contiguous()   # 4 x m x k
+        gathered = torch.empty((world,) + tuple(pack.shape), dtype=pack.dtype, device=dev)
+        dist.all_gather_into_tensor(gathered, pack)               # per-shard top-k
+        g = gathered.cpu().numpy()
+        mi, ms, mp, md = api.topk_merge(g[:, 0].astype(np.int64), g[:, 1], g[:, 2], g[:, 3])
+        db.close()
+        return torch.from_numpy(mi[:, 0]), torch.from_numpy(ms[:, 0])
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(host_inputs: bool, steps: int):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st = torch.cuda.ExternalStream(ctx.stream or 0, device=dev) if ctx.stream else torch.cuda.current_stream()
+        t0 = time.perf_counter()
+        e0.record(st)
+        for _ in range(steps):
+            out = step(host_inputs)
+        e1.record(st)
+        sync_all()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        # the API is host-synchronous per call; events on the library stream bracket the same work
+        ms = max(ms, 0.0)
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), out
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    l0 = ctx.launch_count
+    kern_ms.clear()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms_dev, wall_dev, out = timed(False, args.steps)
+    launches = ctx.launch_count - l0
+    clk = clocks.stop() if rank == 0 else None
+    k_ms = float(np.mean(kern_ms))
+    for _ in range(2):
+        step(True)
+    ms_e2e, wall_e2e, out2 = timed(True, args.steps)
+
+    pairs_step = N_SCANS * n_global            # all ranks together
+    idx = out[0].numpy()
+    expect = (np.arange(N_SCANS) + N_SCANS // 2) % N_SCANS
+    agree = float((idx == expect).mean())
+    same_e2e = bool(np.array_equal(idx, out2[0].numpy()))
+
+    if rank == 0:
+        line = {
+            "metric": "query x DB pair-distances/s (Scan Context generate+match+fuse)",
+            "value": pairs_step * args.steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16x3-split (fp32 accumulate) match; f64 generation", "data": "synthetic",
+            "config": {"workload": "5k-scan DB all-pairs ScanContext match, 4096 pts/scan (BASELINE configs[2])",
+                       "n_queries": N_SCANS, "n_db_per_gpu": n_local, "n_db_total": n_global, "pts_per_scan": N_PTS,
+                       "variants_per_pair": 120, "mask_width": MASK_WIDTH, "topk": 1 if world == 1 else TOPK,
+                       "sharding": "DB rows" if world > 1 else "none",
+                       "l2": "operands per step (DB 77 MB + queries 328 MB + distances 200 MB) exceed the 126 MB L2",
+                       "planted_loop_top1_recovered": agree, "e2e_top1_identical": same_e2e},
+            "e2e": {"value": pairs_step * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s",
+                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(N_SCANS * 12),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "sc_match_tc_kernel",
+                         "achieved": N_SCANS * n_local * FLOP_PER_PAIR / (k_ms * 1e-3) / 1e12,
+                         "peak": peaks["tf"], "unit": "TFLOP/s",
+                         "frac": N_SCANS * n_local * FLOP_PER_PAIR / (k_ms * 1e-3) / 1e12 / peaks["tf"],
+                         "traffic": load_traffic(), "peak_source": peaks["src"] + " bf16 burst",
+                         "peak_sustained": peaks["tf_sus"],
+                         "frac_of_sustained": (N_SCANS * n_local * FLOP_PER_PAIR / (k_ms * 1e-3) / 1e12 / peaks["tf_sus"])
+                         if peaks["tf_sus"] else None,
+                         "kernel_ms": k_ms,
+                         "note": "algorithmic FLOP = 576 kFLOP/pair; the kernel executes 2x that in MMA work "
+                                 "(3-term fp16 split, 64/60 slot and 128/120 column padding)"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_traffic():
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("sc_match_tc_kernel_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def cpu_baseline(args):
+    from oracle import oracle as O
+    from so_dso_place_recognition_b200 import synth
+
+    threads = os.cpu_count() or 1
+    nq = args.ref_queries
+    xyz, inten, off = synth.make_scan_set(N_SCANS, N_PTS, planted_loops=True)
+    hist = O.sc_generate(xyz, inten, off, nthreads=threads)
+    cpu_sample(2, hist, xyz, inten, off, threads)
+    reps, t = 0, 0.0
+    while t < 10.0 and reps < 20:
+        t += cpu_sample(nq, hist, xyz, inten, off, threads)
+        reps += 1
+    return {"value": nq * N_SCANS * reps / t, "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": f"{reps} x ({nq} queries generated+matched+fused against the {N_SCANS}-scan DB), "
+                      f"oracle restatement, numpy/OpenBLAS dgemm per query as MATLAB does, {threads} threads"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-queries", type=int, default=32, help="queries per CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
