@@ -7,27 +7,31 @@
 //      corr_b[s] = sum_{c, r} b[(c + s) mod 60][r] * h[c][r],        b in {x, y}
 // i.e. a dense contraction  D[j, (b, s)] = sum_k A[j, k] * B[(b, s), k]  with
 //      A = DB signatures           (M side: 256 DB rows per CTA pair, TMA-fed, SWIZZLE_128B)
-//      B = Hankel matrix of shifts (N side: 64 shift rows per base vector, never materialised)
+//      B = Hankel matrix of shifts (N side, never materialised)
 //
-// The Hankel operand.  B[(b,s)][c, r] = b[(c+s) mod 60][r] is a *view* of the doubled vector
-// [b, b]: in the canonical K-major no-swizzle UMMA layout ((8,n),2):((16 B, SBO), LBO) rows
-// inside an 8-row core matrix are 16 B apart; choosing SBO = 128 B and LBO = 16 B makes
-// address(row s, k-group g) = base + 16 (s + g): row s reads the 16-byte unit s + g.  With a
-// K ordering in which one 16-byte unit = 8 slots of ONE sector, the shift by one sector is a
-// shift by one unit, so all 64 shift rows of a K-step are overlapping windows of one 2 KB
-// buffer.  The x rows live in CTA 0 of the pair and the y rows in CTA 1 (cta_group::2,
-// M = 256, N = 128: each CTA contributes N/2 = 64 rows of B), so one query costs 16 KB of
-// shared memory per CTA and channel instead of a 120 x 1200 expanded tile per K-block.
+// The Hankel operand.  K is ordered so that one 16-byte "unit" holds slots of ONE sector, and a
+// base vector is stored doubled ([b, b], unit u = sector u mod 60).  In the canonical K-major
+// no-swizzle UMMA layout ((8,n),2):((16 B, SBO), LBO) rows inside an 8-row core matrix are 16 B
+// apart, so a descriptor with SBO = 128 B reads row r at unit (base + r): overlapping windows of one
+// small buffer ARE the shifted copies.  Two queries are interleaved unit-wise (Z[2u + b] = q_b[u]);
+// with LBO = 32 B, row r = 2 s + b then is shift s of query b, and one N = 256 MMA of a CTA pair
+// (cta_group::2, M = 256; CTA 0 supplies the 128 x-rows, CTA 1 the 128 y-rows of B) produces all
+// 120 (+8 duplicate) variants of two queries against 256 DB rows.  A query costs 16 KB (fp16) or
+// 4 KB (fp8) of shared memory per CTA instead of a 120 x 1200 expanded tile per K-block.
 //
-// Precision (target |d - d_ref| <= 1e-5 against the fp64 reference).  Values are row-normalised
-// in fp64 (processSC.m:15-20), scaled by 64 and split v = hi + lo into two fp16; the product is
-// evaluated as hi*lo + lo*hi + hi*hi (lo*lo ~ 2^-22 dropped) with fp32 accumulation in TMEM.
-// The three terms are interleaved per sector into 64 fp16 "slots" (20 + 20 + 20 + 4 pad), the
-// cross terms first so that the large hi*hi partial sums come last (accumulation error).
+// Two arithmetic modes, chosen per channel on the device:
+//  * generic (any real values): rows are normalised in fp64 (processSC.m:15-20), scaled by 64 and
+//    split v = hi + lo into two fp16; the product is evaluated as hi*lo + lo*hi + hi*hi (lo*lo ~
+//    2^-22 dropped) with fp32 accumulation in TMEM.  The three terms are interleaved per sector
+//    into 64 fp16 slots (20 + 20 + 20 + 4 pad), cross terms first so that the large hi*hi partial
+//    sums come last.  |d - d_ref| ~ 1e-6 (measured), bar 1e-5.
+//  * binary (every value 0 or 1 on both sides -- the intensity channel, SC.cpp:67-72): the raw bits
+//    go in as fp8 e4m3 (kind::f8f6f4), TMEM accumulates exact integer overlap counts, and the
+//    epilogue applies 1/(|q| |h|).  4x fewer MMAs, exact up to the final fp32 rounding.
 //
 // Roles per CTA (256 threads): warp 0 TMA producer (DB tiles), warp 1 MMA issuer (leader CTA),
 // warp 2 TMEM allocator, warp 3 query-operand loader, warps 4-7 epilogue (tcgen05.ld -> max over
-// the 128 shift columns -> (1 - x)/2 -> coalesced fp32 stores).
+// the shift columns -> (1 - x)/2 -> coalesced fp32 stores).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -39,23 +43,24 @@
 namespace sodso {
 namespace {
 
-constexpr int KS_CHUNKS = 8;                         // 16-byte units per sector
-constexpr int KS_SLOTS = KS_CHUNKS * 8;              // 64 fp16 slots per sector
-constexpr int K_TOTAL = KS_SLOTS * SC_NUM_S;         // 3840
-constexpr int K_BLOCK = 64;                          // fp16 elements per TMA box row (128 B)
-constexpr int NUM_KB = K_TOTAL / K_BLOCK;            // 60
-constexpr int CHUNK_K = 8 * SC_NUM_S;                // 480 K elements per chunk
-constexpr int Q_UNITS = 128;                         // 16-byte units per (query, base, chunk): doubled vector
-constexpr int Q_BASE_BYTES = KS_CHUNKS * Q_UNITS * 16;  // 16 KB per (query, base, channel)
-constexpr int QG = 4;                                // queries per tile (4 x 128 TMEM columns)
+constexpr int UNITS_PER_CHUNK = SC_NUM_S;            // 60 units (16 B) of K per chunk
+constexpr int F16_CHUNKS = 8;                        // 64 fp16 slots per sector
+constexpr int F8_CHUNKS = 2;                         // 32 fp8 slots per sector
+constexpr int K_F16 = F16_CHUNKS * UNITS_PER_CHUNK * 8;    // 3840 elements
+constexpr int K_F8 = F8_CHUNKS * UNITS_PER_CHUNK * 16;     // 1920 elements (bytes)
+constexpr int KB_UNITS = 8;                          // units per K-block (128 B TMA box row)
+constexpr int Q_UNITS = 256;                         // units per (query pair, base, chunk): 2 x doubled vector
+constexpr int CHUNK_BYTES = Q_UNITS * 16;            // 4 KB
+constexpr int QG = 4;                                // queries per tile = 2 interleaved pairs
 constexpr int TILE_M = 256, CTA_M = 128;             // DB rows per CTA pair / per CTA
-constexpr int N_PER_Q = 128;                         // accumulator columns per query: 64 x-shifts + 64 y-shifts
-constexpr int A_STAGE_BYTES = CTA_M * K_BLOCK * 2;   // 16 KB
-constexpr int NSTAGE = 7;
-constexpr int B_BYTES = QG * Q_BASE_BYTES;           // 64 KB
-constexpr float VAL_SCALE = 64.0f;                   // operand scale
+constexpr int N_MMA = 256;                           // accumulator columns per query pair
+constexpr int A_STAGE_BYTES = CTA_M * 128;           // 16 KB
+constexpr int NSTAGE = 8;
+constexpr int B_BYTES = 2 * F16_CHUNKS * CHUNK_BYTES;   // 64 KB (two pairs, generic mode)
+constexpr float VAL_SCALE = 64.0f;                   // operand scale (generic mode)
 constexpr float ACC_SCALE = 1.0f / (VAL_SCALE * VAL_SCALE);
 constexpr int TC_THREADS = 256;
+constexpr int HEADER_BYTES = 256;
 
 struct __align__(8) TcBarriers {
   uint64_t full[NSTAGE], empty[NSTAGE];
@@ -65,6 +70,32 @@ struct __align__(8) TcBarriers {
 };
 constexpr int SMEM_BYTES = 1024 /*align*/ + NSTAGE * A_STAGE_BYTES + B_BYTES + (int)sizeof(TcBarriers);
 
+inline int pad_to(int v, int a) { return (v + a - 1) / a * a; }
+
+// Operand buffers in HBM.  header: int nonbinary[2] (per channel: some value is not 0/1).
+struct DbLayout {
+  size_t off_f16, off_f8, off_norm, total;
+  int n_pad;
+  explicit DbLayout(int n) {
+    n_pad = pad_to(n, TILE_M);
+    off_f16 = HEADER_BYTES;                                      // [ch][n_pad][3840] fp16
+    off_f8 = off_f16 + (size_t)2 * n_pad * K_F16 * 2;            // [ch][n_pad][1920] e4m3
+    off_norm = off_f8 + (size_t)2 * n_pad * K_F8;                // [ch][n_pad] float 1/|h|
+    total = off_norm + (size_t)2 * n_pad * 4;
+  }
+};
+struct QLayout {
+  size_t off_f16, off_f8, off_norm, total;
+  int m_pad;
+  explicit QLayout(int m) {
+    m_pad = pad_to(m, QG);
+    off_f16 = HEADER_BYTES;                                      // [ch][base][m_pad/2][8][256][16 B]
+    off_f8 = off_f16 + (size_t)2 * 2 * (m_pad / 2) * F16_CHUNKS * CHUNK_BYTES;
+    off_norm = off_f8 + (size_t)2 * 2 * (m_pad / 2) * F8_CHUNKS * CHUNK_BYTES;   // [ch][m_pad] float
+    total = off_norm + (size_t)2 * m_pad * 4;
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // operand preparation
 // ---------------------------------------------------------------------------------------------
@@ -73,96 +104,120 @@ __device__ __forceinline__ void split_fp16(double v, __half &hi, __half &lo) {
   lo = __float2half_rn((float)(v - (double)__half2float(hi)));
 }
 
-__device__ __forceinline__ void row_norms(const double *h, double nrm[2], double *red) {
+// per-row preparation shared by both operands: norms, fp16 split, binary test
+struct RowPrep {
+  __half hi[2][SC_SIZE], lo[2][SC_SIZE];
+  unsigned char bits[2][SC_SIZE];   // e4m3 encoding of the raw value when it is 0 or 1
+  double red[64];
+  int nonbin[2];
+  float inv_norm[2];
+};
+
+__device__ inline void prep_row(const double *h, bool valid, RowPrep &S) {
+  if (threadIdx.x < 2) S.nonbin[threadIdx.x] = 0;
   double ss[2] = {0.0, 0.0};
-  for (int ch = 0; ch < 2; ch++)
-    for (int k = threadIdx.x; k < SC_SIZE; k += blockDim.x) {
-      double v = h[ch * SC_SIZE + k];
-      ss[ch] += v * v;
-    }
+  int nb[2] = {0, 0};
+  if (valid)
+    for (int ch = 0; ch < 2; ch++)
+      for (int k = threadIdx.x; k < SC_SIZE; k += blockDim.x) {
+        double v = h[ch * SC_SIZE + k];
+        ss[ch] += v * v;
+        if (v != 0.0 && v != 1.0) nb[ch] = 1;
+      }
   for (int ch = 0; ch < 2; ch++) {
     double s = ss[ch];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) red[ch * 32 + (threadIdx.x >> 5)] = s;
+    if ((threadIdx.x & 31) == 0) S.red[ch * 32 + (threadIdx.x >> 5)] = s;
   }
   __syncthreads();
+  for (int ch = 0; ch < 2; ch++)
+    if (nb[ch]) atomicOr(&S.nonbin[ch], 1);
+  double nrm[2];
   for (int ch = 0; ch < 2; ch++) {
     double s = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[ch * 32 + w];
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += S.red[ch * 32 + w];
     nrm[ch] = sqrt(s);  // processSC.m:16,19
   }
-}
-
-// A operand: [ch][n_pad][3840] fp16.  k = chunk*480 + sector*8 + t, slot = chunk*8 + t:
-//   slots  0..19: hi[r]   (pairs with the query's lo)
-//   slots 20..39: lo[r]   (pairs with the query's hi)
-//   slots 40..59: hi[r]   (pairs with the query's hi)
-//   slots 60..63: 0
-__global__ void __launch_bounds__(256)
-sc_tc_prep_db_kernel(const double *__restrict__ hist, int n, int n_pad, __half *__restrict__ out) {
-  __shared__ double red[64];
-  __shared__ __half s_hi[2][SC_SIZE], s_lo[2][SC_SIZE];
-  const int row = blockIdx.x;
-  if (row < n) {
-    const double *h = hist + (size_t)row * 2 * SC_SIZE;
-    double nrm[2];
-    row_norms(h, nrm, red);
-    for (int ch = 0; ch < 2; ch++)
-      for (int k = threadIdx.x; k < SC_SIZE; k += blockDim.x)
-        split_fp16(h[ch * SC_SIZE + k] / nrm[ch] * (double)VAL_SCALE, s_hi[ch][k], s_lo[ch][k]);
-  } else {
-    for (int ch = 0; ch < 2; ch++)
-      for (int k = threadIdx.x; k < SC_SIZE; k += blockDim.x) s_hi[ch][k] = s_lo[ch][k] = __float2half(0.0f);
-  }
-  __syncthreads();
-  for (int ch = 0; ch < 2; ch++) {
-    __half *o = out + ((size_t)ch * n_pad + row) * K_TOTAL;
-    for (int k = threadIdx.x; k < K_TOTAL; k += blockDim.x) {
-      const int j = k / CHUNK_K, rem = k - j * CHUNK_K, c = rem >> 3, t = rem & 7, s = j * 8 + t;
-      __half v = __float2half(0.0f);
-      if (s < 20) v = s_hi[ch][c * SC_NUM_R + s];
-      else if (s < 40) v = s_lo[ch][c * SC_NUM_R + s - 20];
-      else if (s < 60) v = s_hi[ch][c * SC_NUM_R + s - 40];
-      o[k] = v;
-    }
-  }
-}
-
-// B operand: [ch][base][m_pad][chunk 8][unit 128][8] fp16; unit u holds sector u % 60 of the base
-// vector (x: the query image, y: its sector reversal y[c] = x[(60 - c) % 60]).
-//   slots  0..19: lo[r],  slots 20..39: hi[r],  slots 40..59: hi[r],  slots 60..63: 0
-__global__ void __launch_bounds__(256)
-sc_tc_prep_query_kernel(const double *__restrict__ hist, int m, int m_pad, __half *__restrict__ out) {
-  __shared__ double red[64];
-  __shared__ __half s_hi[2][SC_SIZE], s_lo[2][SC_SIZE];
-  const int row = blockIdx.x;
-  if (row < m) {
-    const double *h = hist + (size_t)row * 2 * SC_SIZE;
-    double nrm[2];
-    row_norms(h, nrm, red);
-    for (int ch = 0; ch < 2; ch++)
-      for (int k = threadIdx.x; k < SC_SIZE; k += blockDim.x)
-        split_fp16(h[ch * SC_SIZE + k] / nrm[ch] * (double)VAL_SCALE, s_hi[ch][k], s_lo[ch][k]);
-  } else {
-    for (int ch = 0; ch < 2; ch++)
-      for (int k = threadIdx.x; k < SC_SIZE; k += blockDim.x) s_hi[ch][k] = s_lo[ch][k] = __float2half(0.0f);
-  }
-  __syncthreads();
-  constexpr int PER_BASE = Q_BASE_BYTES / 2;  // halves
   for (int ch = 0; ch < 2; ch++)
-    for (int b = 0; b < 2; b++) {
-      __half *o = out + (((size_t)ch * 2 + b) * m_pad + row) * PER_BASE;
-      for (int e = threadIdx.x; e < PER_BASE; e += blockDim.x) {
-        const int t = e & 7, u = (e >> 3) & (Q_UNITS - 1), j = e >> 10, s = j * 8 + t;
-        const int cs = u % SC_NUM_S;
-        const int c = b == 0 ? cs : (SC_NUM_S - cs) % SC_NUM_S;
-        __half v = __float2half(0.0f);
-        if (s < 20) v = s_lo[ch][c * SC_NUM_R + s];
-        else if (s < 40) v = s_hi[ch][c * SC_NUM_R + s - 20];
-        else if (s < 60) v = s_hi[ch][c * SC_NUM_R + s - 40];
-        o[e] = v;
+    for (int k = threadIdx.x; k < SC_SIZE; k += blockDim.x) {
+      if (valid) {
+        double v = h[ch * SC_SIZE + k];
+        split_fp16(v / nrm[ch] * (double)VAL_SCALE, S.hi[ch][k], S.lo[ch][k]);
+        S.bits[ch][k] = v == 1.0 ? 0x38 : 0x00;  // e4m3 1.0 / 0.0
+      } else {
+        S.hi[ch][k] = S.lo[ch][k] = __float2half(0.0f);
+        S.bits[ch][k] = 0;
       }
     }
+  if (threadIdx.x < 2) S.inv_norm[threadIdx.x] = valid ? (float)(1.0 / nrm[threadIdx.x]) : 0.0f;
+  __syncthreads();
+}
+
+// fp16 slot s of a sector: which part of the split value an operand supplies
+//   DB   : slots 0..19 hi, 20..39 lo, 40..59 hi, 60..63 zero
+//   query: slots 0..19 lo, 20..39 hi, 40..59 hi, 60..63 zero          (hi*lo + lo*hi + hi*hi)
+__device__ __forceinline__ __half slot_value(const RowPrep &S, int ch, int sector, int s, bool is_db) {
+  if (s >= 60) return __float2half(0.0f);
+  const int r = s < 20 ? s : (s < 40 ? s - 20 : s - 40);
+  const bool use_lo = is_db ? (s >= 20 && s < 40) : (s < 20);
+  return use_lo ? S.lo[ch][sector * SC_NUM_R + r] : S.hi[ch][sector * SC_NUM_R + r];
+}
+// fp8 slot s (0..31) of a sector: rings 0..19, then zero padding
+__device__ __forceinline__ unsigned char slot_bits(const RowPrep &S, int ch, int sector, int s) {
+  return s < SC_NUM_R ? S.bits[ch][sector * SC_NUM_R + s] : (unsigned char)0;
+}
+
+__global__ void __launch_bounds__(256)
+sc_tc_prep_db_kernel(const double *__restrict__ hist, int n, int n_pad, unsigned char *__restrict__ buf,
+                     size_t off_f16, size_t off_f8, size_t off_norm) {
+  __shared__ RowPrep S;
+  const int row = blockIdx.x;
+  prep_row(hist + (size_t)row * 2 * SC_SIZE, row < n, S);
+  if (threadIdx.x < 2 && S.nonbin[threadIdx.x]) atomicOr(reinterpret_cast<int *>(buf) + threadIdx.x, 1);
+  for (int ch = 0; ch < 2; ch++) {
+    // k = chunk*480 + sector*8 + t ; slot = chunk*8 + t
+    __half *o = reinterpret_cast<__half *>(buf + off_f16) + ((size_t)ch * n_pad + row) * K_F16;
+    for (int k = threadIdx.x; k < K_F16; k += blockDim.x) {
+      const int j = k / (UNITS_PER_CHUNK * 8), rem = k - j * (UNITS_PER_CHUNK * 8);
+      o[k] = slot_value(S, ch, rem >> 3, j * 8 + (rem & 7), true);
+    }
+    // k = chunk*960 + sector*16 + t ; slot = chunk*16 + t
+    unsigned char *o8 = buf + off_f8 + ((size_t)ch * n_pad + row) * K_F8;
+    for (int k = threadIdx.x; k < K_F8; k += blockDim.x) {
+      const int j = k / (UNITS_PER_CHUNK * 16), rem = k - j * (UNITS_PER_CHUNK * 16);
+      o8[k] = slot_bits(S, ch, rem >> 4, j * 16 + (rem & 15));
+    }
+    if (threadIdx.x == 0) reinterpret_cast<float *>(buf + off_norm)[(size_t)ch * n_pad + row] = S.inv_norm[ch];
+  }
+}
+
+// Query operand: per (channel, base, query pair): [chunk][unit 2u+b][16 B], unit u = sector u % 60 of
+// the base vector of query b of the pair (x: the query image, y: its sector reversal y[c] = x[(60-c)%60]).
+__global__ void __launch_bounds__(256)
+sc_tc_prep_query_kernel(const double *__restrict__ hist, int m, int m_pad, unsigned char *__restrict__ buf,
+                        size_t off_f16, size_t off_f8, size_t off_norm) {
+  __shared__ RowPrep S;
+  const int row = blockIdx.x;
+  prep_row(hist + (size_t)row * 2 * SC_SIZE, row < m, S);
+  if (threadIdx.x < 2 && S.nonbin[threadIdx.x]) atomicOr(reinterpret_cast<int *>(buf) + threadIdx.x, 1);
+  const int pair = row >> 1, b = row & 1, npairs = m_pad >> 1;
+  for (int ch = 0; ch < 2; ch++)
+    for (int base = 0; base < 2; base++) {
+      __half *o = reinterpret_cast<__half *>(buf + off_f16 +
+                                             (((size_t)ch * 2 + base) * npairs + pair) * F16_CHUNKS * CHUNK_BYTES);
+      for (int e = threadIdx.x; e < F16_CHUNKS * 128 * 8; e += blockDim.x) {
+        const int t = e & 7, u = (e >> 3) & 127, j = e >> 10;
+        const int cs = u % SC_NUM_S, c = base == 0 ? cs : (SC_NUM_S - cs) % SC_NUM_S;
+        o[((size_t)j * Q_UNITS + 2 * u + b) * 8 + t] = slot_value(S, ch, c, j * 8 + t, false);
+      }
+      unsigned char *o8 = buf + off_f8 + (((size_t)ch * 2 + base) * npairs + pair) * F8_CHUNKS * CHUNK_BYTES;
+      for (int e = threadIdx.x; e < F8_CHUNKS * 128 * 16; e += blockDim.x) {
+        const int t = e & 15, u = (e >> 4) & 127, j = e >> 11;
+        const int cs = u % SC_NUM_S, c = base == 0 ? cs : (SC_NUM_S - cs) % SC_NUM_S;
+        o8[((size_t)j * Q_UNITS + 2 * u + b) * 16 + t] = slot_bits(S, ch, c, j * 16 + t);
+      }
+    }
+  if (threadIdx.x < 2) reinterpret_cast<float *>(buf + off_norm)[(size_t)threadIdx.x * m_pad + row] = S.inv_norm[threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -240,6 +295,15 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, ui
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
+__device__ __forceinline__ void umma_f8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
 // completion of all prior MMAs of this thread -> arrive on the barrier at the same offset in both CTAs
 __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
   asm volatile(
@@ -275,25 +339,28 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-// instruction descriptor (InstrDescriptor): c_format F32 (1) [4,6), a/b format F16 (0), K-major both,
-// n_dim = N>>3 [17,23), m_dim = M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+// instruction descriptor (InstrDescriptor): c_format F32 (1) [4,6), a/b format [7,10)/[10,13)
+// (kind::f16: F16 = 0; kind::f8f6f4: E4M3 = 0), K-major both, n_dim = N>>3 [17,23), m_dim = M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 struct TcParams {
-  const __half *q_op;   // [ch][base][m_pad][16 KB]
-  float *d_out[2];      // per channel, m x ldd
+  const unsigned char *q_buf;   // QLayout
+  const unsigned char *db_buf;  // DbLayout
+  size_t q_off_f16, q_off_f8, q_off_norm, db_off_norm;
+  float *d_out[2];              // per channel, m x ldd
   int m, n, m_pad, n_pad, ldd;
-  int n_units, n_tiles;  // units = 2 channels x (m_pad / 4) query groups; tiles = n_pad / 256
-  int dbg_lbo, dbg_sbo;  // Hankel descriptor strides in bytes (16 / 128)
+  int n_units, n_tiles;         // units = 2 channels x (m_pad / 4) query groups; tiles = n_pad / 256
+  int flags;                    // debug: 1 skip epilogue loads, 2 skip MMAs, 4 force generic mode
 };
 
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_constant__ CUtensorMap map_f16_1,
+                   const __grid_constant__ CUtensorMap map_f8_0, const __grid_constant__ CUtensorMap map_f8_1,
                    const TcParams P) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_raw = smem_u32(smem_dyn);
@@ -306,11 +373,16 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  // binary mode per channel: both operands hold only 0/1 in that channel
+  const int *qf = reinterpret_cast<const int *>(P.q_buf), *df = reinterpret_cast<const int *>(P.db_buf);
+  bool binary[2];
+  for (int ch = 0; ch < 2; ch++) binary[ch] = !(P.flags & 4) && qf[ch] == 0 && df[ch] == 0;
 
   // work items of this CTA pair: contiguous range in unit-major order
   const long long W = (long long)P.n_units * P.n_tiles;
-  const long long it_begin = W * pair / npairs, it_end = W * (pair + 1) / npairs;
+  const long long it_begin = W * pair_id / npairs, it_end = W * (pair_id + 1) / npairs;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; s++) {
@@ -345,12 +417,15 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
       for (long long it = it_begin; it < it_end; ++it) {
         const int unit = (int)(it / P.n_tiles), tile = (int)(it - (long long)unit * P.n_tiles);
         const int ch = unit & 1;
-        const CUtensorMap *map = ch == 0 ? &map_a0 : &map_a1;
+        const bool bin = binary[ch];
+        const CUtensorMap *map = bin ? (ch == 0 ? &map_f8_0 : &map_f8_1) : (ch == 0 ? &map_f16_0 : &map_f16_1);
+        const int num_kb = (bin ? F8_CHUNKS : F16_CHUNKS) * UNITS_PER_CHUNK / KB_UNITS;
+        const int kb_elems = bin ? 128 : 64;
         const int row0 = tile * TILE_M + (int)rank * CTA_M;
-        for (int kb = 0; kb < NUM_KB; kb++) {
+        for (int kb = 0; kb < num_kb; kb++) {
           mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1, 1);
           if (leader) mbar_expect_tx(smem_u32(&bars->full[stage]), 2 * A_STAGE_BYTES);
-          tma_load_2d_2sm(sA + stage * A_STAGE_BYTES, map, kb * K_BLOCK, row0, leader_full0 + stage * 8);
+          tma_load_2d_2sm(sA + stage * A_STAGE_BYTES, map, kb * kb_elems, row0, leader_full0 + stage * 8);
           if (++stage == NSTAGE) {
             stage = 0;
             phase ^= 1;
@@ -368,21 +443,24 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
         }
     }
   } else if (warp == 3) {
-    // ===== query operand loader: 4 queries x 16 KB of this CTA's base vector (x: rank 0, y: rank 1) =====
+    // ===== query operand loader: 2 interleaved query pairs of this CTA's base (x: rank 0, y: rank 1) =====
     if (lane == 0) {
       uint32_t phase = 0;
       int prev_unit = -1;
+      const int qpairs = P.m_pad >> 1;
       for (long long it = it_begin; it < it_end; ++it) {
         const int unit = (int)(it / P.n_tiles);
         if (unit == prev_unit) continue;
         prev_unit = unit;
         const int ch = unit & 1, qg = unit >> 1;
+        const bool bin = binary[ch];
+        const uint32_t pair_bytes = (bin ? F8_CHUNKS : F16_CHUNKS) * CHUNK_BYTES;
         mbar_wait(smem_u32(&bars->b_empty), phase ^ 1, 2);
-        mbar_expect_tx(smem_u32(&bars->b_full), B_BYTES);
-        const unsigned char *src = reinterpret_cast<const unsigned char *>(P.q_op) +
-                                   (((size_t)ch * 2 + rank) * P.m_pad + (size_t)qg * QG) * Q_BASE_BYTES;
-        for (int q = 0; q < QG; q++)
-          bulk_load_1d(sB + q * Q_BASE_BYTES, src + (size_t)q * Q_BASE_BYTES, Q_BASE_BYTES, smem_u32(&bars->b_full));
+        mbar_expect_tx(smem_u32(&bars->b_full), 2 * pair_bytes);
+        const unsigned char *src = P.q_buf + (bin ? P.q_off_f8 : P.q_off_f16) +
+                                   (((size_t)ch * 2 + rank) * qpairs + (size_t)qg * 2) * pair_bytes;
+        for (int p = 0; p < 2; p++)
+          bulk_load_1d(sB + p * pair_bytes, src + (size_t)p * pair_bytes, pair_bytes, smem_u32(&bars->b_full));
         if (!leader) {
           mbar_wait(smem_u32(&bars->b_full), phase, 3);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -395,12 +473,17 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA, one thread) =====
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(TILE_M, N_PER_Q);
+      constexpr uint32_t idesc = make_idesc(TILE_M, N_MMA);
       int stage = 0;
       uint32_t phase = 0, b_phase = 0, t_phase = 0;
       int prev_unit = -1;
       for (long long it = it_begin; it < it_end; ++it) {
         const int unit = (int)(it / P.n_tiles);
+        const int ch = unit & 1;
+        const bool bin = binary[ch];
+        const int nchunks = bin ? F8_CHUNKS : F16_CHUNKS;
+        const int num_kb = nchunks * UNITS_PER_CHUNK / KB_UNITS;
+        const uint32_t pair_bytes = nchunks * CHUNK_BYTES;
         if (unit != prev_unit) {
           prev_unit = unit;
           mbar_wait(smem_u32(&bars->b_full), b_phase, 4);
@@ -409,22 +492,26 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
         }
         mbar_wait(smem_u32(&bars->tmem_empty), t_phase ^ 1, 6);
         tc_fence_after();
-        for (int kb = 0; kb < NUM_KB; kb++) {
+        for (int kb = 0; kb < num_kb; kb++) {
           mbar_wait(smem_u32(&bars->full[stage]), phase, 7);
           tc_fence_after();
           const uint32_t a_base = sA + stage * A_STAGE_BYTES;
+          if (!(P.flags & 2)) {
 #pragma unroll
-          for (int kk = 0; kk < K_BLOCK / 16; kk++) {
-            const int k = kb * K_BLOCK + kk * 16;
-            const int j = k / CHUNK_K, c = (k - j * CHUNK_K) >> 3;
-            // A: SWIZZLE_128B K-major, 8-row groups 1024 B apart; K-step advances the start by 32 B
-            const uint64_t adesc = make_desc(a_base + kk * 32, 16, 1024, 2);
+            for (int kk = 0; kk < 4; kk++) {
+              const int u = kb * KB_UNITS + kk * 2;     // K position in 16-byte units
+              const int j = u / UNITS_PER_CHUNK, c = u - j * UNITS_PER_CHUNK;
+              // A: SWIZZLE_128B K-major, 8-row groups 1024 B apart; a K-step advances the start by 32 B
+              const uint64_t adesc = make_desc(a_base + kk * 32, 16, 1024, 2);
 #pragma unroll
-            for (int q = 0; q < QG; q++) {
-              // B: Hankel view, no swizzle: row s, k-group g -> unit (c + s + g) of chunk j
-              const uint64_t bdesc =
-                  make_desc(sB + q * Q_BASE_BYTES + j * (Q_UNITS * 16) + c * 16, P.dbg_lbo, P.dbg_sbo, 0);
-              umma_f16_2sm(tmem_base + q * N_PER_Q, adesc, bdesc, idesc, (kb | kk) != 0 ? 1u : 0u);
+              for (int p = 0; p < 2; p++) {
+                // B: Hankel view, no swizzle: row r = 2 s + b, k-group g -> unit 2 (c + s + g) + b of chunk j
+                const uint64_t bdesc = make_desc(sB + p * pair_bytes + j * CHUNK_BYTES + c * 32, 32, 128, 0);
+                if (bin)
+                  umma_f8_2sm(tmem_base + p * N_MMA, adesc, bdesc, idesc, (kb | kk) != 0 ? 1u : 0u);
+                else
+                  umma_f16_2sm(tmem_base + p * N_MMA, adesc, bdesc, idesc, (kb | kk) != 0 ? 1u : 0u);
+              }
             }
           }
           umma_commit_2sm(smem_u32(&bars->empty[stage]));
@@ -440,30 +527,49 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> max over 128 shift columns -> d = (1 - dot)/2 -> global =====
+    // ===== epilogue: TMEM -> max over the shift columns -> d = (1 - dot)/2 -> global =====
     const int ew = warp & 3;  // TMEM lane quarter accessible to this warp
     const uint32_t leader_tmem_empty = map_to_cta(smem_u32(&bars->tmem_empty), 0);
+    const float *q_norm = reinterpret_cast<const float *>(P.q_buf + P.q_off_norm);
+    const float *db_norm = reinterpret_cast<const float *>(P.db_buf + P.db_off_norm);
     uint32_t t_phase = 0;
     for (long long it = it_begin; it < it_end; ++it) {
       const int unit = (int)(it / P.n_tiles), tile = (int)(it - (long long)unit * P.n_tiles);
       const int ch = unit & 1, qg = unit >> 1;
+      const bool bin = binary[ch];
       mbar_wait(smem_u32(&bars->tmem_full), t_phase, 8);
       tc_fence_after();
       const int row = tile * TILE_M + (int)rank * CTA_M + ew * 32 + lane;
       float *out = P.d_out[ch];
+      const float rd = bin ? db_norm[(size_t)ch * P.n_pad + row] : 0.0f;
+      if (!(P.flags & 1)) {
 #pragma unroll 1
-      for (int q = 0; q < QG; q++) {
-        float best = __int_as_float(0x7fc00000);  // NaN: min over variants ignores NaN (processSC.m:31)
+        for (int p = 0; p < 2; p++) {
+          // column 128 h + 2 s + b : base h, shift s, query b of the pair
+          float best0 = __int_as_float(0x7fc00000), best1 = best0;  // NaN: min ignores NaN (processSC.m:31)
 #pragma unroll 1
-        for (int cb = 0; cb < N_PER_Q; cb += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(q * N_PER_Q + cb), r);
-          tmem_ld_wait();
+          for (int cb = 0; cb < N_MMA; cb += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(p * N_MMA + cb), r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; i++) best = fmaxf(best, __uint_as_float(r[i]));
+            for (int i = 0; i < 32; i += 2) {
+              best0 = fmaxf(best0, __uint_as_float(r[i]));
+              best1 = fmaxf(best1, __uint_as_float(r[i + 1]));
+            }
+          }
+          const int qi = qg * QG + p * 2;
+          if (row < P.n && out) {
+            if (bin) {
+              if (qi < P.m) out[(size_t)qi * P.ldd + row] = (1.0f - best0 * q_norm[(size_t)ch * P.m_pad + qi] * rd) * 0.5f;
+              if (qi + 1 < P.m)
+                out[(size_t)(qi + 1) * P.ldd + row] = (1.0f - best1 * q_norm[(size_t)ch * P.m_pad + qi + 1] * rd) * 0.5f;
+            } else {
+              if (qi < P.m) out[(size_t)qi * P.ldd + row] = (1.0f - best0 * ACC_SCALE) * 0.5f;
+              if (qi + 1 < P.m) out[(size_t)(qi + 1) * P.ldd + row] = (1.0f - best1 * ACC_SCALE) * 0.5f;
+            }
+          }
         }
-        const int qi = qg * QG + q;
-        if (qi < P.m && row < P.n && out) out[(size_t)qi * P.ldd + row] = (1.0f - best * ACC_SCALE) * 0.5f;
       }
       tc_fence_before();
       __syncwarp();
@@ -499,25 +605,29 @@ PFN_encodeTiled get_encode() {
   return fn;
 }
 
-inline int pad_to(int v, int a) { return (v + a - 1) / a * a; }
-
 }  // namespace
 
-size_t sc_tc_db_bytes(int n) { return (size_t)2 * pad_to(n, TILE_M) * K_TOTAL * sizeof(__half); }
-size_t sc_tc_query_bytes(int m) { return (size_t)2 * 2 * pad_to(m, QG) * Q_BASE_BYTES; }
+size_t sc_tc_db_bytes(int n) { return DbLayout(n).total; }
+size_t sc_tc_query_bytes(int m) { return QLayout(m).total; }
 
 cudaError_t launch_sc_tc_prep_db(const double *hist, int n, void *db_buf, cudaStream_t st, int64_t *launches) {
   if (n <= 0) return cudaSuccess;
-  const int n_pad = pad_to(n, TILE_M);
-  sc_tc_prep_db_kernel<<<n_pad, 256, 0, st>>>(hist, n, n_pad, reinterpret_cast<__half *>(db_buf));
+  DbLayout L(n);
+  cudaError_t e = cudaMemsetAsync(db_buf, 0, HEADER_BYTES, st);
+  if (e != cudaSuccess) return e;
+  sc_tc_prep_db_kernel<<<L.n_pad, 256, 0, st>>>(hist, n, L.n_pad, reinterpret_cast<unsigned char *>(db_buf), L.off_f16,
+                                                L.off_f8, L.off_norm);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
 
 cudaError_t launch_sc_tc_prep_query(const double *hist, int m, void *q_buf, cudaStream_t st, int64_t *launches) {
   if (m <= 0) return cudaSuccess;
-  const int m_pad = pad_to(m, QG);
-  sc_tc_prep_query_kernel<<<m_pad, 256, 0, st>>>(hist, m, m_pad, reinterpret_cast<__half *>(q_buf));
+  QLayout L(m);
+  cudaError_t e = cudaMemsetAsync(q_buf, 0, HEADER_BYTES, st);
+  if (e != cudaSuccess) return e;
+  sc_tc_prep_query_kernel<<<L.m_pad, 256, 0, st>>>(hist, m, L.m_pad, reinterpret_cast<unsigned char *>(q_buf),
+                                                   L.off_f16, L.off_f8, L.off_norm);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -527,41 +637,48 @@ cudaError_t launch_sc_match_tc(const void *q_buf, int m, const void *db_buf, int
   if (m <= 0 || n <= 0) return cudaSuccess;
   PFN_encodeTiled enc = get_encode();
   if (!enc) return cudaErrorNotSupported;
-  const int n_pad = pad_to(n, TILE_M), m_pad = pad_to(m, QG);
-  CUtensorMap maps[2];
-  for (int ch = 0; ch < 2; ch++) {
-    cuuint64_t dims[2] = {(cuuint64_t)K_TOTAL, (cuuint64_t)n_pad};
-    cuuint64_t strides[1] = {(cuuint64_t)K_TOTAL * sizeof(__half)};
-    cuuint32_t box[2] = {(cuuint32_t)K_BLOCK, (cuuint32_t)CTA_M};
-    cuuint32_t estr[2] = {1, 1};
-    void *gaddr = (void *)(reinterpret_cast<const __half *>(db_buf) + (size_t)ch * n_pad * K_TOTAL);
-    CUresult r = enc(&maps[ch], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, gaddr, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-  }
+  DbLayout DL(n);
+  QLayout QL(m);
+  const unsigned char *dbb = reinterpret_cast<const unsigned char *>(db_buf);
+  CUtensorMap maps[4];
+  for (int fmt = 0; fmt < 2; fmt++)
+    for (int ch = 0; ch < 2; ch++) {
+      const size_t kbytes = fmt == 0 ? (size_t)K_F16 * 2 : (size_t)K_F8;
+      cuuint64_t dims[2] = {(cuuint64_t)(fmt == 0 ? K_F16 : K_F8), (cuuint64_t)DL.n_pad};
+      cuuint64_t strides[1] = {(cuuint64_t)kbytes};
+      cuuint32_t box[2] = {(cuuint32_t)(fmt == 0 ? 64 : 128), (cuuint32_t)CTA_M};
+      cuuint32_t estr[2] = {1, 1};
+      void *gaddr = (void *)(dbb + (fmt == 0 ? DL.off_f16 : DL.off_f8) + (size_t)ch * DL.n_pad * kbytes);
+      CUresult r = enc(&maps[fmt * 2 + ch], fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                       gaddr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    }
   TcParams P;
-  P.q_op = reinterpret_cast<const __half *>(q_buf);
+  P.q_buf = reinterpret_cast<const unsigned char *>(q_buf);
+  P.db_buf = dbb;
+  P.q_off_f16 = QL.off_f16;
+  P.q_off_f8 = QL.off_f8;
+  P.q_off_norm = QL.off_norm;
+  P.db_off_norm = DL.off_norm;
   P.d_out[0] = d_p;
   P.d_out[1] = d_i;
   P.m = m;
   P.n = n;
-  P.m_pad = m_pad;
-  P.n_pad = n_pad;
+  P.m_pad = QL.m_pad;
+  P.n_pad = DL.n_pad;
   P.ldd = ldd;
-  P.n_units = 2 * (m_pad / QG);
-  P.n_tiles = n_pad / TILE_M;
-  P.dbg_lbo = 16;
-  P.dbg_sbo = 128;
-  if (const char *e = getenv("SODSO_TC_LBO")) P.dbg_lbo = atoi(e);
-  if (const char *e = getenv("SODSO_TC_SBO")) P.dbg_sbo = atoi(e);
+  P.n_units = 2 * (QL.m_pad / QG);
+  P.n_tiles = DL.n_pad / TILE_M;
+  P.flags = 0;
+  if (const char *e = getenv("SODSO_TC_FLAGS")) P.flags = atoi(e);
   const long long W = (long long)P.n_units * P.n_tiles;
   int npairs = num_sms / 2;
   if (npairs > W) npairs = (int)W;
   if (npairs < 1) npairs = 1;
   cudaError_t e = cudaFuncSetAttribute(sc_match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  sc_match_tc_kernel<<<2 * npairs, TC_THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], P);
+  sc_match_tc_kernel<<<2 * npairs, TC_THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], P);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
