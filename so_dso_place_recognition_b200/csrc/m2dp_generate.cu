@@ -1,7 +1,265 @@
-// placeholder
+// M2DP signature generation: test_m2dp.cpp:41-67 (PCA once, 4 sign variants) around
+// M2DP::getSignature (M2DP.cpp:38-109), one CTA per scan, the whole batch in one launch.
+//
+// Per (scan, variant): 64 planes x n points are projected (two 3-term dot products), binned by
+// (rho, theta) with shared-memory atomics into a 64 x 128 count histogram (u32) and intensity-sum
+// histogram (fp64); the sums are binarised against the float average intensity; the signature
+// is the dominant left/right singular vector pair of each 64 x 128 matrix.
+//
+// SVD: only the dominant pair is needed (M2DP.cpp:96-103), so instead of a full Jacobi SVD the
+// kernel runs the alternating power iteration u <- A v / |A v|, v <- A^T u / |A^T u| in fp64 from
+// the all-ones vector until the update of u falls below 1e-15 (cap 20 000 sweeps).  Both matrices
+// are entrywise non-negative, so the iteration converges to the Perron pair, which also fixes
+// the sign the same way as the oracle (sum(u) >= 0; Eigen's own sign is unobservable).
+//
+// The projection table (xProj / yProj, M2DP.cpp:4-34) is computed on the host with float
+// cosf/sinf exactly like the reference constructor and passed in constant memory.
+// Compiled with -fmad=false (see pca.cuh).
+#include <cmath>
+
 #include "../../include/sodso_pr.h"
-#include "common.cuh"
+#include "pca.cuh"
+
 namespace sodso {
-size_t m2dp_generate_workspace_bytes(int, bool) { return 256; }
-cudaError_t launch_m2dp_generate(const double *, const float *, const int64_t *, int, double, bool, double *, void *, size_t, int, cudaStream_t, int64_t *) { return cudaErrorNotSupported; }
+namespace {
+
+constexpr int M2_THREADS = 512;
+constexpr int M2_CAP = 4096;  // staged points per scan
+constexpr int HB = M2DP_PQ * M2DP_SR;  // 8192 histogram bins
+
+__constant__ double c_xproj[3 * M2DP_PQ];
+__constant__ double c_yproj[3 * M2DP_PQ];
+
+struct M2Smem {
+  double sx[M2_CAP], sy[M2_CAP], sz[M2_CAP];
+  double hsum[HB];          // intensity sums -> binarised matrix (0/1)
+  double u[M2DP_PQ], v[M2DP_SR], un[M2DP_PQ];
+  double scratch[6 * 32];
+  double bc[16];
+  float si[M2_CAP];
+  unsigned hcnt[HB];
+  int ibc[4];
+};
+
+// dominant singular pair of the 64 x 128 matrix held in shared memory (as u32 counts or as
+// doubles), written to out[0..63] (u) and out[64..191] (v).
+template <class T>
+__device__ void dominant_pair(const T *A, M2Smem &S, double *out) {
+  const int tid = threadIdx.x;
+  for (int k = tid; k < M2DP_SR; k += blockDim.x) S.v[k] = 1.0;
+  for (int k = tid; k < M2DP_PQ; k += blockDim.x) S.u[k] = 0.0;
+  __syncthreads();
+  double sigma = 0.0;
+  for (int iter = 0; iter < 20000; iter++) {
+    // u' = A v : 64 rows, 8 threads per row
+    {
+      const int row = tid >> 3, part = tid & 7;
+      double acc = 0.0;
+      if (row < M2DP_PQ)
+        for (int k = part; k < M2DP_SR; k += 8) acc += (double)A[row * M2DP_SR + k] * S.v[k];
+      acc += __shfl_down_sync(0xffffffffu, acc, 4);
+      acc += __shfl_down_sync(0xffffffffu, acc, 2);
+      acc += __shfl_down_sync(0xffffffffu, acc, 1);
+      if (row < M2DP_PQ && part == 0) S.un[row] = acc;
+    }
+    __syncthreads();
+    double nu[1] = {0.0};
+    if (tid < M2DP_PQ) nu[0] = S.un[tid] * S.un[tid];
+    block_sum<1>(nu, S.scratch);
+    const double nrm_u = sqrt(nu[0]);
+    if (nrm_u == 0.0) {  // zero matrix: JacobiSVD-like convention of the oracle: u = e_0, v = 0
+      sigma = 0.0;
+      break;
+    }
+    double diff[1] = {0.0};
+    if (tid < M2DP_PQ) {
+      const double nv = S.un[tid] / nrm_u;
+      const double d = nv - S.u[tid];
+      diff[0] = d * d;
+      S.u[tid] = nv;
+    }
+    __syncthreads();
+    // v' = A^T u : 128 columns, 4 threads per column
+    {
+      const int col = tid >> 2, part = tid & 3;
+      double acc = 0.0;
+      for (int r = part; r < M2DP_PQ; r += 4) acc += (double)A[r * M2DP_SR + col] * S.u[r];
+      acc += __shfl_down_sync(0xffffffffu, acc, 2);
+      acc += __shfl_down_sync(0xffffffffu, acc, 1);
+      if (part == 0) S.v[col] = acc;
+    }
+    __syncthreads();
+    double nv2[2] = {0.0, diff[0]};
+    if (tid < M2DP_SR) nv2[0] = S.v[tid] * S.v[tid];
+    block_sum<2>(nv2, S.scratch);
+    sigma = sqrt(nv2[0]);
+    if (tid < M2DP_SR) S.v[tid] = S.v[tid] / sigma;
+    __syncthreads();
+    if (nv2[1] < 1e-28) break;
+  }
+  if (sigma == 0.0) {
+    for (int k = tid; k < M2DP_PQ; k += blockDim.x) out[k] = k == 0 ? 1.0 : 0.0;
+    for (int k = tid; k < M2DP_SR; k += blockDim.x) out[M2DP_PQ + k] = 0.0;
+  } else {
+    for (int k = tid; k < M2DP_PQ; k += blockDim.x) out[k] = S.u[k];
+    for (int k = tid; k < M2DP_SR; k += blockDim.x) out[M2DP_PQ + k] = S.v[k];
+  }
+  __syncthreads();
 }
+
+__global__ void __launch_bounds__(M2_THREADS, 1)
+m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ inten,
+                     const int64_t *__restrict__ off, int nscan, double S_res_inv, double R_res_inv,
+                     int variants, double *__restrict__ hist) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  M2Smem &S = *reinterpret_cast<M2Smem *>(smem_raw);
+  const double PI = 3.14159265358979323846;
+  const int lane = threadIdx.x & 31;
+
+  for (int scan = blockIdx.x; scan < nscan; scan += gridDim.x) {
+    const int64_t p0 = off[scan];
+    const int n = (int)(off[scan + 1] - p0);
+    const double *g = xyz + 3 * p0;
+    const float *gi = inten + p0;
+    const int nst = n < M2_CAP ? n : M2_CAP;
+    stage_scan(g, n, M2_CAP, S.sx, S.sy, S.sz);
+    for (int i = threadIdx.x; i < nst; i += blockDim.x) S.si[i] = gi[i];
+    __syncthreads();
+    ScanPoints P{g, S.sx, S.sy, S.sz, n, nst};
+    const float ave = scan_ave_intensity(gi, S.si, n, nst, S.scratch, S.ibc);  // M2DP.cpp:77-81
+    if (variants) {
+      scan_pca(P, S.scratch, S.bc);  // test_m2dp.cpp:44-45
+    } else {
+      // the class contract: input already aligned.  identity transform
+      if (threadIdx.x < 16) S.bc[threadIdx.x] = (threadIdx.x == 3 || threadIdx.x == 7 || threadIdx.x == 11) ? 1.0 : 0.0;
+      __syncthreads();
+    }
+    const int nvar = variants ? 4 : 1;
+    for (int var = 0; var < nvar; var++) {
+      // test_m2dp.cpp:47-57: dx outer, dy inner, both in {-1, +1}
+      const double dx = variants ? ((var >> 1) ? 1.0 : -1.0) : 1.0;
+      const double dy = variants ? ((var & 1) ? 1.0 : -1.0) : 1.0;
+      const double dz = dx * dy;
+      for (int b = threadIdx.x; b < HB; b += blockDim.x) {
+        S.hcnt[b] = 0u;
+        S.hsum[b] = 0.0;
+      }
+      __syncthreads();
+      // M2DP.cpp:47-74
+      for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const bool act = i < n;
+        double px = 0.0, py = 0.0, pz = 0.0;
+        float it = 0.0f;
+        if (act) {
+          double x, y, z, ax, ay, az;
+          P.get(i, x, y, z);
+          if (variants) {
+            pca_rotate(S.bc, x, y, z, ax, ay, az);
+          } else {
+            ax = x;
+            ay = y;
+            az = z;
+          }
+          px = dx * ax;
+          py = dy * ay;
+          pz = dz * az;
+          it = i < nst ? S.si[i] : gi[i];
+        }
+        for (int pq = 0; pq < M2DP_PQ; pq++) {
+          int idx = -1;
+          if (act) {
+            const double xp = (c_xproj[3 * pq] * px + c_xproj[3 * pq + 1] * py) + c_xproj[3 * pq + 2] * pz;
+            const double yp = (c_yproj[3 * pq] * px + c_yproj[3 * pq + 1] * py) + c_yproj[3 * pq + 2] * pz;
+            const double ang = (atan2(yp, xp) + PI) * S_res_inv;
+            const double rad = sqrt(xp * xp + yp * yp) * R_res_inv;
+            if (rad < (double)M2DP_SR && ang < 32.0) {
+              const int si = (int)floor(ang), ri = (int)floor(rad);
+              const int sr = ri * M2DP_NUM_S + si;  // M2DP.cpp:63
+              if (sr < M2DP_SR) idx = pq * M2DP_SR + sr;  // M2DP.cpp:66 (si == 16 aliases into ring ri+1)
+            }
+          }
+          // warp-aggregate the degenerate planes where every lane hits the same bin
+          const int idx0 = __shfl_sync(0xffffffffu, idx, 0);
+          if (__all_sync(0xffffffffu, idx == idx0)) {
+            if (idx0 >= 0) {
+              const double s = warp_sum((double)it);
+              if (lane == 0) {
+                atomicAdd(&S.hcnt[idx0], 32u);
+                atomicAdd(&S.hsum[idx0], s);
+              }
+            }
+          } else if (idx >= 0) {
+            atomicAdd(&S.hcnt[idx], 1u);
+            atomicAdd(&S.hsum[idx], (double)it);
+          }
+        }
+      }
+      __syncthreads();
+      // M2DP.cpp:84-91
+      for (int b = threadIdx.x; b < HB; b += blockDim.x) {
+        const unsigned c = S.hcnt[b];
+        double v = 0.0;
+        if (c) v = (S.hsum[b] / (double)c) > (double)ave ? 1.0 : 0.0;
+        S.hsum[b] = v;
+      }
+      __syncthreads();
+      double *row = hist + ((size_t)scan * nvar + var) * 2 * M2DP_SIG;
+      dominant_pair<unsigned>(S.hcnt, S, row);           // M2DP.cpp:94-98,107
+      dominant_pair<double>(S.hsum, S, row + M2DP_SIG);  // M2DP.cpp:100-108
+    }
+    __syncthreads();
+  }
+}
+
+// M2DP::M2DP (M2DP.cpp:4-34) -- float azimuth / elevation and float cos/sin products, like the reference
+void build_tables(double *xproj, double *yproj) {
+  for (int p = 0; p < M2DP_NUM_P; p++) {
+    float azm = -M_PI / 2.0 + (M_PI / M2DP_NUM_P) * p;
+    for (int q = 0; q < M2DP_NUM_Q; q++) {
+      float elv = (M_PI / 2.0 / M2DP_NUM_Q) * q;
+      double n0 = std::cos(elv) * std::cos(azm);
+      double n1 = std::cos(elv) * std::sin(azm);
+      double n2 = std::sin(elv);
+      double d = (1.0 * n0 + 0.0 * n1) + 0.0 * n2;
+      double x0 = 1.0 - d * n0, x1 = 0.0 - d * n1, x2 = 0.0 - d * n2;
+      double y0 = n1 * x2 - n2 * x1;
+      double y1 = n2 * x0 - n0 * x2;
+      double y2 = n0 * x1 - n1 * x0;
+      int k = p * M2DP_NUM_Q + q;
+      xproj[3 * k + 0] = x0;
+      xproj[3 * k + 1] = x1;
+      xproj[3 * k + 2] = x2;
+      yproj[3 * k + 0] = y0;
+      yproj[3 * k + 1] = y1;
+      yproj[3 * k + 2] = y2;
+    }
+  }
+}
+
+}  // namespace
+
+size_t m2dp_generate_workspace_bytes(int, bool) { return 256; }
+
+cudaError_t launch_m2dp_generate(const double *xyz, const float *inten, const int64_t *off, int nscan,
+                                 double max_rho, bool do_align_and_variants, double *hist, void *, size_t,
+                                 int num_sms, cudaStream_t st, int64_t *launches) {
+  if (nscan <= 0) return cudaSuccess;
+  double xp[3 * M2DP_PQ], yp[3 * M2DP_PQ];
+  build_tables(xp, yp);
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_xproj, xp, sizeof(xp), 0, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyToSymbolAsync(c_yproj, yp, sizeof(yp), 0, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(m2dp_generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(M2Smem));
+  if (e != cudaSuccess) return e;
+  const double S_res_inv = M2DP_NUM_S / (2.0 * 3.14159265358979323846);  // M2DP.cpp:32
+  const double R_res_inv = M2DP_NUM_R / max_rho;                          // M2DP.cpp:33
+  int grid = nscan < num_sms ? nscan : num_sms;
+  m2dp_generate_kernel<<<grid, M2_THREADS, sizeof(M2Smem), st>>>(xyz, inten, off, nscan, S_res_inv, R_res_inv,
+                                                                 do_align_and_variants ? 1 : 0, hist);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+}  // namespace sodso

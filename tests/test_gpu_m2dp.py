@@ -1,0 +1,71 @@
+"""GPU parity: M2DP generation (test_m2dp.cpp:41-67, M2DP.cpp:38-109) and matching
+(processM2DP.m:1-22) through the C ABI vs the CPU oracle.
+
+Bar: signatures within 1e-9 of the oracle (dominant singular pair, oracle sign convention
+sum(U1) >= 0); distances within 1e-5; identical top-1 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from so_dso_place_recognition_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+TOL_SIG = 1e-9
+TOL_D = 1e-5
+
+
+def test_m2dp_generate_vs_oracle(gpu_ctx, oracle):
+    xyz, inten, off = synth.make_scan_set(12, 2048)
+    h = api.m2dp_generate(xyz, inten, off)
+    ref = oracle.m2dp_generate(xyz, inten, off, nthreads=8)
+    assert h.shape == (48, 384)
+    np.testing.assert_allclose(h, ref, rtol=0, atol=TOL_SIG)
+    # unit-norm singular vectors, non-negative orientation
+    assert np.allclose(np.linalg.norm(h[:, :64], axis=1), 1) and np.allclose(np.linalg.norm(h[:, 64:192], axis=1), 1)
+    assert (h[:, :64].sum(1) >= 0).all()
+
+
+def test_m2dp_class_contract_prealigned(gpu_ctx, oracle):
+    """M2DP::getSignature takes already aligned points (M2DP.h:18-20)."""
+    xyz, inten = synth.make_scan(21, 3000)
+    al, _, _ = oracle.align_pca(xyz)
+    c_ref, i_ref = oracle.m2dp_signature(al, inten)
+    m = api.M2DP(45.0)
+    assert m.getSignatureSize() == 192
+    c, i = m.getSignature(al, inten)
+    np.testing.assert_allclose(c, c_ref, rtol=0, atol=TOL_SIG)
+    np.testing.assert_allclose(i, i_ref, rtol=0, atol=TOL_SIG)
+
+
+def test_m2dp_real_scans_and_ragged(gpu_ctx, oracle, real_scans):
+    h = api.m2dp_generate(real_scans["m2dp_xyz"], real_scans["m2dp_inten"], real_scans["m2dp_off"])
+    np.testing.assert_allclose(h, real_scans["m2dp_hist"], rtol=0, atol=TOL_SIG)
+    sizes = [5, 300, 4096, 4500]
+    parts = [synth.make_scan(300 + k, n) for k, n in enumerate(sizes)]
+    xyz = np.concatenate([p[0] for p in parts])
+    inten = np.concatenate([p[1] for p in parts])
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    np.testing.assert_allclose(api.m2dp_generate(xyz, inten, off), oracle.m2dp_generate(xyz, inten, off, nthreads=4),
+                               rtol=0, atol=TOL_SIG)
+
+
+def test_m2dp_match_and_top1(gpu_ctx, oracle):
+    xyz, inten, off = synth.make_scan_set(96, 1024, planted_loops=True)
+    sig = oracle.m2dp_generate(xyz, inten, off, nthreads=16)
+    dp, di = api.processM2DP(sig[:4 * 37], sig)
+    rp, ri = oracle.m2dp_match(sig[:4 * 37], sig, nthreads=8)
+    assert dp.shape == (37, 96)
+    assert np.abs(dp - rp).max() < TOL_D and np.abs(di - ri).max() < TOL_D
+    rp, ri = oracle.m2dp_match(sig, sig, nthreads=8)
+    ridx, rsc = oracle.fuse_top1(rp, ri, 5)
+    idx, sc = api.run_test("m2dp", sig, sig, 5)
+    np.testing.assert_array_equal(idx, ridx)
+    np.testing.assert_allclose(sc, rsc, atol=2e-3)
+
+
+def test_m2dp_end_to_end_planted_loops(gpu_ctx):
+    """BASELINE configs[4] in small: GPU generation -> GPU match -> loops recovered."""
+    n = 64
+    xyz, inten, off = synth.make_scan_set(n, 2048, planted_loops=True)
+    sig = api.m2dp_generate(xyz, inten, off)
+    idx, sc = api.run_test("m2dp", sig, sig, 3)
+    assert (idx == (np.arange(n) + n // 2) % n).mean() > 0.8

@@ -27,3 +27,12 @@ t = time.time()
 idx, sc = api.run_test("sc", h, h, 100)
 torch.cuda.synchronize()
 print("run_test e2e (device sigs)", ns, time.time() - t, "s; launches", ctx.launch_count)
+if "--m2dp" in sys.argv:
+    nm = 592
+    for it in range(2):
+        hm = api.m2dp_generate(dx[:nm * npts], di[:nm * npts], do[:nm + 1])
+        print("m2dp_generate", nm, "scans:", round(ctx.last_kernel_ms, 3), "ms ->", round(ctx.last_kernel_ms / nm * 1e3, 1), "us/scan")
+    hh = hm.repeat(8, 1)[:4 * 4000]
+    for it in range(2):
+        a, b = api.processM2DP(hh, hh, f32=True)
+        print("m2dp match 4000 x 4000:", round(ctx.last_kernel_ms, 3), "ms", round(16e6 / ctx.last_kernel_ms / 1e3, 1), "Mpairs/s")
