@@ -15,8 +15,8 @@
 // apart, so a descriptor with SBO = 128 B reads row r at unit (base + r): overlapping windows of one
 // small buffer ARE the shifted copies.  Two queries are interleaved unit-wise (Z[2u + b] = q_b[u]);
 // with LBO = 32 B, row r = 2 s + b then is shift s of query b, and one N = 256 MMA of a CTA pair
-// (cta_group::2, M = 256; CTA 0 supplies the 128 x-rows, CTA 1 the 128 y-rows of B) produces all
-// 120 (+8 duplicate) variants of two queries against 256 DB rows.  A query costs 16 KB (fp16) or
+// (cta_group::2, M = 256, N = 240; CTA 0 supplies the 120 x-rows, CTA 1 the 120 y-rows of B)
+// produces exactly the 120 variants of two queries against 256 DB rows.  A query costs 16 KB (fp16) or
 // 4 KB (fp8) of shared memory per CTA instead of a 120 x 1200 expanded tile per K-block.
 //
 // Two arithmetic modes, chosen per channel on the device:
@@ -53,7 +53,8 @@ constexpr int Q_UNITS = 256;                         // units per (query pair, b
 constexpr int CHUNK_BYTES = Q_UNITS * 16;            // 4 KB
 constexpr int QG = 4;                                // queries per tile = 2 interleaved pairs
 constexpr int TILE_M = 256, CTA_M = 128;             // DB rows per CTA pair / per CTA
-constexpr int N_MMA = 256;                           // accumulator columns per query pair
+constexpr int N_MMA = 256;                           // TMEM column stride between the two query pairs
+constexpr int N_INST = 240;                          // MMA N: 2 bases x 60 shifts x 2 interleaved queries
 constexpr int A_STAGE_BYTES = CTA_M * 128;           // 16 KB
 constexpr int NSTAGE = 8;
 constexpr int B_BYTES = 2 * F16_CHUNKS * CHUNK_BYTES;   // 64 KB (two pairs, generic mode)
@@ -324,6 +325,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptors (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14),
@@ -473,7 +483,7 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA, one thread) =====
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TILE_M, N_MMA);
+      constexpr uint32_t idesc = make_idesc(TILE_M, N_INST);
       int stage = 0;
       uint32_t phase = 0, b_phase = 0, t_phase = 0;
       int prev_unit = -1;
@@ -545,15 +555,27 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
       if (!(P.flags & 1)) {
 #pragma unroll 1
         for (int p = 0; p < 2; p++) {
-          // column 128 h + 2 s + b : base h, shift s, query b of the pair
+          // column 120 h + 2 s + b : base h, shift s, query b of the pair
           float best0 = __int_as_float(0x7fc00000), best1 = best0;  // NaN: min ignores NaN (processSC.m:31)
+          const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(p * N_MMA);
 #pragma unroll 1
-          for (int cb = 0; cb < N_MMA; cb += 32) {
+          for (int cb = 0; cb + 32 <= N_INST; cb += 32) {
             uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(p * N_MMA + cb), r);
+            tmem_ld32(tcol + (uint32_t)cb, r);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
+              best0 = fmaxf(best0, __uint_as_float(r[i]));
+              best1 = fmaxf(best1, __uint_as_float(r[i + 1]));
+            }
+          }
+          {
+            static_assert(N_INST % 32 == 16, "tail of 16 columns");
+            uint32_t r[16];
+            tmem_ld16(tcol + (uint32_t)(N_INST - 16), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
               best0 = fmaxf(best0, __uint_as_float(r[i]));
               best1 = fmaxf(best1, __uint_as_float(r[i + 1]));
             }

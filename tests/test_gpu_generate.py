@@ -48,8 +48,8 @@ def test_config1_1000_scans(gpu_ctx, oracle):
 
 def test_ragged_empty_and_oversized(gpu_ctx, oracle):
     """ragged batch incl. an empty scan (0/0 -> all-zero signature), tiny scans and one larger than the
-    shared-memory staging capacity (6144 points)."""
-    sizes = [0, 1, 2, 3, 17, 1000, 4096, 0, 6144, 6145, 9000, 33]
+    shared-memory staging capacity (3200 points)."""
+    sizes = [0, 1, 2, 3, 17, 1000, 4096, 0, 3199, 3200, 3201, 6145, 9000, 33]
     parts = [synth.make_scan(100 + k, max(n, 1)) for k, n in enumerate(sizes)]
     xyz = np.concatenate([p[0][:n] for p, n in zip(parts, sizes)])
     inten = np.concatenate([p[1][:n] for p, n in zip(parts, sizes)])
