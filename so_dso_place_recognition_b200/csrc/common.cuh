@@ -20,6 +20,30 @@ constexpr int M2DP_SIG = M2DP_PQ + M2DP_SR;       // 192
 
 constexpr double STAT_SHIFT = 0.25;  // centre of the [0, 0.5] distance range, see sodso_db_partial_stats
 
+#ifdef __CUDACC__
+// atan2(num, den) / 2pi + 1/2 in [0, 1] ("turns"), fp32, |error| < 2e-7 turns for finite inputs that are
+// not both zero (odd polynomial of degree 13 on the octant-reduced ratio: 5e-7 rad, + a 2-ulp divide).
+// Used only to PROPOSE a polar bin; the generation kernels accept it only away from bin edges.
+__device__ __forceinline__ float fast_turns(float num, float den) {
+  const float an = fabsf(num), ad = fabsf(den);
+  const float mx = fmaxf(an, ad), mn = fminf(an, ad);
+  const float a = __fdividef(mn, mx);
+  const float s = a * a;
+  float p = 0.00782548f;
+  p = __fmaf_rn(p, s, -0.03689863f);
+  p = __fmaf_rn(p, s, 0.08374156f);
+  p = __fmaf_rn(p, s, -0.13480406f);
+  p = __fmaf_rn(p, s, 0.19879872f);
+  p = __fmaf_rn(p, s, -0.33326375f);
+  p = __fmaf_rn(p, s, 0.99999933f);
+  float t = p * a * 0.15915494309f;  // atan(a) / 2pi in [0, 1/8]
+  t = an > ad ? 0.25f - t : t;
+  t = den < 0.0f ? 0.5f - t : t;
+  t = num < 0.0f ? -t : t;
+  return t + 0.5f;
+}
+#endif
+
 void set_error(const std::string &msg);
 
 struct KernelTimer;  // capi.cu

@@ -1,22 +1,26 @@
 // Scan Context signature generation: SC::getSignature (SC.cpp:12-76) + align_points_PCA
 // (pts_align.h:7-46) for a whole batch of scans in ONE launch.
 //
-// Two persistent CTAs per SM (256 threads each) walk over scans; while one CTA sits in a
-// latency-bound phase (bulk copy in flight, the serial 3x3 eigen-solve) the other one computes.
-// Per scan:
-//   cp.async.bulk (TMA, 1-D) lands the scan's raw AoS fp64 points in shared memory, no register
-//   staging, next scan prefetched into L2   ->   mean + intensity sums (one fixed-tree block
-//   reduction)   ->   scatter matrix (second reduction)   ->   3x3 Jacobi on one thread while the
-//   other threads clear the bins   ->   point -> (sector, ring) scatter with shared-memory atomics
-//   (u32 count, int32 / fp64 intensity sum, order-preserving int64 min / max of the height)   ->
-//   2 x 1200 coalesced fp64 stores.
-// The bin of a point is found in fp32 (atan2f / sqrtf) and accepted only when the fractional
-// position is at least GUARD away from a bin edge -- 10x the worst-case fp32 error -- otherwise the
-// point takes the reference's own fp64 atan2 / sqrt / floor expression (SC.cpp:37-38).  The bins
+// Four persistent CTAs per SM (256 threads each) walk over scans.  The only shared-memory state of a
+// CTA is the 1200-bin accumulator set (37 KB), so many CTAs are resident and hide each other's
+// latency-bound phases.  Per scan:
+//   pass 1 (HBM read): one pass of sums about the scan's first point -> mean, 3x3 scatter matrix,
+//           intensity sums; one fixed-tree block reduction
+//   serial: thread 0 solves the 3x3 eigenproblem (short-chain Jacobi), thread 32 replays the order
+//           dependent float intensity sum of SC.cpp:60-63 if it cannot be proven exact
+//   pass 2 (L2 read, backwards so that the lines pass 1 touched last are re-read first; measured DRAM
+//           read = 1.07 x the algorithmic bytes): point -> (sector, ring), shared-memory atomics (u32 count,
+//           int32 / fp64 intensity sum, order-preserving int64 min / max of the height); 64-point
+//           chunks are handed out by a shared counter so that all warps reach the barrier together
+//   output: 2 x 1200 coalesced fp64 stores, bins cleared in the same sweep.
+// The bin of a point is found in fp32 (fast_turns / rsqrt) and accepted only when the fractional
+// position is at least BIN_GUARD away from a bin edge -- 10x the worst-case fp32 error -- otherwise
+// the point takes the reference's own fp64 atan2 / sqrt / floor expression (SC.cpp:37-38).  The bins
 // are therefore exactly those of the fp64 expression.
 // HBM traffic per scan = the algorithmic bytes: 28 B/point in, 19 200 B out.
-// Compiled with -fmad=false (see pca.cuh).
+// Compiled with -fmad=false (see pca.cuh); fused multiply-adds are written explicitly where wanted.
 #include <climits>
+#include <cstdlib>
 
 #include "../../include/sodso_pr.h"
 #include "pca.cuh"
@@ -25,64 +29,21 @@ namespace sodso {
 namespace {
 
 constexpr int GEN_THREADS = 256;
-constexpr int GEN_CAP = 3200;       // points of a scan staged in shared memory; the rest is re-read from L2
-constexpr float BIN_GUARD = 2.5e-4f;  // fp32 bin coordinate error is < 2e-5 (see bin_of_point)
+constexpr int GEN_CTAS_PER_SM = 4;
+constexpr int GEN_CHUNK = 64;         // points per work grab in the scatter pass
+constexpr int GEN_CAP = 3200;         // align_pca_kernel: points of a scan staged in shared memory
+constexpr float BIN_GUARD = 2.5e-4f;  // fp32 bin coordinates are accurate to < 2.5e-5 (see bin_of_point)
 
 struct ScSmem {
-  double pts[3 * GEN_CAP + 2];   // raw AoS as landed by the bulk copy; element j of the scan at pts[j + shift]
-  double b_sum[SC_SIZE];         // fp64 intensity sums; aliased as int32 sums in exact mode
-  long long b_lo[SC_SIZE], b_hi[SC_SIZE];
-  double scratch[6 * 32];
-  double bc[16];
-  unsigned long long mbar;
+  double b_sum[SC_SIZE];                    // fp64 intensity sums (int32 sums in exact mode)
+  long long b_lo[SC_SIZE], b_hi[SC_SIZE];   // min / max of the height (order-preserving int64 keys)
   unsigned b_cnt[SC_SIZE];
-  int ibc[4];
+  double scratch[11 * 32];
+  double bc[16];                            // mean + eigenvectors
+  int ibc[4];                               // [emin, -, float sum bits, -]
+  int next_chunk;
 };
-static_assert(sizeof(ScSmem) <= 113 * 1024, "two CTAs per SM");
-
-__device__ __forceinline__ uint32_t gen_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ bool gen_mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-
-// Thread 0: start the bulk copy of the 16-byte aligned part of a scan's xyz block.  Element j of the
-// scan (double index) lands at pts[j + shift], shift = 1 when the block starts at an address that
-// is 8 mod 16; the unaligned head / tail element is copied by gen_fix_edges.
-__device__ __forceinline__ void gen_issue_load(ScSmem &S, const double *g, int nst) {
-  const uintptr_t addr = reinterpret_cast<uintptr_t>(g);
-  const int shift = (int)((addr >> 3) & 1);
-  const int ne = 3 * nst;
-  const int e0 = ne > 0 ? shift : 0;
-  const uint32_t bytes = ne > e0 ? (uint32_t)(((ne - e0) * 8) & ~15) : 0u;
-  const uint32_t bar = gen_smem_u32(&S.mbar);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of pts vs the async write
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-  if (bytes)
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     gen_smem_u32(&S.pts[e0 + shift])),
-                 "l"(g + e0), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
-__device__ __forceinline__ void gen_fix_edges(ScSmem &S, const double *g, int nst) {
-  const uintptr_t addr = reinterpret_cast<uintptr_t>(g);
-  const int shift = (int)((addr >> 3) & 1);
-  const int ne = 3 * nst;
-  if (ne == 0) return;
-  const int e0 = shift;
-  const int bulk_e = ne > e0 ? (((ne - e0) * 8) & ~15) / 8 : 0;
-  if (threadIdx.x == 0 && e0 == 1) S.pts[shift] = g[0];
-  if (threadIdx.x == 32 && e0 + bulk_e < ne) S.pts[shift + ne - 1] = g[ne - 1];  // at most one tail element
-}
+static_assert(sizeof(ScSmem) * GEN_CTAS_PER_SM <= 200 * 1024, "four CTAs per SM");
 
 __device__ __forceinline__ void gen_prefetch_l2(const void *p, int64_t bytes) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(p);
@@ -171,223 +132,240 @@ __device__ __noinline__ void sym_eig3_fast(const double *cov6, double *bc) {
   bc[14] = w2;
 }
 
-// SC.cpp:33-44 for one point already in the PCA frame: flat bin index or -1 (dropped).
-// Fast path: fp32.  Error budget of the fp32 sector coordinate tf (<= 60.5): inputs rounded to fp32
-// (1.2e-7 rad), atan2f (<= 3 ulp at pi = 7.2e-7), the +pi add (3.3e-7), the multiply by 60/2pi
-// (x 9.55) and its rounding (1.9e-6 + 3.6e-6): < 2e-5.  Ring coordinate rf: relative 3e-7 of a value
-// < 1199: accepted only below 64 where that is < 2e-5.  A point closer than BIN_GUARD to an edge, or
-// anything unusual (NaN, huge), takes the fp64 expression of the reference.
-__device__ __forceinline__ int bin_of_point(double yp, double zp, double S_res_inv, double R_res_inv, float S_f,
-                                            float R_f) {
-  const float yf = (float)yp, zf = (float)zp;
-  const float tf = (atan2f(zf, yf) + 3.14159274f) * S_f;
-  const float rf = sqrtf(yf * yf + zf * zf) * R_f;
-  const float ft = floorf(tf), fr = floorf(rf);
-  const float dt = tf - ft, dr = rf - fr;
-  const bool safe = dt > BIN_GUARD && dt < 1.0f - BIN_GUARD && dr > BIN_GUARD && dr < 1.0f - BIN_GUARD &&
-                    tf > 0.0f && tf < 60.0f && rf < 64.0f;
-  int si, ri;
-  if (safe) {
-    si = (int)ft;
-    ri = (int)fr;
-  } else {
-    const double PI = 3.14159265358979323846;  // M_PI, SC.cpp:37
-    const double ang = (atan2(zp, yp) + PI) * S_res_inv;
-    const double rad = sqrt(yp * yp + zp * zp) * R_res_inv;
-    // `idx >= getSignatureSize()` (SC.cpp:42) is the ONLY range check: a point with ri >= 20 and
-    // si < 59 aliases into the next sector.  NaN / huge values give INT_MIN on x86 and
-    // are dropped there; dropped explicitly here.
-    if (!(rad < (double)SC_SIZE) || !(ang < 64.0)) return -1;
-    si = (int)floor(ang);
-    ri = (int)floor(rad);
-  }
-  const int idx = si * SC_NUM_R + ri;
+// SC.cpp:33-44 in fp64, exactly the reference's expression: flat bin index or -1 (dropped).
+__device__ __noinline__ int bin_of_point_exact(double yp, double zp, double S_res_inv, double R_res_inv) {
+  const double PI = 3.14159265358979323846;  // M_PI, SC.cpp:37
+  const double ang = (atan2(zp, yp) + PI) * S_res_inv;
+  const double rad = sqrt(yp * yp + zp * zp) * R_res_inv;
+  // `idx >= getSignatureSize()` (SC.cpp:42) is the ONLY range check: a point with ri >= 20 and
+  // si < 59 aliases into the next sector.  NaN / huge values give INT_MIN on x86 and
+  // are dropped there; dropped explicitly here.
+  if (!(rad < (double)SC_SIZE) || !(ang < 64.0)) return -1;
+  const int idx = (int)floor(ang) * SC_NUM_R + (int)floor(rad);
   return (unsigned)idx >= (unsigned)SC_SIZE ? -1 : idx;
 }
 
-// point i of the scan: staged part from shared memory, the rest (scans above GEN_CAP) from global / L2
-__device__ __forceinline__ void gen_point(const double *sp, const double *g, int nst, int i, double &x, double &y,
-                                          double &z) {
-  if (i < nst) {
-    x = sp[3 * i + 0];
-    y = sp[3 * i + 1];
-    z = sp[3 * i + 2];
-  } else {
-    x = g[3 * (size_t)i + 0];
-    y = g[3 * (size_t)i + 1];
-    z = g[3 * (size_t)i + 2];
+// The bin of a point already in the PCA frame.  Fast path in fp32: the sector coordinate comes from
+// fast_turns (common.cuh, |error| < 2e-7 turns -> 1.2e-5 sectors, plus the fp32 rounding of the inputs
+// 1.1e-6 and of the final multiply 3.8e-6), the ring coordinate from r2 * rsqrt(r2) (relative 3e-7 of a
+// value accepted only below 64: < 2e-5).  A point closer than BIN_GUARD = 2.5e-4 to a bin edge, or
+// anything unusual (NaN, origin, huge), takes the fp64 expression of the reference, so the bins are
+// exactly those of SC.cpp:37-39.
+__device__ __forceinline__ int bin_of_point(double yp, double zp, double S_res_inv, double R_res_inv, float R_f) {
+  const float yf = (float)yp, zf = (float)zp;
+  const float tf = fast_turns(zf, yf) * (float)SC_NUM_S;
+  const float r2 = __fmaf_rn(yf, yf, zf * zf);
+  const float rf = r2 * rsqrtf(r2) * R_f;
+  const float ft = floorf(tf), fr = floorf(rf);
+  const float dt = tf - ft, dr = rf - fr;
+  const bool safe = fminf(dt, dr) > BIN_GUARD && fmaxf(dt, dr) < 1.0f - BIN_GUARD && tf < (float)SC_NUM_S && rf < 64.0f;
+  if (!safe) return bin_of_point_exact(yp, zp, S_res_inv, R_res_inv);
+  const int idx = (int)ft * SC_NUM_R + (int)fr;
+  return (unsigned)idx >= (unsigned)SC_SIZE ? -1 : idx;
+}
+
+// global loads with an L2 eviction-priority hint: the moments pass asks L2 to keep the scan
+// (evict_last), the scatter pass that follows is its last use (evict_first)
+__device__ __forceinline__ double ldg_hint(const double *p, uint64_t pol) {
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ldg_hint(const float *p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
+// min / max on the order-preserving int64 keys: the value read for the pre-check seeds the CAS loop
+__device__ __forceinline__ void smem_min_i64(long long *addr, long long key) {
+  long long cur = *addr;
+  while (key < cur) {
+    const long long prev = (long long)atomicCAS(reinterpret_cast<unsigned long long *>(addr),
+                                                (unsigned long long)cur, (unsigned long long)key);
+    if (prev == cur) break;
+    cur = prev;
+  }
+}
+__device__ __forceinline__ void smem_max_i64(long long *addr, long long key) {
+  long long cur = *addr;
+  while (key > cur) {
+    const long long prev = (long long)atomicCAS(reinterpret_cast<unsigned long long *>(addr),
+                                                (unsigned long long)cur, (unsigned long long)key);
+    if (prev == cur) break;
+    cur = prev;
   }
 }
 
-__global__ void __launch_bounds__(GEN_THREADS, 2)
+__global__ void __launch_bounds__(GEN_THREADS, GEN_CTAS_PER_SM)
 sc_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ inten,
                    const int64_t *__restrict__ off, int nscan, double S_res_inv, double R_res_inv,
-                   double *__restrict__ hist) {
+                   double *__restrict__ hist, int flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScSmem &S = *reinterpret_cast<ScSmem *>(smem_raw);
-  const float S_f = (float)S_res_inv, R_f = (float)R_res_inv;
-  const uint32_t bar = gen_smem_u32(&S.mbar);
+  const float R_f = (float)R_res_inv;
   int *b_isum = reinterpret_cast<int *>(S.b_sum);
-
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if ((int)blockIdx.x < nscan) {
-      const int64_t p0 = off[blockIdx.x];
-      const int n0 = (int)(off[blockIdx.x + 1] - p0);
-      gen_issue_load(S, xyz + 3 * p0, n0 < GEN_CAP ? n0 : GEN_CAP);
-    }
+  uint64_t pol_keep, pol_drop;
+  if (flags & 4) {
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_drop));
+  } else {
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
+    pol_drop = pol_keep;
   }
-  __syncthreads();
 
-  uint32_t phase = 0;
+  for (int b = threadIdx.x; b < SC_SIZE; b += GEN_THREADS) {
+    S.b_sum[b] = 0.0;
+    S.b_cnt[b] = 0u;
+    S.b_lo[b] = LLONG_MAX;
+    S.b_hi[b] = LLONG_MIN;
+  }
+  if (threadIdx.x == 0) S.next_chunk = 0;
+
   for (int scan = blockIdx.x; scan < nscan; scan += gridDim.x) {
     const int64_t p0 = off[scan];
     const int n = (int)(off[scan + 1] - p0);
     const double *g = xyz + 3 * p0;
     const float *gi = inten + p0;
-    const int nst = n < GEN_CAP ? n : GEN_CAP;
-    const int shift = (int)((reinterpret_cast<uintptr_t>(g) >> 3) & 1);
-    const double *sp = S.pts + shift;
 
-    // pull the next scan of this CTA towards L2 while this one is processed
-    const int nxt = scan + gridDim.x;
-    if (threadIdx.x == 64 && nxt < nscan) {
-      const int64_t q0 = off[nxt];
-      const int64_t nn = off[nxt + 1] - q0;
-      gen_prefetch_l2(xyz + 3 * q0, nn * 24);
-      gen_prefetch_l2(inten + q0, nn * 4);
+    // ---- pass 1 (HBM): moments about the scan's first point o, d = p - o:
+    //   s11 = [sum d (3), sum d d^T (6), sum v, sum |v|]
+    double s11[11];
+#pragma unroll
+    for (int k = 0; k < 11; k++) s11[k] = 0.0;
+    int emin = 1 << 20;
+    double ox = 0.0, oy = 0.0, oz = 0.0;
+    if (n > 0) {
+      ox = g[0];
+      oy = g[1];
+      oz = g[2];
     }
-
-    // ---- pass 1: mean (pts_align.h:10-18) and the intensity sums for SC.cpp:60-64
-    double s5[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    int emin = 1 << 20, bad = 0;
+    if (threadIdx.x == 0) S.ibc[0] = 1 << 20;
+#pragma unroll 4
     for (int i = threadIdx.x; i < n; i += GEN_THREADS) {
-      const float v = gi[i];
-      s5[3] += (double)v;
-      s5[4] += fabs((double)v);
+      const float v = ldg_hint(gi + i, pol_keep);
+      const double x = ldg_hint(g + 3 * (size_t)i + 0, pol_keep) - ox;
+      const double y = ldg_hint(g + 3 * (size_t)i + 1, pol_keep) - oy;
+      const double z = ldg_hint(g + 3 * (size_t)i + 2, pol_keep) - oz;
+      s11[0] += x;
+      s11[1] += y;
+      s11[2] += z;
+      s11[3] = fma(x, x, s11[3]);
+      s11[4] = fma(x, y, s11[4]);
+      s11[5] = fma(x, z, s11[5]);
+      s11[6] = fma(y, y, s11[6]);
+      s11[7] = fma(y, z, s11[7]);
+      s11[8] = fma(z, z, s11[8]);
+      s11[9] += (double)v;
+      s11[10] += fabs((double)v);
+      // lowest set bit of v as a power of two (denormals come out one too small, which only makes the
+      // exactness test below more conservative; inf / NaN poison s11[10])
       const unsigned b = __float_as_uint(v);
-      const unsigned ex = (b >> 23) & 0xffu, man = b & 0x7fffffu;
-      if (ex == 0xffu) bad = 1;
-      if (ex != 0 || man != 0) {
-        const unsigned m = ex ? (man | 0x800000u) : man;
-        const int e = (ex ? (int)ex - 150 : -149) + (__ffs(m) - 1);
-        emin = e < emin ? e : emin;
-      }
-    }
-    if (threadIdx.x == 0) {
-      S.ibc[0] = 1 << 20;
-      S.ibc[1] = 0;
-    }
-    while (!gen_mbar_try(bar, phase)) {
-    }
-    phase ^= 1;
-    gen_fix_edges(S, g, nst);
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += GEN_THREADS) {
-      double x, y, z;
-      gen_point(sp, g, nst, i, x, y, z);
-      s5[0] += x;
-      s5[1] += y;
-      s5[2] += z;
+      const int e = (int)((b >> 23) & 0xffu) - 151 + __ffs(b | 0x800000u);
+      emin = (v != 0.0f && e < emin) ? e : emin;
     }
     emin = __reduce_min_sync(0xffffffffu, emin);
-    bad = __any_sync(0xffffffffu, bad);
-    if ((threadIdx.x & 31) == 0) {
-      atomicMin(&S.ibc[0], emin);
-      if (bad) atomicOr(&S.ibc[1], 1);
-    }
-    block_sum<5>(s5, S.scratch);
-    const double mx = s5[0] / (double)n, my = s5[1] / (double)n, mz = s5[2] / (double)n;
+    __syncthreads();  // ibc initialised, bins and scratch free
+    if ((threadIdx.x & 31) == 0) atomicMin(&S.ibc[0], emin);
+    block_sum<11>(s11, S.scratch);
     emin = S.ibc[0];
     // every partial sum of the sequential float loop is exact -> the float sum is the exact sum
-    const bool exact = !S.ibc[1] && (emin == (1 << 20) || s5[4] < ldexp(1.0, 24 + emin));
+    const bool exact = emin == (1 << 20) ? s11[10] == 0.0 : s11[10] < ldexp(1.0, 24 + emin);
 
-    // ---- pass 2: scatter matrix of the centred points (pts_align.h:21-30)
-    double c6[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int i = threadIdx.x; i < n; i += GEN_THREADS) {
-      double x, y, z;
-      gen_point(sp, g, nst, i, x, y, z);
-      x -= mx;
-      y -= my;
-      z -= mz;
-      c6[0] += x * x;
-      c6[1] += x * y;
-      c6[2] += x * z;
-      c6[3] += y * y;
-      c6[4] += y * z;
-      c6[5] += z * z;
-    }
-    __syncthreads();  // scratch reuse
-    block_sum<6>(c6, S.scratch);
-
-    // ---- eigen-solve on one thread (pts_align.h:31-34); the others clear the bins meanwhile
-    if (threadIdx.x == 0) {
-      S.bc[0] = mx;
-      S.bc[1] = my;
-      S.bc[2] = mz;
+    // ---- serial jobs: thread 0 solves the eigenproblem (pts_align.h:31-34), thread 32 replays the order
+    // dependent float sum of SC.cpp:60-63 when it is not provably exact.  The other CTAs of the SM hide this.
+    if (threadIdx.x == 0 && n > 0) {
+      // mean = o + sum(d)/n (pts_align.h:10-18); scatter matrix = sum(d d^T) - sum(d) sum(d)^T / n (pts_align.h:21-30)
+      const double dn = (double)n;
+      const double mx = s11[0] / dn, my = s11[1] / dn, mz = s11[2] / dn;
+      double c6[6] = {s11[3] - s11[0] * mx, s11[4] - s11[0] * my, s11[5] - s11[0] * mz,
+                      s11[6] - s11[1] * my, s11[7] - s11[1] * mz, s11[8] - s11[2] * mz};
+      S.bc[0] = ox + mx;
+      S.bc[1] = oy + my;
+      S.bc[2] = oz + mz;
       sym_eig3_fast(c6, S.bc);
-    } else if (threadIdx.x == 32) {
-      if (!exact) {  // replay the sequential float loop of SC.cpp:60-63 (order dependent rounding)
-        float a = 0.0f;
+    } else if (threadIdx.x == 32 && !exact) {
+      float a = 0.0f;
 #pragma unroll 16
-        for (int i = 0; i < n; i++) a += gi[i];
-        reinterpret_cast<float *>(S.ibc)[2] = a;
-      }
-    } else {
-      for (int b = threadIdx.x - (threadIdx.x > 32 ? 2 : 1); b < SC_SIZE; b += GEN_THREADS - 2) {
-        S.b_sum[b] = 0.0;
-        S.b_cnt[b] = 0u;
-        S.b_lo[b] = LLONG_MAX;
-        S.b_hi[b] = LLONG_MIN;
+      for (int i = 0; i < n; i++) a += gi[i];
+      S.ibc[2] = __float_as_int(a);
+    } else if (threadIdx.x == 64 && (flags & 1)) {  // pull the next scan of this CTA towards L2
+      const int nxt = scan + gridDim.x;
+      if (nxt < nscan) {
+        const int64_t q0 = off[nxt];
+        const int64_t nn = off[nxt + 1] - q0;
+        gen_prefetch_l2(xyz + 3 * q0, nn * 24);
+        gen_prefetch_l2(inten + q0, nn * 4);
       }
     }
     __syncthreads();
-    const float ave = (exact ? (float)s5[3] : reinterpret_cast<float *>(S.ibc)[2]) / (float)n;  // SC.cpp:64
-    const float iscale = exact && emin != (1 << 20) ? (float)ldexp(1.0, -emin) : 0.0f;
-    const double unscale = exact && emin != (1 << 20) ? ldexp(1.0, emin) : 0.0;
 
-    // ---- SC.cpp:29-57
-    for (int i = threadIdx.x; i < n; i += GEN_THREADS) {
-      const float it = gi[i];
-      double x, y, z, hx, yp, zp;
-      gen_point(sp, g, nst, i, x, y, z);
-      pca_rotate(S.bc, x, y, z, hx, yp, zp);
-      const int idx = bin_of_point(yp, zp, S_res_inv, R_res_inv, S_f, R_f);
-      if (idx < 0) continue;
-      atomicAdd(&S.b_cnt[idx], 1u);
-      if (exact)
-        atomicAdd(&b_isum[2 * idx], (int)(it * iscale));  // exact integer multiple of 2^emin, |sum| < 2^24
-      else
-        atomicAdd(&S.b_sum[idx], (double)it);
-      const long long key = f64_key(hx);
-      if (key < S.b_lo[idx]) atomicMin(&S.b_lo[idx], key);
-      if (key > S.b_hi[idx]) atomicMax(&S.b_hi[idx], key);
-    }
-    __syncthreads();
-
-    // the point buffer is free: start the next scan's copy before writing this one's signature
-    if (threadIdx.x == 0 && nxt < nscan) {
-      const int64_t q0 = off[nxt];
-      const int nn = (int)(off[nxt + 1] - q0);
-      gen_issue_load(S, xyz + 3 * q0, nn < GEN_CAP ? nn : GEN_CAP);
-    }
-
-    // ---- SC.cpp:67-75
-    double *row = hist + (size_t)scan * 2 * SC_SIZE;
-    for (int b = threadIdx.x; b < SC_SIZE; b += GEN_THREADS) {
-      const unsigned c = S.b_cnt[b];
-      double st = 0.0, iv = 0.0;
-      if (c) {
-        st = f64_unkey(S.b_hi[b]) - f64_unkey(S.b_lo[b]);
-        const double sum = exact ? (double)b_isum[2 * b] * unscale : S.b_sum[b];
-        const double mean = sum / (double)c;
-        iv = mean > (double)ave ? 1.0 : 0.0;
+    // ---- pass 2 (L2): SC.cpp:29-57.  Backwards, so that the lines pass 1 touched last are re-read first.
+    {
+      const float iscale = exact && emin != (1 << 20) ? (float)ldexp(1.0, -emin) : 0.0f;
+      // chunks of GEN_CHUNK points are handed out by a shared counter: warps that hit the fp64 path or
+      // contended bins take fewer chunks, so all warps reach the barrier together
+      const int nchunk = (n + GEN_CHUNK - 1) / GEN_CHUNK;
+      const int lane = threadIdx.x & 31;
+      for (;;) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&S.next_chunk, 1);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= nchunk) break;
+        if (flags & 2) c = nchunk - 1 - c;
+#pragma unroll
+        for (int r = 0; r < GEN_CHUNK / 32; r++) {
+          const int i = c * GEN_CHUNK + r * 32 + lane;
+          if (i >= n) continue;
+          const float it = ldg_hint(gi + i, pol_drop);
+          // pts_align.h:37-45 (fused multiply-adds: the frame itself already differs from the oracle's in the last bits)
+          const double x = ldg_hint(g + 3 * (size_t)i + 0, pol_drop) - S.bc[0];
+          const double y = ldg_hint(g + 3 * (size_t)i + 1, pol_drop) - S.bc[1];
+          const double z = ldg_hint(g + 3 * (size_t)i + 2, pol_drop) - S.bc[2];
+          const double hx = fma(z, S.bc[9], fma(y, S.bc[6], x * S.bc[3]));
+          const double yp = fma(z, S.bc[10], fma(y, S.bc[7], x * S.bc[4]));
+          const double zp = fma(z, S.bc[11], fma(y, S.bc[8], x * S.bc[5]));
+          const int idx = bin_of_point(yp, zp, S_res_inv, R_res_inv, R_f);
+          if (idx >= 0) {
+            atomicAdd(&S.b_cnt[idx], 1u);
+            if (exact)
+              atomicAdd(&b_isum[2 * idx], (int)(it * iscale));  // exact integer multiple of 2^emin, |sum| < 2^24
+            else
+              atomicAdd(&S.b_sum[idx], (double)it);
+            const long long key = f64_key(hx);
+            smem_min_i64(&S.b_lo[idx], key);
+            smem_max_i64(&S.b_hi[idx], key);
+          }
+        }
       }
-      row[b] = st;
-      row[SC_SIZE + b] = iv;
     }
     __syncthreads();
+
+    // ---- SC.cpp:60-75: binarise against the float average, write the signature, clear the bins
+    {
+      const float fsum = exact ? (float)s11[9] : __int_as_float(S.ibc[2]);
+      const float ave = fsum / (float)n;  // SC.cpp:64
+      const double unscale = exact && emin != (1 << 20) ? ldexp(1.0, emin) : 0.0;
+      double *row = hist + (size_t)scan * 2 * SC_SIZE;
+      for (int b = threadIdx.x; b < SC_SIZE; b += GEN_THREADS) {
+        const unsigned c = S.b_cnt[b];
+        double st = 0.0, iv = 0.0;
+        if (c) {
+          st = f64_unkey(S.b_hi[b]) - f64_unkey(S.b_lo[b]);
+          const double sum = exact ? (double)b_isum[2 * b] * unscale : S.b_sum[b];
+          const double mean = sum / (double)c;
+          iv = mean > (double)ave ? 1.0 : 0.0;
+          S.b_sum[b] = 0.0;
+          S.b_cnt[b] = 0u;
+          S.b_lo[b] = LLONG_MAX;
+          S.b_hi[b] = LLONG_MIN;
+        }
+        row[b] = st;
+        row[SC_SIZE + b] = iv;
+      }
+      if (threadIdx.x == 0) S.next_chunk = 0;
+    }
+    // no barrier needed here: the next scan touches the bins / ibc / scratch only after its first barrier
   }
 }
 
@@ -436,9 +414,12 @@ cudaError_t launch_sc_generate(const double *xyz, const float *inten, const int6
   if (e != cudaSuccess) return e;
   const double S_res_inv = SC_NUM_S / (2.0 * 3.14159265358979323846);  // SC.cpp:6
   const double R_res_inv = SC_NUM_R / max_rho;                          // SC.cpp:7
-  int grid = nscan < 2 * num_sms ? nscan : 2 * num_sms;
+  int per_sm = GEN_CTAS_PER_SM, flags = 2;
+  if (const char *e = getenv("SODSO_GEN_CTAS")) per_sm = atoi(e);
+  if (const char *e = getenv("SODSO_GEN_FLAGS")) flags = atoi(e);
+  int grid = nscan < per_sm * num_sms ? nscan : per_sm * num_sms;
   sc_generate_kernel<<<grid, GEN_THREADS, sizeof(ScSmem), st>>>(xyz, inten, off, nscan, S_res_inv,
-                                                                R_res_inv, hist);
+                                                                R_res_inv, hist, flags);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
