@@ -122,6 +122,17 @@ int sodso_loop_top1(sodso_ctx *ctx, int type, const double *hist1, int m, const 
                     int n, int mask_width, double p_weight, int32_t *idx, double *score,
                     double *d_p_at, double *d_i_at);
 
+/* test_sc.cpp:36-57 followed by run_test('sc', hist, hist, ...) (run_test.m:25-57; the KITTI self-match of
+ * test_kitti.m:28) in one call: scans in, loop candidates out.  hist (optional, nscan x 2400) receives the
+ * signatures.  When the point buffers are host memory the scans are streamed: 512-scan chunks are copied on
+ * a second stream while earlier chunks are binned and matched (new queries x all DB rows so far, old queries
+ * x new DB rows), so the transfer hides behind the tensor-core work.  Results are identical to
+ * sodso_sc_generate + sodso_loop_top1. */
+int sodso_sc_scans_to_loops(sodso_ctx *ctx, const double *xyz, const float *inten,
+                            const int64_t *scan_off, int nscan, double max_rho, int mask_width,
+                            double p_weight, double *hist, int32_t *idx, double *score,
+                            double *d_p_at, double *d_i_at);
+
 /* ---- resident, row-sharded signature database ------------------------ */
 /* A shard holds n_local consecutive DB signatures whose first row has global index
  * global_row0; the signatures stay resident in HBM in MMA operand format. */

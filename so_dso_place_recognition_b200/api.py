@@ -268,6 +268,29 @@ def run_test(type, hist1, hist2, mask_width, p_weight=2.0, want_channels=False, 
     return (idx, score, dpa, dia) if want_channels else (idx, score)
 
 
+def sc_scans_to_loops(xyz, inten, scan_off, mask_width, p_weight=2.0, max_rho=45.0, want_hist=False, ctx=None):
+    """test_sc.cpp:36-57 + run_test('sc', hist, hist, ...) (run_test.m:25-57, self-match as in test_kitti.m:28)
+    in one call: scans in -> (diff_idx 0-based int32[n], diff_v[n] [, history_sc]).  Host (numpy / pinned torch)
+    point buffers are streamed to the GPU chunk by chunk, overlapped with binning and matching."""
+    if _is_torch(xyz) and not xyz.is_cuda:      # pinned host tensors: pass as host pointers
+        dev_like = None
+    else:
+        dev_like = xyz if _is_torch(xyz) else None
+    xyz = _prep(xyz, np.float64, "float64")
+    inten = _prep(inten, np.float32, "float32")
+    scan_off = _prep(scan_off, np.int64, "int64")
+    n = int(scan_off.shape[0]) - 1
+    c = _ctx_for(*( [dev_like] if dev_like is not None else []), ctx=ctx)
+    ref = dev_like if dev_like is not None else np.empty(0)
+    idx = _empty_like_kind(ref, (n,), np.int32, "int32")
+    score = _empty_like_kind(ref, (n,), np.float64, "float64")
+    hist = _empty_like_kind(ref, (n, 2 * SC_SIZE), np.float64, "float64") if want_hist else None
+    N.check(N.lib().sodso_sc_scans_to_loops(c.handle, _ptr(xyz), _ptr(inten), _ptr(scan_off), n, float(max_rho),
+                                            int(mask_width), float(p_weight), _ptr(hist), _ptr(idx), _ptr(score),
+                                            None, None))
+    return (idx, score, hist) if want_hist else (idx, score)
+
+
 # ----------------------------------------------------------------------------------------------
 # resident, row-sharded database (SURVEY.md §8e)
 # ----------------------------------------------------------------------------------------------

@@ -1,5 +1,6 @@
 // extern "C" surface of libsodso_pr.so (include/sodso_pr.h): context, host<->HBM staging,
 // call sequencing.  All compute is in the kernel translation units; there is no CPU path.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -55,6 +56,7 @@ struct sodso_ctx {
   int device = 0;
   int num_sms = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // host -> HBM chunk copies of the streamed path
   int algo = SODSO_ALGO_TC;
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -331,6 +333,7 @@ void sodso_ctx_destroy(sodso_ctx *c) {
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->own_stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
 }
 
@@ -495,6 +498,9 @@ int sodso_fuse_top1(sodso_ctx *c, const double *d_p, const double *d_i, int m, i
   return sync_ctx(c);
 }
 
+static int fuse_top1_tail(sodso_ctx *c, int m, int n, int mask_width, double p_weight, int32_t *idx,
+                          double *score, double *d_p_at, double *d_i_at);
+
 int sodso_loop_top1(sodso_ctx *c, int type, const double *hist1, int m, const double *hist2, int n,
                     int mask_width, double p_weight, int32_t *idx, double *score, double *d_p_at,
                     double *d_i_at) {
@@ -510,6 +516,13 @@ int sodso_loop_top1(sodso_ctx *c, int type, const double *hist1, int m, const do
   SODSO_CUDA_CHECK(c->dp32.reserve(cnt * 4));
   SODSO_CUDA_CHECK(c->di32.reserve(cnt * 4));
   if ((rc = match_to_device(c, type, hist1, m, hist2, n, c->dp32.as<float>(), c->di32.as<float>()))) return rc;
+  return fuse_top1_tail(c, m, n, mask_width, p_weight, idx, score, d_p_at, d_i_at);
+}
+
+// shared tail of sodso_loop_top1 / sodso_sc_scans_to_loops: row statistics, fusion, top-1, outputs
+static int fuse_top1_tail(sodso_ctx *c, int m, int n, int mask_width, double p_weight, int32_t *idx,
+                          double *score, double *d_p_at, double *d_i_at) {
+  int rc;
   SODSO_CUDA_CHECK(c->stats.reserve((size_t)m * 4 * sizeof(double)));
   SODSO_CUDA_CHECK(launch_row_stats(c->dp32.as<float>(), c->di32.as<float>(), m, n, n, c->stats.as<double>(),
                                     c->stream, &c->launches));
@@ -536,6 +549,131 @@ int sodso_loop_top1(sodso_ctx *c, int type, const double *hist1, int m, const do
   else
     std::memcpy(idx, t32.data(), (size_t)m * sizeof(int32_t));
   return SODSO_OK;
+}
+
+int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten, const int64_t *off, int nscan,
+                            double max_rho, int mask_width, double p_weight, double *hist, int32_t *idx,
+                            double *score, double *d_p_at, double *d_i_at) {
+  CTX_CHECK(c);
+  if (nscan <= 0 || !xyz || !inten || !off || !idx || !score) {
+    set_error("bad scans_to_loops arguments");
+    return SODSO_E_ARG;
+  }
+  if (c->algo != SODSO_ALGO_TC) {
+    set_error("sodso_sc_scans_to_loops needs the tensor-core match (SODSO_ALGO_TC)");
+    return SODSO_E_STATE;
+  }
+  int rc;
+  int64_t total = 0;
+  if ((rc = check_offsets_host(off, nscan, &total))) return rc;
+  const bool host_pts = !is_device_ptr(xyz), host_int = !is_device_ptr(inten), host_off = !is_device_ptr(off);
+  // scans are streamed in chunks (a multiple of the 256-row DB tile) when the points live in host memory
+  const int CH = 512;
+  const bool streamed = host_pts && host_int && host_off && nscan >= 4 * CH;
+  const int nchunk = streamed ? (nscan + CH - 1) / CH : 1;
+
+  const double *xd = xyz;
+  const float *id = inten;
+  const int64_t *od = off;
+  if (host_pts) {
+    SODSO_CUDA_CHECK(c->in_xyz.reserve((size_t)total * 3 * sizeof(double)));
+    xd = c->in_xyz.as<double>();
+  }
+  if (host_int) {
+    SODSO_CUDA_CHECK(c->in_inten.reserve((size_t)total * sizeof(float)));
+    id = c->in_inten.as<float>();
+  }
+  if ((rc = stage_in(c, off, (size_t)nscan + 1, c->in_off, &od))) return rc;
+  double *hd;
+  const size_t hcnt = (size_t)nscan * 2 * SC_SIZE;
+  if (hist && is_device_ptr(hist)) {
+    hd = hist;
+  } else {  // host output, or no signature output requested: they are still needed on the device
+    SODSO_CUDA_CHECK(c->out_hist.reserve(hcnt * sizeof(double) + 16));
+    hd = c->out_hist.as<double>();
+  }
+  const size_t cnt = (size_t)nscan * nscan;
+  SODSO_CUDA_CHECK(c->dp32.reserve(cnt * 4));
+  SODSO_CUDA_CHECK(c->di32.reserve(cnt * 4));
+  SODSO_CUDA_CHECK(c->db_op.reserve(sc_tc_db_bytes(nscan)));
+  SODSO_CUDA_CHECK(c->q_op.reserve(sc_tc_query_bytes(nscan)));
+  SODSO_CUDA_CHECK(launch_sc_tc_clear_flags(c->db_op.p, c->stream));
+  SODSO_CUDA_CHECK(launch_sc_tc_clear_flags(c->q_op.p, c->stream));
+  float *dp = c->dp32.as<float>(), *di = c->di32.as<float>();
+
+  std::vector<cudaEvent_t> evs;
+  if (streamed) {
+    if (!c->copy_stream) SODSO_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    evs.resize(nchunk, nullptr);
+    // the staging buffers may still be read by earlier work on the compute stream
+    cudaEvent_t e0;
+    SODSO_CUDA_CHECK(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+    SODSO_CUDA_CHECK(cudaEventRecord(e0, c->stream));
+    SODSO_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, e0, 0));
+    cudaEventDestroy(e0);
+    for (int k = 0; k < nchunk; k++) {
+      const int s0 = k * CH, s1 = std::min(nscan, s0 + CH);
+      const int64_t p0 = off[s0], p1 = off[s1];
+      if (p1 > p0) {
+        SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_xyz.as<double>() + 3 * p0, xyz + 3 * p0,
+                                         (size_t)(p1 - p0) * 3 * sizeof(double), cudaMemcpyHostToDevice,
+                                         c->copy_stream));
+        SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_inten.as<float>() + p0, inten + p0, (size_t)(p1 - p0) * sizeof(float),
+                                         cudaMemcpyHostToDevice, c->copy_stream));
+      }
+      SODSO_CUDA_CHECK(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
+      SODSO_CUDA_CHECK(cudaEventRecord(evs[k], c->copy_stream));
+    }
+  } else {
+    if (host_pts)
+      SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_xyz.p, xyz, (size_t)total * 3 * sizeof(double), cudaMemcpyHostToDevice,
+                                       c->stream));
+    if (host_int)
+      SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_inten.p, inten, (size_t)total * sizeof(float), cudaMemcpyHostToDevice,
+                                       c->stream));
+  }
+
+  const int n_pad = sc_tc_db_rows_padded(nscan), m_pad = sc_tc_query_rows_padded(nscan);
+  rc = SODSO_OK;
+  c->kname = "sc_match_tc_kernel";
+  c->ev_valid = false;
+  for (int k = 0; k < nchunk && rc == SODSO_OK; k++) {
+    const int s0 = streamed ? k * CH : 0, s1 = streamed ? std::min(nscan, s0 + CH) : nscan;
+    const bool last = k == nchunk - 1;
+    cudaError_t e = cudaSuccess;
+    if (streamed) e = cudaStreamWaitEvent(c->stream, evs[k], 0);
+    // test_sc.cpp:40-57 for the scans of this chunk
+    if (e == cudaSuccess)
+      e = launch_sc_generate(xd, id, od + s0, s1 - s0, max_rho, hd + (size_t)s0 * 2 * SC_SIZE, c->num_sms, c->stream,
+                             &c->launches);
+    // their rows of both match operands (the last chunk also writes the zero padding)
+    if (e == cudaSuccess)
+      e = launch_sc_tc_prep_db_rows(hd, nscan, s0, last ? n_pad : s1, c->db_op.p, c->stream, &c->launches);
+    if (e == cudaSuccess)
+      e = launch_sc_tc_prep_query_rows(hd, nscan, s0, last ? m_pad : s1, c->q_op.p, c->stream, &c->launches);
+    // processSC.m:22-33 for every (query, DB) pair that has become available: new queries x all DB rows so far,
+    // old queries x new DB rows
+    if (!streamed && e == cudaSuccess) c->ev_valid = cudaEventRecord(c->ev0, c->stream) == cudaSuccess;
+    if (e == cudaSuccess)
+      e = launch_sc_match_tc_block(c->q_op.p, nscan, s0, s1, c->db_op.p, nscan, 0, s1, dp, di, nscan, c->num_sms,
+                                   c->stream, &c->launches);
+    if (e == cudaSuccess && s0 > 0)
+      e = launch_sc_match_tc_block(c->q_op.p, nscan, 0, s0, c->db_op.p, nscan, s0, s1, dp, di, nscan, c->num_sms,
+                                   c->stream, &c->launches);
+    if (!streamed && c->ev_valid) c->ev_valid = cudaEventRecord(c->ev1, c->stream) == cudaSuccess;
+    if (e != cudaSuccess) {
+      set_error(std::string("scans_to_loops: ") + cudaGetErrorString(e));
+      rc = SODSO_E_CUDA;
+    }
+  }
+  for (cudaEvent_t ev : evs)
+    if (ev) cudaEventDestroy(ev);
+  if (rc) {
+    cudaStreamSynchronize(c->stream);
+    return rc;
+  }
+  if (hist && hist != hd && (rc = finish_out(c, hist, hcnt, hd))) return rc;
+  return fuse_top1_tail(c, nscan, nscan, mask_width, p_weight, idx, score, d_p_at, d_i_at);
 }
 
 // ---- resident row-sharded database ---------------------------------------------------------

@@ -91,6 +91,17 @@ cudaError_t launch_sc_tc_prep_db(const double *hist, int n, void *db_buf, cudaSt
                                  int64_t *launches);
 cudaError_t launch_sc_tc_prep_query(const double *hist, int m, void *q_buf, cudaStream_t st,
                                     int64_t *launches);
+// streamed / blocked variants: operands are filled row range by row range and matched block by block
+cudaError_t launch_sc_tc_clear_flags(void *buf, cudaStream_t st);
+cudaError_t launch_sc_tc_prep_db_rows(const double *hist, int n, int row0, int row1, void *db_buf,
+                                      cudaStream_t st, int64_t *launches);
+cudaError_t launch_sc_tc_prep_query_rows(const double *hist, int m, int row0, int row1, void *q_buf,
+                                         cudaStream_t st, int64_t *launches);
+int sc_tc_db_rows_padded(int n);
+int sc_tc_query_rows_padded(int m);
+cudaError_t launch_sc_match_tc_block(const void *q_buf, int m, int q0, int q1, const void *db_buf, int n,
+                                     int r0, int r1, float *d_p, float *d_i, int ldd, int num_sms,
+                                     cudaStream_t st, int64_t *launches);
 // d_p / d_i: fp32 m x ldd.  Returns cudaErrorNotSupported if tensor maps cannot be encoded.
 cudaError_t launch_sc_match_tc(const void *q_buf, int m, const void *db_buf, int n, float *d_p,
                                float *d_i, int ldd, int num_sms, cudaStream_t st, int64_t *launches);

@@ -170,9 +170,9 @@ __device__ __forceinline__ unsigned char slot_bits(const RowPrep &S, int ch, int
 
 __global__ void __launch_bounds__(256)
 sc_tc_prep_db_kernel(const double *__restrict__ hist, int n, int n_pad, unsigned char *__restrict__ buf,
-                     size_t off_f16, size_t off_f8, size_t off_norm) {
+                     size_t off_f16, size_t off_f8, size_t off_norm, int row0) {
   __shared__ RowPrep S;
-  const int row = blockIdx.x;
+  const int row = row0 + blockIdx.x;
   prep_row(hist + (size_t)row * 2 * SC_SIZE, row < n, S);
   if (threadIdx.x < 2 && S.nonbin[threadIdx.x]) atomicOr(reinterpret_cast<int *>(buf) + threadIdx.x, 1);
   for (int ch = 0; ch < 2; ch++) {
@@ -196,9 +196,9 @@ sc_tc_prep_db_kernel(const double *__restrict__ hist, int n, int n_pad, unsigned
 // the base vector of query b of the pair (x: the query image, y: its sector reversal y[c] = x[(60-c)%60]).
 __global__ void __launch_bounds__(256)
 sc_tc_prep_query_kernel(const double *__restrict__ hist, int m, int m_pad, unsigned char *__restrict__ buf,
-                        size_t off_f16, size_t off_f8, size_t off_norm) {
+                        size_t off_f16, size_t off_f8, size_t off_norm, int row0) {
   __shared__ RowPrep S;
-  const int row = blockIdx.x;
+  const int row = row0 + blockIdx.x;
   prep_row(hist + (size_t)row * 2 * SC_SIZE, row < m, S);
   if (threadIdx.x < 2 && S.nonbin[threadIdx.x]) atomicOr(reinterpret_cast<int *>(buf) + threadIdx.x, 1);
   const int pair = row >> 1, b = row & 1, npairs = m_pad >> 1;
@@ -361,7 +361,8 @@ struct TcParams {
   size_t q_off_f16, q_off_f8, q_off_norm, db_off_norm;
   float *d_out[2];              // per channel, m x ldd
   int m, n, m_pad, n_pad, ldd;
-  int n_units, n_tiles;         // units = 2 channels x (m_pad / 4) query groups; tiles = n_pad / 256
+  int n_units, n_tiles;         // units = 2 channels x query groups of 4; tiles of 256 DB rows (of this launch)
+  int qg0, tile0;               // first query group / DB tile of this launch (block launches of the streamed path)
   int flags;                    // debug: 1 skip epilogue loads, 2 skip MMAs, 4 force generic mode
 };
 
@@ -431,7 +432,7 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
         const CUtensorMap *map = bin ? (ch == 0 ? &map_f8_0 : &map_f8_1) : (ch == 0 ? &map_f16_0 : &map_f16_1);
         const int num_kb = (bin ? F8_CHUNKS : F16_CHUNKS) * UNITS_PER_CHUNK / KB_UNITS;
         const int kb_elems = bin ? 128 : 64;
-        const int row0 = tile * TILE_M + (int)rank * CTA_M;
+        const int row0 = (P.tile0 + tile) * TILE_M + (int)rank * CTA_M;
         for (int kb = 0; kb < num_kb; kb++) {
           mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1, 1);
           if (leader) mbar_expect_tx(smem_u32(&bars->full[stage]), 2 * A_STAGE_BYTES);
@@ -462,7 +463,7 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
         const int unit = (int)(it / P.n_tiles);
         if (unit == prev_unit) continue;
         prev_unit = unit;
-        const int ch = unit & 1, qg = unit >> 1;
+        const int ch = unit & 1, qg = P.qg0 + (unit >> 1);
         const bool bin = binary[ch];
         const uint32_t pair_bytes = (bin ? F8_CHUNKS : F16_CHUNKS) * CHUNK_BYTES;
         mbar_wait(smem_u32(&bars->b_empty), phase ^ 1, 2);
@@ -544,8 +545,8 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
     const float *db_norm = reinterpret_cast<const float *>(P.db_buf + P.db_off_norm);
     uint32_t t_phase = 0;
     for (long long it = it_begin; it < it_end; ++it) {
-      const int unit = (int)(it / P.n_tiles), tile = (int)(it - (long long)unit * P.n_tiles);
-      const int ch = unit & 1, qg = unit >> 1;
+      const int unit = (int)(it / P.n_tiles), tile = P.tile0 + (int)(it - (long long)unit * P.n_tiles);
+      const int ch = unit & 1, qg = P.qg0 + (unit >> 1);
       const bool bin = binary[ch];
       mbar_wait(smem_u32(&bars->tmem_full), t_phase, 8);
       tc_fence_after();
@@ -634,29 +635,55 @@ size_t sc_tc_query_bytes(int m) { return QLayout(m).total; }
 
 cudaError_t launch_sc_tc_prep_db(const double *hist, int n, void *db_buf, cudaStream_t st, int64_t *launches) {
   if (n <= 0) return cudaSuccess;
-  DbLayout L(n);
-  cudaError_t e = cudaMemsetAsync(db_buf, 0, HEADER_BYTES, st);
+  cudaError_t e = launch_sc_tc_clear_flags(db_buf, st);
   if (e != cudaSuccess) return e;
-  sc_tc_prep_db_kernel<<<L.n_pad, 256, 0, st>>>(hist, n, L.n_pad, reinterpret_cast<unsigned char *>(db_buf), L.off_f16,
-                                                L.off_f8, L.off_norm);
+  return launch_sc_tc_prep_db_rows(hist, n, 0, DbLayout(n).n_pad, db_buf, st, launches);
+}
+
+cudaError_t launch_sc_tc_clear_flags(void *buf, cudaStream_t st) { return cudaMemsetAsync(buf, 0, HEADER_BYTES, st); }
+
+// rows [row0, row1) of an n-row operand (row1 may run into the zero padding up to n_pad)
+cudaError_t launch_sc_tc_prep_db_rows(const double *hist, int n, int row0, int row1, void *db_buf, cudaStream_t st,
+                                      int64_t *launches) {
+  if (row1 <= row0) return cudaSuccess;
+  DbLayout L(n);
+  sc_tc_prep_db_kernel<<<row1 - row0, 256, 0, st>>>(hist, n, L.n_pad, reinterpret_cast<unsigned char *>(db_buf),
+                                                    L.off_f16, L.off_f8, L.off_norm, row0);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
 
-cudaError_t launch_sc_tc_prep_query(const double *hist, int m, void *q_buf, cudaStream_t st, int64_t *launches) {
-  if (m <= 0) return cudaSuccess;
+cudaError_t launch_sc_tc_prep_query_rows(const double *hist, int m, int row0, int row1, void *q_buf, cudaStream_t st,
+                                         int64_t *launches) {
+  if (row1 <= row0) return cudaSuccess;
   QLayout L(m);
-  cudaError_t e = cudaMemsetAsync(q_buf, 0, HEADER_BYTES, st);
-  if (e != cudaSuccess) return e;
-  sc_tc_prep_query_kernel<<<L.m_pad, 256, 0, st>>>(hist, m, L.m_pad, reinterpret_cast<unsigned char *>(q_buf),
-                                                   L.off_f16, L.off_f8, L.off_norm);
+  sc_tc_prep_query_kernel<<<row1 - row0, 256, 0, st>>>(hist, m, L.m_pad, reinterpret_cast<unsigned char *>(q_buf),
+                                                       L.off_f16, L.off_f8, L.off_norm, row0);
   if (launches) ++*launches;
   return cudaGetLastError();
+}
+
+int sc_tc_db_rows_padded(int n) { return DbLayout(n).n_pad; }
+int sc_tc_query_rows_padded(int m) { return QLayout(m).m_pad; }
+
+cudaError_t launch_sc_tc_prep_query(const double *hist, int m, void *q_buf, cudaStream_t st, int64_t *launches) {
+  if (m <= 0) return cudaSuccess;
+  cudaError_t e = launch_sc_tc_clear_flags(q_buf, st);
+  if (e != cudaSuccess) return e;
+  return launch_sc_tc_prep_query_rows(hist, m, 0, QLayout(m).m_pad, q_buf, st, launches);
 }
 
 cudaError_t launch_sc_match_tc(const void *q_buf, int m, const void *db_buf, int n, float *d_p, float *d_i, int ldd,
                                int num_sms, cudaStream_t st, int64_t *launches) {
-  if (m <= 0 || n <= 0) return cudaSuccess;
+  return launch_sc_match_tc_block(q_buf, m, 0, m, db_buf, n, 0, n, d_p, d_i, ldd, num_sms, st, launches);
+}
+
+// queries [q0, q1) x DB rows [r0, r1) of the m x n problem; q0 must be a multiple of 4 and r0 of 256
+cudaError_t launch_sc_match_tc_block(const void *q_buf, int m, int q0, int q1, const void *db_buf, int n, int r0, int r1,
+                                     float *d_p, float *d_i, int ldd, int num_sms, cudaStream_t st,
+                                     int64_t *launches) {
+  if (m <= 0 || n <= 0 || q1 <= q0 || r1 <= r0) return cudaSuccess;
+  if ((q0 % QG) || (r0 % TILE_M)) return cudaErrorInvalidValue;
   PFN_encodeTiled enc = get_encode();
   if (!enc) return cudaErrorNotSupported;
   DbLayout DL(n);
@@ -690,8 +717,10 @@ cudaError_t launch_sc_match_tc(const void *q_buf, int m, const void *db_buf, int
   P.m_pad = QL.m_pad;
   P.n_pad = DL.n_pad;
   P.ldd = ldd;
-  P.n_units = 2 * (QL.m_pad / QG);
-  P.n_tiles = DL.n_pad / TILE_M;
+  P.qg0 = q0 / QG;
+  P.tile0 = r0 / TILE_M;
+  P.n_units = 2 * ((q1 - q0 + QG - 1) / QG);
+  P.n_tiles = (r1 - r0 + TILE_M - 1) / TILE_M;
   P.flags = 0;
   if (const char *e = getenv("SODSO_TC_FLAGS")) P.flags = atoi(e);
   const long long W = (long long)P.n_units * P.n_tiles;
