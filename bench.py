@@ -199,6 +199,7 @@ def run_ours(args):
         db_kernel_ms[0] = ctx.last_kernel_ms
 
     api.SignatureDB.match = _timed_match
+    shard_db = [None]
 
     def step(host_inputs: bool):
         """one pass of the hot path; returns (idx, score) of the top-1 on the host"""
@@ -225,11 +226,14 @@ def run_ours(args):
         else:
             hist_db = api.sc_generate(d_xyz, d_inten, d_off)
             hist_q = hist_db if rank == 0 else api.sc_generate(dq_xyz, dq_inten, d_off)
-        db = api.SignatureDB("sc", hist_db, global_row0=row0, ctx=ctx)
+        # the rank's resident shard: operand buffers rewritten in place with this step's signatures
+        if shard_db[0] is None:
+            shard_db[0] = api.SignatureDB("sc", hist_db, global_row0=row0, ctx=ctx)
+        else:
+            shard_db[0].reload(hist_db)
         # stats all-reduce + per-shard top-k all-gather + merge (so_dso_place_recognition_b200/sharded.py)
-        mi, ms, mp, md = sharded.sharded_query(db, hist_q, n_global, 0, MASK_WIDTH, P_WEIGHT, TOPK, device=dev)
+        mi, ms, mp, md = sharded.sharded_query(shard_db[0], hist_q, n_global, 0, MASK_WIDTH, P_WEIGHT, TOPK, device=dev)
         kern_ms.append(db_kernel_ms[0])
-        db.close()
         return torch.from_numpy(mi[:, 0]), torch.from_numpy(ms[:, 0])
 
     def sync_all():

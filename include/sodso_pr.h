@@ -139,6 +139,9 @@ int sodso_sc_scans_to_loops(sodso_ctx *ctx, const double *xyz, const float *inte
 int sodso_db_create(sodso_ctx *ctx, int type, const double *hist2, int n_local,
                     int64_t global_row0, sodso_db **out);
 void sodso_db_destroy(sodso_db *db);
+/* Replace the shard's signatures by n_local new ones (same size, same global_row0): the operand buffers
+ * are rewritten in place, nothing is reallocated. */
+int sodso_db_reload(sodso_db *db, const double *hist2);
 int sodso_db_size(sodso_db *db);
 /* Distances of m queries against the shard (kept on the device inside the handle). */
 int sodso_db_match(sodso_db *db, const double *hist1, int m);

@@ -53,6 +53,7 @@ _PROTOS = {
     "sodso_sc_scans_to_loops": (_i, [_vp, _vp, _vp, _vp, _i, _d, _i, _d, _vp, _vp, _vp, _vp, _vp]),
     "sodso_db_create": (_i, [_vp, _i, _vp, _i, _i64, C.POINTER(_vp)]),
     "sodso_db_destroy": (None, [_vp]),
+    "sodso_db_reload": (_i, [_vp, _vp]),
     "sodso_db_size": (_i, [_vp]),
     "sodso_db_match": (_i, [_vp, _vp, _i]),
     "sodso_db_partial_stats": (_i, [_vp, _vp]),

@@ -116,12 +116,22 @@ def default_context(device: int | None = None) -> Context:
 
 
 def _ctx_for(*arrays, ctx=None):
-    if ctx is not None:
-        return ctx
+    """The context of a call.  If any argument is a torch CUDA tensor, the context's stream is made to wait for
+    torch's current stream first, so that tensors produced by earlier torch work (copies, NCCL collectives)
+    are complete before the library reads them; every library call that writes a device output synchronises
+    its stream before returning, which orders the other direction."""
+    c = ctx
     for a in arrays:
         if a is not None and _is_torch(a) and a.is_cuda:
-            return default_context(a.device.index or 0)
-    return default_context(0)
+            if c is None:
+                c = default_context(a.device.index or 0)
+            import torch
+
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(a.device))
+            torch.cuda.ExternalStream(c.stream or 0, device=a.device).wait_event(ev)
+            break
+    return c if c is not None else default_context(0)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -320,8 +330,16 @@ class SignatureDB:
         except Exception:
             pass
 
+    def reload(self, hist2):
+        """new signatures for the same shard (same number of rows), operand buffers rewritten in place"""
+        hist2 = _prep(hist2, np.float64, "float64")
+        assert hist2.shape[0] // self._rows == self.n
+        _ctx_for(hist2, ctx=self.ctx)
+        N.check(N.lib().sodso_db_reload(self._h, _ptr(hist2)))
+
     def match(self, hist1):
         hist1 = _prep(hist1, np.float64, "float64")
+        _ctx_for(hist1, ctx=self.ctx)
         self.m = hist1.shape[0] // self._rows
         self._ref = hist1
         N.check(N.lib().sodso_db_match(self._h, _ptr(hist1), self.m))
@@ -334,6 +352,7 @@ class SignatureDB:
 
     def topk(self, global_stats, n_global, q_global_row0, mask_width, p_weight=2.0, k=8):
         gs = _prep(global_stats, np.float64, "float64")
+        _ctx_for(gs, ctx=self.ctx)
         idx = _empty_like_kind(gs, (self.m, k), np.int64, "int64")
         score = _empty_like_kind(gs, (self.m, k), np.float64, "float64")
         dp = _empty_like_kind(gs, (self.m, k), np.float64, "float64")

@@ -717,6 +717,27 @@ int sodso_db_create(sodso_ctx *c, int type, const double *hist2, int n_local, in
   return SODSO_OK;
 }
 
+int sodso_db_reload(sodso_db *db, const double *hist2) {
+  if (!db || !hist2) {
+    set_error("bad db_reload arguments");
+    return SODSO_E_ARG;
+  }
+  sodso_ctx *c = db->ctx;
+  CTX_CHECK(c);
+  db->matched = false;
+  const size_t w = db->type == SODSO_TYPE_SC ? 2 * SC_SIZE : 2 * M2DP_SIG;
+  const size_t rows = db->type == SODSO_TYPE_SC ? db->n : 4 * (size_t)db->n;
+  const double *hd;
+  int rc;
+  if ((rc = stage_in(c, hist2, rows * w, c->h2, &hd))) return rc;
+  if (db->type == SODSO_TYPE_SC) {
+    if ((rc = sc_prepare(c, db->op_algo, hd, db->n, db->op, true))) return rc;
+  } else {
+    SODSO_CUDA_CHECK(cudaMemcpyAsync(db->op.p, hd, rows * w * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return sync_ctx(c);
+}
+
 void sodso_db_destroy(sodso_db *db) {
   if (!db) return;
   cudaSetDevice(db->ctx->device);
