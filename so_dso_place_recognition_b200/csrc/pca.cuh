@@ -121,6 +121,85 @@ __device__ inline void sym_eig3(const double a_in[9], double w[3], double v[9]) 
   }
 }
 
+// Symmetric 3x3 eigen-decomposition for the kernels (ascending eigenvalues, sign convention of
+// sym_eig3).  Cyclic Jacobi like the oracle's, arranged for a short dependency chain on one
+// thread: per rotation  h = sqrt(d^2 + b^2),  t = +-b / (|d| + h)  and  c = sqrt((h + |d|) / 2h)  are
+// algebraically the oracle's  t = sgn/(|theta| + sqrt(theta^2 + 1)),  c = 1/sqrt(t^2 + 1)  with theta =
+// d / b, and a rotation is skipped once |a_pq| <= 2^-54 (|a_pp| + |a_qq|) (a backward error below
+// half an ulp of the diagonal) instead of iterating to exact zeros.  Eigenvectors agree with the
+// oracle's to ~1e-15 / gap.
+__device__ __forceinline__ bool jacobi_rot(double &app, double &arr, double &apr, double &akp, double &akr,
+                                           double &q0p, double &q0r, double &q1p, double &q1r, double &q2p,
+                                           double &q2r) {
+  if (fabs(apr) <= 0x1p-54 * (fabs(app) + fabs(arr))) {
+    apr = 0.0;
+    return false;
+  }
+  const double d = arr - app, b = 2.0 * apr;
+  const double h = sqrt(d * d + b * b);
+  const double ad = fabs(d);
+  double t = b / (ad + h);
+  if (d < 0.0) t = -t;
+  const double c = sqrt((h + ad) / (2.0 * h));
+  const double s = t * c;
+  app = app - t * apr;
+  arr = arr + t * apr;
+  apr = 0.0;
+  const double kp = akp, kr = akr;
+  akp = c * kp - s * kr;
+  akr = s * kp + c * kr;
+  double a, bb;
+  a = q0p, bb = q0r, q0p = c * a - s * bb, q0r = s * a + c * bb;
+  a = q1p, bb = q1r, q1p = c * a - s * bb, q1r = s * a + c * bb;
+  a = q2p, bb = q2r, q2p = c * a - s * bb, q2r = s * a + c * bb;
+  return true;
+}
+
+static __device__ __noinline__ void sym_eig3_fast(const double *cov6, double *bc) {
+  // cov6 = {xx, xy, xz, yy, yz, zz}
+  double a00 = cov6[0], a01 = cov6[1], a02 = cov6[2], a11 = cov6[3], a12 = cov6[4], a22 = cov6[5];
+  double q00 = 1, q01 = 0, q02 = 0, q10 = 0, q11 = 1, q12 = 0, q20 = 0, q21 = 0, q22 = 1;
+  for (int sweep = 0; sweep < 32; sweep++) {
+    bool any = false;
+    any |= jacobi_rot(a00, a11, a01, a02, a12, q00, q01, q10, q11, q20, q21);  // (0,1), k = 2
+    any |= jacobi_rot(a00, a22, a02, a01, a12, q00, q02, q10, q12, q20, q22);  // (0,2), k = 1
+    any |= jacobi_rot(a11, a22, a12, a01, a02, q01, q02, q11, q12, q21, q22);  // (1,2), k = 0
+    if (!any) break;
+  }
+  double w0 = a00, w1 = a11, w2 = a22;
+  double v0[3] = {q00, q10, q20}, v1[3] = {q01, q11, q21}, v2[3] = {q02, q12, q22};
+  // stable ascending sort of three (same result as the oracle's insertion sort)
+#define SODSO_SWAP(wa, va, wb, vb)              \
+  if (wa > wb) {                                \
+    double tw = wa;                             \
+    wa = wb;                                    \
+    wb = tw;                                    \
+    for (int i_ = 0; i_ < 3; i_++) {            \
+      double tv = va[i_];                       \
+      va[i_] = vb[i_];                          \
+      vb[i_] = tv;                              \
+    }                                           \
+  }
+  SODSO_SWAP(w0, v0, w1, v1)
+  SODSO_SWAP(w1, v1, w2, v2)
+  SODSO_SWAP(w0, v0, w1, v1)
+#undef SODSO_SWAP
+  double *vs[3] = {v0, v1, v2};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double *col = vs[k];
+    int big = 0;
+    if (fabs(col[1]) > fabs(col[big])) big = 1;
+    if (fabs(col[2]) > fabs(col[big])) big = 2;
+    const double sgn = (col[big] < 0.0) ? -1.0 : 1.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) bc[3 + i * 3 + k] = sgn * col[i];
+  }
+  bc[12] = w0;
+  bc[13] = w1;
+  bc[14] = w2;
+}
+
 // Points of one scan: the first `nst` are staged in shared memory as SoA, the rest (scans
 // larger than the staging capacity) are read from global memory.
 struct ScanPoints {
