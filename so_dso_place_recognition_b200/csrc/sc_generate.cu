@@ -10,7 +10,7 @@
 //           dependent float intensity sum of SC.cpp:60-63 if it cannot be proven exact
 //   pass 2 (L2 read, backwards so that the lines pass 1 touched last are re-read first; measured DRAM
 //           read = 1.07 x the algorithmic bytes): point -> (sector, ring), shared-memory atomics (u32 count,
-//           int32 / fp64 intensity sum, order-preserving int64 min / max of the height); 64-point
+//           int32 / fp64 intensity sum, order-preserving int64 min / max of the height); 128-point
 //           chunks are handed out by a shared counter so that all warps reach the barrier together
 //   output: 2 x 1200 coalesced fp64 stores, bins cleared in the same sweep.
 // The bin of a point is found in fp32 (fast_turns / rsqrt) and accepted only when the fractional
@@ -30,7 +30,7 @@ namespace {
 
 constexpr int GEN_THREADS = 256;
 constexpr int GEN_CTAS_PER_SM = 4;
-constexpr int GEN_CHUNK = 64;         // points per work grab in the scatter pass
+constexpr int GEN_CHUNK = 128;        // points per work grab in the scatter pass
 constexpr int GEN_CAP = 3200;         // align_pca_kernel: points of a scan staged in shared memory
 constexpr float BIN_GUARD = 2.5e-4f;  // fp32 bin coordinates are accurate to < 2.5e-5 (see bin_of_point)
 
@@ -85,19 +85,6 @@ __device__ __forceinline__ int bin_of_point(double yp, double zp, double S_res_i
   return (unsigned)idx >= (unsigned)SC_SIZE ? -1 : idx;
 }
 
-// global loads with an L2 eviction-priority hint: the moments pass asks L2 to keep the scan
-// (evict_last), the scatter pass that follows is its last use (evict_first)
-__device__ __forceinline__ double ldg_hint(const double *p, uint64_t pol) {
-  double v;
-  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ float ldg_hint(const float *p, uint64_t pol) {
-  float v;
-  asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-  return v;
-}
-
 // min / max on the order-preserving int64 keys: the value read for the pre-check seeds the CAS loop
 __device__ __forceinline__ void smem_min_i64(long long *addr, long long key) {
   long long cur = *addr;
@@ -126,15 +113,6 @@ sc_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ int
   ScSmem &S = *reinterpret_cast<ScSmem *>(smem_raw);
   const float R_f = (float)R_res_inv;
   int *b_isum = reinterpret_cast<int *>(S.b_sum);
-  uint64_t pol_keep, pol_drop;
-  if (flags & 4) {
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_drop));
-  } else {
-    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
-    pol_drop = pol_keep;
-  }
-
   for (int b = threadIdx.x; b < SC_SIZE; b += GEN_THREADS) {
     S.b_sum[b] = 0.0;
     S.b_cnt[b] = 0u;
@@ -164,10 +142,10 @@ sc_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ int
     if (threadIdx.x == 0) S.ibc[0] = 1 << 20;
 #pragma unroll 4
     for (int i = threadIdx.x; i < n; i += GEN_THREADS) {
-      const float v = ldg_hint(gi + i, pol_keep);
-      const double x = ldg_hint(g + 3 * (size_t)i + 0, pol_keep) - ox;
-      const double y = ldg_hint(g + 3 * (size_t)i + 1, pol_keep) - oy;
-      const double z = ldg_hint(g + 3 * (size_t)i + 2, pol_keep) - oz;
+      const float v = __ldg(gi + i);
+      const double x = __ldg(g + 3 * (size_t)i + 0) - ox;
+      const double y = __ldg(g + 3 * (size_t)i + 1) - oy;
+      const double z = __ldg(g + 3 * (size_t)i + 2) - oz;
       s11[0] += x;
       s11[1] += y;
       s11[2] += z;
@@ -238,11 +216,11 @@ sc_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ int
         for (int r = 0; r < GEN_CHUNK / 32; r++) {
           const int i = c * GEN_CHUNK + r * 32 + lane;
           if (i >= n) continue;
-          const float it = ldg_hint(gi + i, pol_drop);
+          const float it = __ldg(gi + i);
           // pts_align.h:37-45 (fused multiply-adds: the frame itself already differs from the oracle's in the last bits)
-          const double x = ldg_hint(g + 3 * (size_t)i + 0, pol_drop) - S.bc[0];
-          const double y = ldg_hint(g + 3 * (size_t)i + 1, pol_drop) - S.bc[1];
-          const double z = ldg_hint(g + 3 * (size_t)i + 2, pol_drop) - S.bc[2];
+          const double x = __ldg(g + 3 * (size_t)i + 0) - S.bc[0];
+          const double y = __ldg(g + 3 * (size_t)i + 1) - S.bc[1];
+          const double z = __ldg(g + 3 * (size_t)i + 2) - S.bc[2];
           const double hx = fma(z, S.bc[9], fma(y, S.bc[6], x * S.bc[3]));
           const double yp = fma(z, S.bc[10], fma(y, S.bc[7], x * S.bc[4]));
           const double zp = fma(z, S.bc[11], fma(y, S.bc[8], x * S.bc[5]));
