@@ -48,6 +48,8 @@ constexpr int F16_CHUNKS = 8;                        // 64 fp16 slots per sector
 constexpr int F8_CHUNKS = 2;                         // 32 fp8 slots per sector
 constexpr int K_F16 = F16_CHUNKS * UNITS_PER_CHUNK * 8;    // 3840 elements
 constexpr int K_F8 = F8_CHUNKS * UNITS_PER_CHUNK * 16;     // 1920 elements (bytes)
+constexpr int F4_ROW_BYTES = 1024;                   // e2m1: 60 units x 32 slots (20 rings + 12 pad) + 4 zero units
+constexpr int F4_KB = F4_ROW_BYTES / 128;            // 8 K-blocks
 constexpr int KB_UNITS = 8;                          // units per K-block (128 B TMA box row)
 constexpr int Q_UNITS = 256;                         // units per (query pair, base, chunk): 2 x doubled vector
 constexpr int CHUNK_BYTES = Q_UNITS * 16;            // 4 KB
@@ -75,24 +77,26 @@ inline int pad_to(int v, int a) { return (v + a - 1) / a * a; }
 
 // Operand buffers in HBM.  header: int nonbinary[2] (per channel: some value is not 0/1).
 struct DbLayout {
-  size_t off_f16, off_f8, off_norm, total;
+  size_t off_f16, off_f8, off_f4, off_norm, total;
   int n_pad;
   explicit DbLayout(int n) {
     n_pad = pad_to(n, TILE_M);
     off_f16 = HEADER_BYTES;                                      // [ch][n_pad][3840] fp16
     off_f8 = off_f16 + (size_t)2 * n_pad * K_F16 * 2;            // [ch][n_pad][1920] e4m3
-    off_norm = off_f8 + (size_t)2 * n_pad * K_F8;                // [ch][n_pad] float 1/|h|
+    off_f4 = off_f8 + (size_t)2 * n_pad * K_F8;                  // [ch][n_pad][1024 B] e2m1, two per byte
+    off_norm = off_f4 + (size_t)2 * n_pad * F4_ROW_BYTES;        // [ch][n_pad] float 1/|h|
     total = off_norm + (size_t)2 * n_pad * 4;
   }
 };
 struct QLayout {
-  size_t off_f16, off_f8, off_norm, total;
+  size_t off_f16, off_f8, off_f4, off_norm, total;
   int m_pad;
   explicit QLayout(int m) {
     m_pad = pad_to(m, QG);
     off_f16 = HEADER_BYTES;                                      // [ch][base][m_pad/2][8][256][16 B]
     off_f8 = off_f16 + (size_t)2 * 2 * (m_pad / 2) * F16_CHUNKS * CHUNK_BYTES;
-    off_norm = off_f8 + (size_t)2 * 2 * (m_pad / 2) * F8_CHUNKS * CHUNK_BYTES;   // [ch][m_pad] float
+    off_f4 = off_f8 + (size_t)2 * 2 * (m_pad / 2) * F8_CHUNKS * CHUNK_BYTES;     // [ch][base][m_pad/2][256][16 B]
+    off_norm = off_f4 + (size_t)2 * 2 * (m_pad / 2) * CHUNK_BYTES;               // [ch][m_pad] float
     total = off_norm + (size_t)2 * m_pad * 4;
   }
 };
@@ -168,14 +172,24 @@ __device__ __forceinline__ unsigned char slot_bits(const RowPrep &S, int ch, int
   return s < SC_NUM_R ? S.bits[ch][sector * SC_NUM_R + s] : (unsigned char)0;
 }
 
+// e2m1 byte t (0..15) of a sector's unit: slots 2t (low nibble) and 2t + 1 (high nibble), 1.0 = 0b0010
+__device__ __forceinline__ unsigned char slot_nibbles(const RowPrep &S, int ch, int sector, int t) {
+  const unsigned lo = slot_bits(S, ch, sector, 2 * t) ? 0x2u : 0u, hi = slot_bits(S, ch, sector, 2 * t + 1) ? 0x20u : 0u;
+  return (unsigned char)(lo | hi);
+}
+
 __global__ void __launch_bounds__(256)
 sc_tc_prep_db_kernel(const double *__restrict__ hist, int n, int n_pad, unsigned char *__restrict__ buf,
-                     size_t off_f16, size_t off_f8, size_t off_norm, int row0) {
+                     size_t off_f16, size_t off_f8, size_t off_f4, size_t off_norm, int row0) {
   __shared__ RowPrep S;
   const int row = row0 + blockIdx.x;
   prep_row(hist + (size_t)row * 2 * SC_SIZE, row < n, S);
   if (threadIdx.x < 2 && S.nonbin[threadIdx.x]) atomicOr(reinterpret_cast<int *>(buf) + threadIdx.x, 1);
   for (int ch = 0; ch < 2; ch++) {
+    // byte k = unit * 16 + t ; unit = sector (units 60..63: zero padding of the 1024-byte row)
+    unsigned char *o4 = buf + off_f4 + ((size_t)ch * n_pad + row) * F4_ROW_BYTES;
+    for (int k = threadIdx.x; k < F4_ROW_BYTES; k += blockDim.x)
+      o4[k] = (k >> 4) < SC_NUM_S ? slot_nibbles(S, ch, k >> 4, k & 15) : (unsigned char)0;
     // k = chunk*480 + sector*8 + t ; slot = chunk*8 + t
     __half *o = reinterpret_cast<__half *>(buf + off_f16) + ((size_t)ch * n_pad + row) * K_F16;
     for (int k = threadIdx.x; k < K_F16; k += blockDim.x) {
@@ -196,7 +210,7 @@ sc_tc_prep_db_kernel(const double *__restrict__ hist, int n, int n_pad, unsigned
 // the base vector of query b of the pair (x: the query image, y: its sector reversal y[c] = x[(60-c)%60]).
 __global__ void __launch_bounds__(256)
 sc_tc_prep_query_kernel(const double *__restrict__ hist, int m, int m_pad, unsigned char *__restrict__ buf,
-                        size_t off_f16, size_t off_f8, size_t off_norm, int row0) {
+                        size_t off_f16, size_t off_f8, size_t off_f4, size_t off_norm, int row0) {
   __shared__ RowPrep S;
   const int row = row0 + blockIdx.x;
   prep_row(hist + (size_t)row * 2 * SC_SIZE, row < m, S);
@@ -216,6 +230,12 @@ sc_tc_prep_query_kernel(const double *__restrict__ hist, int m, int m_pad, unsig
         const int t = e & 15, u = (e >> 4) & 127, j = e >> 11;
         const int cs = u % SC_NUM_S, c = base == 0 ? cs : (SC_NUM_S - cs) % SC_NUM_S;
         o8[((size_t)j * Q_UNITS + 2 * u + b) * 16 + t] = slot_bits(S, ch, c, j * 16 + t);
+      }
+      unsigned char *o4 = buf + off_f4 + (((size_t)ch * 2 + base) * npairs + pair) * CHUNK_BYTES;
+      for (int e = threadIdx.x; e < 128 * 16; e += blockDim.x) {
+        const int t = e & 15, u = e >> 4;
+        const int cs = u % SC_NUM_S, c = base == 0 ? cs : (SC_NUM_S - cs) % SC_NUM_S;
+        o4[((size_t)2 * u + b) * 16 + t] = slot_nibbles(S, ch, c, t);
       }
     }
   if (threadIdx.x < 2) reinterpret_cast<float *>(buf + off_norm)[(size_t)threadIdx.x * m_pad + row] = S.inv_norm[threadIdx.x];
@@ -284,6 +304,17 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// one lane of a converged warp (the MMA-issuing warp runs its loop warp-uniformly so that the descriptor
+// arithmetic stays on the uniform datapath; only the tcgen05 instructions themselves are predicated)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -303,6 +334,16 @@ __device__ __forceinline__ void umma_f8_2sm(uint32_t tmem_d, uint64_t adesc, uin
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// block-scaled e2m1 MMA (kind::mxf4, one ue8m0 scale per 32 elements; the scales are all 1.0 here)
+__device__ __forceinline__ void umma_mxf4_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate, uint32_t tmem_sfa, uint32_t tmem_sfb) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
       : "memory");
 }
 // completion of all prior MMAs of this thread -> arrive on the barrier at the same offset in both CTAs
@@ -334,6 +375,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16_const(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr),
+      "r"(v)
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptors (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14),
@@ -349,6 +397,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// block-scaled instruction descriptor (InstrDescriptorBlockScaled): a/b format MXF4 E2M1 (1) [7,10)/[10,13), K-major both,
+// n_dim = N>>3 [17,23), scale format E8M0 (1) [23,24), m_dim = M>>4 [24,29), scale-factor ids 0, K = 64
+__host__ __device__ constexpr uint32_t make_idesc_mxf4(int M, int N) {
+  return (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (1u << 23) | ((uint32_t)(M >> 4) << 24);
+}
+
 // instruction descriptor (InstrDescriptor): c_format F32 (1) [4,6), a/b format [7,10)/[10,13)
 // (kind::f16: F16 = 0; kind::f8f6f4: E4M3 = 0), K-major both, n_dim = N>>3 [17,23), m_dim = M>>4 [24,29)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
@@ -358,13 +412,71 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 struct TcParams {
   const unsigned char *q_buf;   // QLayout
   const unsigned char *db_buf;  // DbLayout
-  size_t q_off_f16, q_off_f8, q_off_norm, db_off_norm;
+  size_t q_off_f16, q_off_f8, q_off_f4, q_off_norm, db_off_norm;
   float *d_out[2];              // per channel, m x ldd
   int m, n, m_pad, n_pad, ldd;
   int n_units, n_tiles;         // units = 2 channels x query groups of 4; tiles of 256 DB rows (of this launch)
   int qg0, tile0;               // first query group / DB tile of this launch (block launches of the streamed path)
-  int flags;                    // debug: 1 skip epilogue loads, 2 skip MMAs, 4 force generic mode
+  int flags;                    // debug: 1 skip epilogue loads, 2 skip MMAs, 4 force generic mode, 8 binary channel in e4m3
 };
+
+// One work item's K loop on the issuing thread, specialised per operand format so that the loop body is
+// straight-line: descriptors are advanced by integer adds on their 16-byte address field.
+//   MODE 0: fp16 3-term split (kind::f16), 1: e4m3 (kind::f8f6f4), 2: e2m1 (kind::mxf4, block scales = 1)
+template <int MODE>
+__device__ __forceinline__ void issue_k_loop(TcBarriers *bars, uint32_t sA, uint32_t sB, uint32_t tmem_base,
+                                             uint32_t tmem_sf, int &stage, uint32_t &phase, bool skip) {
+  constexpr int NCHUNK = MODE == 0 ? F16_CHUNKS : (MODE == 1 ? F8_CHUNKS : 1);
+  constexpr int NUM_KB = MODE == 2 ? F4_KB : NCHUNK * UNITS_PER_CHUNK / KB_UNITS;
+  constexpr uint32_t PAIR_UNITS = NCHUNK * CHUNK_BYTES / 16;     // second query pair, in 16-byte descriptor units
+  constexpr uint32_t idesc = MODE == 2 ? make_idesc_mxf4(TILE_M, N_INST) : make_idesc(TILE_M, N_INST);
+  // A: SWIZZLE_128B K-major, 8-row groups 1024 B apart; a K-step advances the start by 32 B (2 units)
+  const uint64_t adesc0 = make_desc(sA, 16, 1024, 2);
+  // B: Hankel view, no swizzle: row r = 2 s + b, k-group g -> unit 2 (c + s + g) + b of chunk j
+  const uint64_t bdesc0 = make_desc(sB, 32, 128, 0);
+  uint32_t boff = 0;    // (chunk j) * 256 + 2 * (sector c): the K position of the next MMA in the Hankel buffer
+  uint32_t c2 = 0;      // 2 * c
+  uint32_t acc = 0;
+#pragma unroll 1
+  for (int kb = 0; kb < NUM_KB; kb++) {
+    mbar_wait(smem_u32(&bars->full[stage]), phase, 7);
+    tc_fence_after();
+    const uint64_t ad = adesc0 + (uint64_t)(stage * (A_STAGE_BYTES >> 4));
+    if (!skip) {
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        const uint64_t a = ad + (uint64_t)(kk * 2), b = bdesc0 + (uint64_t)boff;
+        if (elect_one()) {
+          if (MODE == 0) {
+            umma_f16_2sm(tmem_base, a, b, idesc, acc);
+            umma_f16_2sm(tmem_base + N_MMA, a, b + PAIR_UNITS, idesc, acc);
+          } else if (MODE == 1) {
+            umma_f8_2sm(tmem_base, a, b, idesc, acc);
+            umma_f8_2sm(tmem_base + N_MMA, a, b + PAIR_UNITS, idesc, acc);
+          } else {
+            umma_mxf4_2sm(tmem_base, a, b, idesc, acc, tmem_sf, tmem_sf + 8);
+            umma_mxf4_2sm(tmem_base + N_MMA, a, b + PAIR_UNITS, idesc, acc, tmem_sf, tmem_sf + 8);
+          }
+        }
+        acc = 1;
+        boff += 4;
+        if (MODE != 2) {   // e2m1: one chunk; units 60..63 of the DB row are zero, what the view reads there is moot
+          c2 += 4;
+          if (c2 >= 2 * UNITS_PER_CHUNK) {
+            c2 -= 2 * UNITS_PER_CHUNK;
+            boff += CHUNK_BYTES / 16 - 2 * UNITS_PER_CHUNK;
+          }
+        }
+      }
+    }
+    if (elect_one()) umma_commit_2sm(smem_u32(&bars->empty[stage]));
+    __syncwarp();
+    if (++stage == NSTAGE) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // the kernel
@@ -372,6 +484,7 @@ struct TcParams {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_constant__ CUtensorMap map_f16_1,
                    const __grid_constant__ CUtensorMap map_f8_0, const __grid_constant__ CUtensorMap map_f8_1,
+                   const __grid_constant__ CUtensorMap map_f4_0, const __grid_constant__ CUtensorMap map_f4_1,
                    const TcParams P) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base_raw = smem_u32(smem_dyn);
@@ -418,6 +531,18 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_ptr;
+  // binary channels run as e2m1 under kind::mxf4 (2x the e4m3 rate); its block scales (ue8m0, all 1.0 = 0x7f)
+  // live in the 16 TMEM columns that the N = 240 accumulators leave free in each 256-column slot
+  const bool use_f4 = !(P.flags & 8);
+  const uint32_t tmem_sf = tmem_base + (uint32_t)N_INST;
+  if (warp >= 4) {
+    tmem_st16_const(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)N_INST, 0x7f7f7f7fu);
+    tmem_st16_const(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(N_MMA + N_INST), 0x7f7f7f7fu);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
 
   if (warp == 0) {
     // ===== TMA producer: this CTA's 128 DB rows of every K-block =====
@@ -429,8 +554,9 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
         const int unit = (int)(it / P.n_tiles), tile = (int)(it - (long long)unit * P.n_tiles);
         const int ch = unit & 1;
         const bool bin = binary[ch];
-        const CUtensorMap *map = bin ? (ch == 0 ? &map_f8_0 : &map_f8_1) : (ch == 0 ? &map_f16_0 : &map_f16_1);
-        const int num_kb = (bin ? F8_CHUNKS : F16_CHUNKS) * UNITS_PER_CHUNK / KB_UNITS;
+        const CUtensorMap *map = bin ? (use_f4 ? (ch == 0 ? &map_f4_0 : &map_f4_1) : (ch == 0 ? &map_f8_0 : &map_f8_1))
+                                     : (ch == 0 ? &map_f16_0 : &map_f16_1);
+        const int num_kb = bin ? (use_f4 ? F4_KB : F8_CHUNKS * UNITS_PER_CHUNK / KB_UNITS) : F16_CHUNKS * UNITS_PER_CHUNK / KB_UNITS;
         const int kb_elems = bin ? 128 : 64;
         const int row0 = (P.tile0 + tile) * TILE_M + (int)rank * CTA_M;
         for (int kb = 0; kb < num_kb; kb++) {
@@ -465,10 +591,10 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
         prev_unit = unit;
         const int ch = unit & 1, qg = P.qg0 + (unit >> 1);
         const bool bin = binary[ch];
-        const uint32_t pair_bytes = (bin ? F8_CHUNKS : F16_CHUNKS) * CHUNK_BYTES;
+        const uint32_t pair_bytes = (bin ? (use_f4 ? 1 : F8_CHUNKS) : F16_CHUNKS) * CHUNK_BYTES;
         mbar_wait(smem_u32(&bars->b_empty), phase ^ 1, 2);
         mbar_expect_tx(smem_u32(&bars->b_full), 2 * pair_bytes);
-        const unsigned char *src = P.q_buf + (bin ? P.q_off_f8 : P.q_off_f16) +
+        const unsigned char *src = P.q_buf + (bin ? (use_f4 ? P.q_off_f4 : P.q_off_f8) : P.q_off_f16) +
                                    (((size_t)ch * 2 + rank) * qpairs + (size_t)qg * 2) * pair_bytes;
         for (int p = 0; p < 2; p++)
           bulk_load_1d(sB + p * pair_bytes, src + (size_t)p * pair_bytes, pair_bytes, smem_u32(&bars->b_full));
@@ -482,19 +608,15 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
       if (prev_unit >= 0) mbar_wait(smem_u32(&bars->b_empty), phase ^ 1, 10);  // drain the last commit
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (leader CTA, one thread) =====
-    if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TILE_M, N_INST);
+    // ===== MMA issuer (leader CTA; the warp runs the loop uniformly, one elected lane issues) =====
+    if (leader) {
       int stage = 0;
       uint32_t phase = 0, b_phase = 0, t_phase = 0;
       int prev_unit = -1;
+      const bool skip = (P.flags & 2) != 0;
       for (long long it = it_begin; it < it_end; ++it) {
         const int unit = (int)(it / P.n_tiles);
         const int ch = unit & 1;
-        const bool bin = binary[ch];
-        const int nchunks = bin ? F8_CHUNKS : F16_CHUNKS;
-        const int num_kb = nchunks * UNITS_PER_CHUNK / KB_UNITS;
-        const uint32_t pair_bytes = nchunks * CHUNK_BYTES;
         if (unit != prev_unit) {
           prev_unit = unit;
           mbar_wait(smem_u32(&bars->b_full), b_phase, 4);
@@ -503,37 +625,18 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
         }
         mbar_wait(smem_u32(&bars->tmem_empty), t_phase ^ 1, 6);
         tc_fence_after();
-        for (int kb = 0; kb < num_kb; kb++) {
-          mbar_wait(smem_u32(&bars->full[stage]), phase, 7);
-          tc_fence_after();
-          const uint32_t a_base = sA + stage * A_STAGE_BYTES;
-          if (!(P.flags & 2)) {
-#pragma unroll
-            for (int kk = 0; kk < 4; kk++) {
-              const int u = kb * KB_UNITS + kk * 2;     // K position in 16-byte units
-              const int j = u / UNITS_PER_CHUNK, c = u - j * UNITS_PER_CHUNK;
-              // A: SWIZZLE_128B K-major, 8-row groups 1024 B apart; a K-step advances the start by 32 B
-              const uint64_t adesc = make_desc(a_base + kk * 32, 16, 1024, 2);
-#pragma unroll
-              for (int p = 0; p < 2; p++) {
-                // B: Hankel view, no swizzle: row r = 2 s + b, k-group g -> unit 2 (c + s + g) + b of chunk j
-                const uint64_t bdesc = make_desc(sB + p * pair_bytes + j * CHUNK_BYTES + c * 32, 32, 128, 0);
-                if (bin)
-                  umma_f8_2sm(tmem_base + p * N_MMA, adesc, bdesc, idesc, (kb | kk) != 0 ? 1u : 0u);
-                else
-                  umma_f16_2sm(tmem_base + p * N_MMA, adesc, bdesc, idesc, (kb | kk) != 0 ? 1u : 0u);
-              }
-            }
-          }
-          umma_commit_2sm(smem_u32(&bars->empty[stage]));
-          if (++stage == NSTAGE) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        umma_commit_2sm(smem_u32(&bars->tmem_full));
+        if (!binary[ch])
+          issue_k_loop<0>(bars, sA, sB, tmem_base, tmem_sf, stage, phase, skip);
+        else if (use_f4)
+          issue_k_loop<2>(bars, sA, sB, tmem_base, tmem_sf, stage, phase, skip);
+        else
+          issue_k_loop<1>(bars, sA, sB, tmem_base, tmem_sf, stage, phase, skip);
         const bool last_of_unit = (it + 1 == it_end) || ((int)((it + 1) / P.n_tiles) != unit);
-        if (last_of_unit) umma_commit_2sm(smem_u32(&bars->b_empty));
+        if (elect_one()) {
+          umma_commit_2sm(smem_u32(&bars->tmem_full));
+          if (last_of_unit) umma_commit_2sm(smem_u32(&bars->b_empty));
+        }
+        __syncwarp();
         t_phase ^= 1;
       }
     }
@@ -648,7 +751,7 @@ cudaError_t launch_sc_tc_prep_db_rows(const double *hist, int n, int row0, int r
   if (row1 <= row0) return cudaSuccess;
   DbLayout L(n);
   sc_tc_prep_db_kernel<<<row1 - row0, 256, 0, st>>>(hist, n, L.n_pad, reinterpret_cast<unsigned char *>(db_buf),
-                                                    L.off_f16, L.off_f8, L.off_norm, row0);
+                                                    L.off_f16, L.off_f8, L.off_f4, L.off_norm, row0);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -658,7 +761,7 @@ cudaError_t launch_sc_tc_prep_query_rows(const double *hist, int m, int row0, in
   if (row1 <= row0) return cudaSuccess;
   QLayout L(m);
   sc_tc_prep_query_kernel<<<row1 - row0, 256, 0, st>>>(hist, m, L.m_pad, reinterpret_cast<unsigned char *>(q_buf),
-                                                       L.off_f16, L.off_f8, L.off_norm, row0);
+                                                       L.off_f16, L.off_f8, L.off_f4, L.off_norm, row0);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -689,15 +792,15 @@ cudaError_t launch_sc_match_tc_block(const void *q_buf, int m, int q0, int q1, c
   DbLayout DL(n);
   QLayout QL(m);
   const unsigned char *dbb = reinterpret_cast<const unsigned char *>(db_buf);
-  CUtensorMap maps[4];
-  for (int fmt = 0; fmt < 2; fmt++)
+  CUtensorMap maps[6];
+  for (int fmt = 0; fmt < 3; fmt++)
     for (int ch = 0; ch < 2; ch++) {
-      const size_t kbytes = fmt == 0 ? (size_t)K_F16 * 2 : (size_t)K_F8;
-      cuuint64_t dims[2] = {(cuuint64_t)(fmt == 0 ? K_F16 : K_F8), (cuuint64_t)DL.n_pad};
+      const size_t kbytes = fmt == 0 ? (size_t)K_F16 * 2 : (fmt == 1 ? (size_t)K_F8 : (size_t)F4_ROW_BYTES);
+      cuuint64_t dims[2] = {(cuuint64_t)(fmt == 0 ? K_F16 : (fmt == 1 ? K_F8 : F4_ROW_BYTES)), (cuuint64_t)DL.n_pad};
       cuuint64_t strides[1] = {(cuuint64_t)kbytes};
       cuuint32_t box[2] = {(cuuint32_t)(fmt == 0 ? 64 : 128), (cuuint32_t)CTA_M};
       cuuint32_t estr[2] = {1, 1};
-      void *gaddr = (void *)(dbb + (fmt == 0 ? DL.off_f16 : DL.off_f8) + (size_t)ch * DL.n_pad * kbytes);
+      void *gaddr = (void *)(dbb + (fmt == 0 ? DL.off_f16 : (fmt == 1 ? DL.off_f8 : DL.off_f4)) + (size_t)ch * DL.n_pad * kbytes);
       CUresult r = enc(&maps[fmt * 2 + ch], fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
                        gaddr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -708,6 +811,7 @@ cudaError_t launch_sc_match_tc_block(const void *q_buf, int m, int q0, int q1, c
   P.db_buf = dbb;
   P.q_off_f16 = QL.off_f16;
   P.q_off_f8 = QL.off_f8;
+  P.q_off_f4 = QL.off_f4;
   P.q_off_norm = QL.off_norm;
   P.db_off_norm = DL.off_norm;
   P.d_out[0] = d_p;
@@ -729,7 +833,7 @@ cudaError_t launch_sc_match_tc_block(const void *q_buf, int m, int q0, int q1, c
   if (npairs < 1) npairs = 1;
   cudaError_t e = cudaFuncSetAttribute(sc_match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  sc_match_tc_kernel<<<2 * npairs, TC_THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], P);
+  sc_match_tc_kernel<<<2 * npairs, TC_THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], P);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
