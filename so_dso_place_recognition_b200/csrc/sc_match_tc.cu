@@ -279,12 +279,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (surfacing as a CUDA error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (surfacing as a CUDA error) instead of hanging the GPU.  The clock is only
+// consulted every 4096 failed probes, so a waiting warp costs few issue slots.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s
+    if ((++spins & 0xfffu) == 0 && clock64() - t0 > 4000000000LL) {  // ~2 s
       printf("sc_match_tc: barrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
              (int)threadIdx.x, parity);
       __trap();
