@@ -288,7 +288,7 @@ def run_ours(args):
             "value": pairs_step * args.steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "match: fp16 3-term split (structure) + e4m3 exact counts (binary intensity), fp32 accumulate in TMEM; generation: f64", "data": "synthetic",
+            "dtype": "match: fp16 3-term split (structure) + e2m1 exact counts (binary intensity), fp32 accumulate in TMEM; generation: f64", "data": "synthetic",
             "config": {"workload": "5k-scan DB all-pairs ScanContext match, 4096 pts/scan (BASELINE configs[2])",
                        "n_queries": N_SCANS, "n_db_per_gpu": n_local, "n_db_total": n_global, "pts_per_scan": N_PTS,
                        "variants_per_pair": 120, "mask_width": MASK_WIDTH, "topk": 1 if world == 1 else TOPK,
@@ -310,7 +310,7 @@ def run_ours(args):
                          if peaks["tf_sus"] else None,
                          "kernel_ms": k_ms,
                          "note": "algorithmic FLOP = 576 kFLOP/pair (2 channels x 120 variants x 1200 MACs); executed MMA "
-                                 "work per pair: structure 3-term fp16 split (K 3840) + intensity e4m3 (K 1920), "
+                                 "work per pair: structure 3-term fp16 split (K 3840) + intensity e2m1 under kind::mxf4 (K 2048), "
                                  "MMA N = 240 = 120 variants x 2 interleaved queries"},
         }
         if world == 1 and not args.no_cpu_baseline:
