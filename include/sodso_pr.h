@@ -47,6 +47,7 @@ extern "C" {
 
 typedef struct sodso_ctx sodso_ctx;
 typedef struct sodso_db sodso_db;
+typedef struct sodso_staged sodso_staged;
 
 /* ---- context ---------------------------------------------------------------------- */
 int sodso_ctx_create(int device, sodso_ctx **out);
@@ -68,6 +69,27 @@ const char *sodso_ctx_last_kernel_name(sodso_ctx *ctx);
 /* ---- signature sizes:  SC::getSignatureSize (SC.cpp:10), M2DP::getSignatureSize (M2DP.cpp:36) */
 int sodso_sc_signature_size(void);
 int sodso_m2dp_signature_size(void);
+
+/* ---- point staging --------------------------------------------------------------- */
+/* pts_preprocess(poses_file, pts_file, id_file, lidarRange, out_vec, polar_filter) (pts_preprocess.h:169-232) on
+ * the records the two files parse to (PosesPts.h:5-40): pose_id[n_pose], w2c[n_pose x 12] (row-major 3x4),
+ * pt_id[n_pts], pt_xyz[n_pts x 3] (world frame), pt_inten[n_pts].  The sequential pose walk (reset rule, the 30
+ * skipped frames, which points have entered) is bookkeeping on the host; the per-frame transform + range crop of
+ * every accumulated point and the voxel-grid (polar_filter = 0, SC) / 1-degree polar (polar_filter = 1, M2DP)
+ * de-duplication run on the GPU.  The staged scans stay in HBM inside the handle; inside a scan the points are
+ * ordered by voxel index (the reference's order is the iteration order of a libstdc++ unordered_map; the point set
+ * is identical).  sodso_staged_xyz/inten/scan_off are DEVICE pointers that can be handed to sodso_sc_generate /
+ * sodso_m2dp_generate / sodso_sc_scans_to_loops; sodso_staged_copy copies out (ids = incoming_id_file.txt). */
+int sodso_stage_points(sodso_ctx *ctx, const int32_t *pose_id, const double *w2c, int n_pose,
+                       const int32_t *pt_id, const double *pt_xyz, const float *pt_inten, int64_t n_pts,
+                       double lidar_range, int polar_filter, sodso_staged **out);
+void sodso_staged_destroy(sodso_staged *s);
+int sodso_staged_num_scans(sodso_staged *s);
+int64_t sodso_staged_num_points(sodso_staged *s);
+const double *sodso_staged_xyz(sodso_staged *s);
+const float *sodso_staged_inten(sodso_staged *s);
+const int64_t *sodso_staged_scan_off(sodso_staged *s);
+int sodso_staged_copy(sodso_staged *s, int32_t *ids, int64_t *scan_off, double *xyz, float *inten);
 
 /* ---- generation ------------------------------------------------------------------- */
 /* pts_align.h:7-46  align_points_PCA for a batch of scans.

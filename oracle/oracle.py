@@ -42,6 +42,7 @@ def lib():
             build(force=True)
             _lib = C.CDLL(_SO)
         _lib.orc_stage_run.restype = C.c_void_p
+        _lib.orc_stage_arrays.restype = C.c_void_p
         _lib.orc_stage_num_points.restype = C.c_int64
     return _lib
 
@@ -184,6 +185,10 @@ def stage(poses_file, pts_file, lidar_range=45.0, polar_filter=False):
     L = lib()
     h = C.c_void_p(L.orc_stage_run(poses_file.encode(), pts_file.encode(), C.c_double(lidar_range),
                                    C.c_int(1 if polar_filter else 0)))
+    return _stage_result(L, h)
+
+
+def _stage_result(L, h):
     try:
         ns = L.orc_stage_num_scans(h)
         npts = L.orc_stage_num_points(h)
@@ -195,6 +200,20 @@ def stage(poses_file, pts_file, lidar_range=45.0, polar_filter=False):
         return dict(ids=ids, off=off, xyz=xyz, inten=inten, n_poses=L.orc_stage_num_poses(h))
     finally:
         L.orc_stage_free(h)
+
+
+def stage_arrays(pose_id, w2c, pt_id, pt_xyz, pt_inten, lidar_range=45.0, polar_filter=False):
+    """pts_preprocess on in-memory records (what read_poses_pts parses, pts_preprocess.h:17-49)."""
+    L = lib()
+    pose_id = np.ascontiguousarray(pose_id, dtype=np.int32)
+    w2c = np.ascontiguousarray(w2c, dtype=np.float64).reshape(-1, 12)
+    pt_id = np.ascontiguousarray(pt_id, dtype=np.int32)
+    pt_xyz = np.ascontiguousarray(pt_xyz, dtype=np.float64).reshape(-1, 3)
+    pt_inten = np.ascontiguousarray(pt_inten, dtype=np.float32)
+    h = C.c_void_p(L.orc_stage_arrays(_p(pose_id, C.c_int), _p(w2c, C.c_double), C.c_int(len(pose_id)),
+                                      _p(pt_id, C.c_int), _p(pt_xyz, C.c_double), _p(pt_inten, C.c_float),
+                                      C.c_int64(len(pt_id)), C.c_double(lidar_range), C.c_int(1 if polar_filter else 0)))
+    return _stage_result(L, h)
 
 
 # ---------------------------------------------------------------------------------------

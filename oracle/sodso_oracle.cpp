@@ -603,36 +603,19 @@ static void filter_polar(const std::vector<PtI>& in, const double resolution[3],
   }
 }
 
-void* orc_stage_run(const char* poses_file, const char* pts_file, double lidar_range, int polar_filter) {
+static StageResult* stage_core(const std::vector<PoseI>& poses, const std::vector<PtI>& pts, double lidar_range,
+                               int polar_filter) {
   constexpr int INIT_FRAME = 30;                       // pts_preprocess.h:13
   constexpr double RES_GRID = 30;                      // :14
   const double RES_POLAR = 1.0 / 180.0 * M_PI;         // :15
   auto* R = new StageResult();
-  std::vector<PoseI> poses;
-  std::vector<PtI> pts;
-  {                                                    // read_poses_pts, :17-49
-    std::ifstream f(poses_file);
-    while (true) {
-      PoseI p;
-      if (!(f >> p.id)) break;
-      for (int k = 0; k < 12; k++)
-        if (!(f >> p.w[k])) break;
-      poses.push_back(p);
-    }
-    std::ifstream g(pts_file);
-    while (true) {
-      PtI p;
-      if (!(g >> p.id >> p.p[0] >> p.p[1] >> p.p[2] >> p.it)) break;
-      pts.push_back(p);
-    }
-  }
   R->n_poses = (int)poses.size();
   R->n_pts = (int64_t)pts.size();
   R->off.push_back(0);
   std::vector<const PtI*> nearby;
   size_t pts_idx = 0;
   int frame_from_reset = 0;
-  for (auto& pose : poses) {                           // :187-216
+  for (const auto& pose : poses) {                           // :187-216
     const double* w = pose.w;                          // row-major 3x4
     double tn = std::sqrt((w[3] * w[3] + w[7] * w[7]) + w[11] * w[11]);
     if (tn < 1.0) {                                    // :189-193
@@ -678,6 +661,46 @@ void* orc_stage_run(const char* poses_file, const char* pts_file, double lidar_r
     R->incoming_ids.push_back(pose.id);                // :215
   }
   return R;
+}
+
+
+void* orc_stage_run(const char* poses_file, const char* pts_file, double lidar_range, int polar_filter) {
+  std::vector<PoseI> poses;
+  std::vector<PtI> pts;
+  {                                                    // read_poses_pts, pts_preprocess.h:17-49
+    std::ifstream f(poses_file);
+    while (true) {
+      PoseI p;
+      if (!(f >> p.id)) break;
+      for (int k = 0; k < 12; k++)
+        if (!(f >> p.w[k])) break;
+      poses.push_back(p);
+    }
+    std::ifstream g(pts_file);
+    while (true) {
+      PtI p;
+      if (!(g >> p.id >> p.p[0] >> p.p[1] >> p.p[2] >> p.it)) break;
+      pts.push_back(p);
+    }
+  }
+  return stage_core(poses, pts, lidar_range, polar_filter);
+}
+
+// same staging from in-memory records (what the files parse to)
+void* orc_stage_arrays(const int* pose_id, const double* w2c, int n_pose, const int* pt_id, const double* pt_xyz,
+                       const float* pt_inten, int64_t n_pts, double lidar_range, int polar_filter) {
+  std::vector<PoseI> poses((size_t)n_pose);
+  std::vector<PtI> pts((size_t)n_pts);
+  for (int i = 0; i < n_pose; i++) {
+    poses[i].id = pose_id[i];
+    for (int k = 0; k < 12; k++) poses[i].w[k] = w2c[12 * (size_t)i + k];
+  }
+  for (int64_t i = 0; i < n_pts; i++) {
+    pts[i].id = pt_id[i];
+    for (int k = 0; k < 3; k++) pts[i].p[k] = pt_xyz[3 * i + k];
+    pts[i].it = pt_inten[i];
+  }
+  return stage_core(poses, pts, lidar_range, polar_filter);
 }
 
 int orc_stage_num_scans(void* h) { return (int)((StageResult*)h)->incoming_ids.size(); }

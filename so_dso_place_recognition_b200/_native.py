@@ -41,6 +41,14 @@ _PROTOS = {
     "sodso_sc_signature_size": (_i, []),
     "sodso_m2dp_signature_size": (_i, []),
     "sodso_align_pca": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "sodso_stage_points": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i64, _d, _i, C.POINTER(_vp)]),
+    "sodso_staged_destroy": (None, [_vp]),
+    "sodso_staged_num_scans": (_i, [_vp]),
+    "sodso_staged_num_points": (_i64, [_vp]),
+    "sodso_staged_xyz": (_vp, [_vp]),
+    "sodso_staged_inten": (_vp, [_vp]),
+    "sodso_staged_scan_off": (_vp, [_vp]),
+    "sodso_staged_copy": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "sodso_sc_generate": (_i, [_vp, _vp, _vp, _vp, _i, _d, _vp]),
     "sodso_m2dp_generate": (_i, [_vp, _vp, _vp, _vp, _i, _d, _vp]),
     "sodso_m2dp_signature": (_i, [_vp, _vp, _vp, _vp, _i, _d, _vp]),

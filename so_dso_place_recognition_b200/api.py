@@ -135,6 +135,43 @@ def _ctx_for(*arrays, ctx=None):
 
 
 # ----------------------------------------------------------------------------------------------
+# point staging
+# ----------------------------------------------------------------------------------------------
+def pts_preprocess(pose_id, w2c, pt_id, pt_xyz, pt_inten, lidar_range=45.0, polar_filter=False, device=False, ctx=None):
+    """pts_preprocess(poses_file, pts_file, id_file, lidarRange, out_vec, polar_filter) (pts_preprocess.h:169-232)
+    on the parsed records -> dict(ids, off, xyz, inten).  Points of a scan are ordered by voxel index.
+    device=True returns xyz / inten / off as torch CUDA tensors (ready for sc_generate / m2dp_generate)."""
+    pose_id = np.ascontiguousarray(pose_id, dtype=np.int32)
+    w2c = np.ascontiguousarray(w2c, dtype=np.float64).reshape(-1, 12)
+    pt_id = np.ascontiguousarray(pt_id, dtype=np.int32)
+    pt_xyz = _prep(pt_xyz, np.float64, "float64")
+    pt_inten = _prep(pt_inten, np.float32, "float32")
+    c = _ctx_for(pt_xyz, ctx=ctx)
+    h = C.c_void_p()
+    L = N.lib()
+    N.check(L.sodso_stage_points(c.handle, _ptr(pose_id), _ptr(w2c), len(pose_id), _ptr(pt_id), _ptr(pt_xyz),
+                                 _ptr(pt_inten), len(pt_id), float(lidar_range), 1 if polar_filter else 0, C.byref(h)))
+    try:
+        ns, npts = L.sodso_staged_num_scans(h), L.sodso_staged_num_points(h)
+        ids = np.zeros(ns, dtype=np.int32)
+        if device:
+            import torch
+
+            dev = torch.device("cuda", c.device)
+            off = torch.empty(ns + 1, dtype=torch.int64, device=dev)
+            xyz = torch.empty((npts, 3), dtype=torch.float64, device=dev)
+            inten = torch.empty(npts, dtype=torch.float32, device=dev)
+        else:
+            off = np.zeros(ns + 1, dtype=np.int64)
+            xyz = np.zeros((npts, 3))
+            inten = np.zeros(npts, dtype=np.float32)
+        N.check(L.sodso_staged_copy(h, _ptr(ids), _ptr(off), _ptr(xyz), _ptr(inten)))
+    finally:
+        L.sodso_staged_destroy(h)
+    return dict(ids=ids, off=off, xyz=xyz, inten=inten)
+
+
+# ----------------------------------------------------------------------------------------------
 # generation
 # ----------------------------------------------------------------------------------------------
 def align_points_PCA(xyz, off=None, want_evec=False, ctx=None):

@@ -80,6 +80,13 @@ struct sodso_db {
   bool matched = false;
 };
 
+struct sodso_staged {
+  sodso_ctx *ctx = nullptr;
+  std::vector<int> ids;
+  std::vector<int64_t> off;   // nscan + 1
+  Buf d_off, d_xyz, d_inten;
+};
+
 namespace {
 
 #define CTX_CHECK(ctx)                                   \
@@ -674,6 +681,168 @@ int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten,
   }
   if (hist && hist != hd && (rc = finish_out(c, hist, hcnt, hd))) return rc;
   return fuse_top1_tail(c, nscan, nscan, mask_width, p_weight, idx, score, d_p_at, d_i_at);
+}
+
+// ---- point staging (pts_preprocess.h) ----------------------------------------------------------
+int sodso_stage_points(sodso_ctx *c, const int32_t *pose_id, const double *w2c, int n_pose, const int32_t *pt_id,
+                       const double *pt_xyz, const float *pt_inten, int64_t n_pts, double lidar_range,
+                       int polar_filter, sodso_staged **out) {
+  CTX_CHECK(c);
+  if (!out || n_pose < 0 || n_pts < 0 || (n_pose > 0 && (!pose_id || !w2c)) ||
+      (n_pts > 0 && (!pt_id || !pt_xyz || !pt_inten)) || !(lidar_range > 0)) {
+    set_error("bad stage_points arguments");
+    return SODSO_E_ARG;
+  }
+  *out = nullptr;
+  // the pose walk is sequential bookkeeping on ids and translations: host copies of the small arrays
+  std::vector<int32_t> h_pose_id, h_pt_id;
+  std::vector<double> h_w2c;
+  auto to_host = [&](const void *src, size_t bytes, void *dst) -> cudaError_t {
+    if (bytes == 0) return cudaSuccess;
+    if (is_device_ptr(src)) return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+    std::memcpy(dst, src, bytes);
+    return cudaSuccess;
+  };
+  h_pose_id.resize((size_t)n_pose);
+  h_w2c.resize((size_t)n_pose * 12);
+  h_pt_id.resize((size_t)n_pts);
+  SODSO_CUDA_CHECK(to_host(pose_id, (size_t)n_pose * 4, h_pose_id.data()));
+  SODSO_CUDA_CHECK(to_host(w2c, (size_t)n_pose * 96, h_w2c.data()));
+  SODSO_CUDA_CHECK(to_host(pt_id, (size_t)n_pts * 4, h_pt_id.data()));
+  StagePlan P;
+  stage_plan(h_pose_id.data(), h_w2c.data(), n_pose, h_pt_id.data(), n_pts, P);
+  const int nscan = (int)P.frame_of_scan.size();
+
+  sodso_staged *S = new sodso_staged();
+  S->ctx = c;
+  S->ids = P.ids;
+  S->off.assign((size_t)nscan + 1, 0);
+  auto fail = [&](int rc) {
+    sodso_staged_destroy(S);
+    return rc;
+  };
+  if (nscan == 0 || n_pts == 0) {
+    *out = S;
+    return SODSO_OK;
+  }
+  int rc;
+  const double *d_pts;
+  const float *d_int;
+  if ((rc = stage_in(c, pt_xyz, (size_t)n_pts * 3, c->in_xyz, &d_pts))) return fail(rc);
+  if ((rc = stage_in(c, pt_inten, (size_t)n_pts, c->in_inten, &d_int))) return fail(rc);
+  Buf b_w2c, b_entry, b_sof, b_segend, b_s0, b_s1, b_diff, b_fos, b_lo, b_hi, b_coff, b_win, b_nout, b_ws;
+  auto release_all = [&]() {
+    for (Buf *b : {&b_w2c, &b_entry, &b_sof, &b_segend, &b_s0, &b_s1, &b_diff, &b_fos, &b_lo, &b_hi, &b_coff, &b_win,
+                   &b_nout, &b_ws})
+      b->release();
+  };
+  auto up = [&](Buf &b, const void *src, size_t bytes) -> cudaError_t {
+    cudaError_t e = b.reserve(bytes ? bytes : 16);
+    if (e != cudaSuccess) return e;
+    return bytes ? cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
+  };
+#define ST_CHECK(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      set_error(std::string("stage_points: ") + #expr + ": " + cudaGetErrorString(_e));         \
+      cudaStreamSynchronize(c->stream);                                                         \
+      release_all();                                                                            \
+      return fail(SODSO_E_CUDA);                                                                \
+    }                                                                                           \
+  } while (0)
+  ST_CHECK(up(b_w2c, h_w2c.data(), h_w2c.size() * 8));
+  ST_CHECK(up(b_entry, P.entry.data(), P.entry.size() * 4));
+  ST_CHECK(up(b_sof, P.scan_of_frame.data(), P.scan_of_frame.size() * 4));
+  ST_CHECK(up(b_segend, P.seg_end.data(), P.seg_end.size() * 4));
+  ST_CHECK(b_s0.reserve((size_t)n_pts * 4));
+  ST_CHECK(b_s1.reserve((size_t)n_pts * 4));
+  ST_CHECK(b_diff.reserve(((size_t)nscan + 1) * 4));
+  ST_CHECK(cudaMemsetAsync(b_diff.p, 0, ((size_t)nscan + 1) * 4, c->stream));
+  {
+    TimedRegion tr(c, "stage_dedupe_kernel");
+    ST_CHECK(launch_stage_lifetime(d_pts, b_entry.as<int>(), n_pts, b_w2c.as<double>(), b_sof.as<int>(),
+                                   b_segend.as<int>(), lidar_range, b_s0.as<int>(), b_s1.as<int>(), b_diff.as<int>(),
+                                   c->stream, &c->launches));
+    std::vector<int> diff((size_t)nscan + 1);
+    ST_CHECK(cudaMemcpyAsync(diff.data(), b_diff.p, diff.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    ST_CHECK(cudaStreamSynchronize(c->stream));
+    std::vector<int64_t> cand_off((size_t)nscan + 1, 0);
+    int run = 0, maxcand = 0;
+    for (int s = 0; s < nscan; s++) {
+      run += diff[(size_t)s];
+      maxcand = std::max(maxcand, run);
+      cand_off[(size_t)s + 1] = cand_off[(size_t)s] + run;
+    }
+    const int grid = std::min(nscan, 2 * c->num_sms);
+    ST_CHECK(up(b_fos, P.frame_of_scan.data(), P.frame_of_scan.size() * 4));
+    ST_CHECK(up(b_lo, P.pt_lo.data(), P.pt_lo.size() * 8));
+    ST_CHECK(up(b_hi, P.pt_hi.data(), P.pt_hi.size() * 8));
+    ST_CHECK(up(b_coff, cand_off.data(), cand_off.size() * 8));
+    ST_CHECK(b_win.reserve((size_t)std::max<int64_t>(cand_off[(size_t)nscan], 1) * 4));
+    ST_CHECK(b_nout.reserve((size_t)nscan * 4));
+    ST_CHECK(b_ws.reserve(stage_dedupe_workspace_bytes(grid, maxcand, nullptr)));
+    ST_CHECK(launch_stage_dedupe(d_pts, b_w2c.as<double>(), b_s0.as<int>(), b_s1.as<int>(), b_fos.as<int>(),
+                                 b_lo.as<int64_t>(), b_hi.as<int64_t>(), b_coff.as<int64_t>(), nscan, maxcand,
+                                 lidar_range, polar_filter != 0, b_ws.p, grid, b_win.as<int>(), b_nout.as<int>(),
+                                 c->stream, &c->launches));
+    std::vector<int> n_out((size_t)nscan);
+    ST_CHECK(cudaMemcpyAsync(n_out.data(), b_nout.p, n_out.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    ST_CHECK(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < nscan; s++) S->off[(size_t)s + 1] = S->off[(size_t)s] + n_out[(size_t)s];
+    const int64_t total = S->off[(size_t)nscan];
+    ST_CHECK(S->d_off.reserve(((size_t)nscan + 1) * 8));
+    ST_CHECK(cudaMemcpyAsync(S->d_off.p, S->off.data(), ((size_t)nscan + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    ST_CHECK(S->d_xyz.reserve((size_t)std::max<int64_t>(total, 1) * 24));
+    ST_CHECK(S->d_inten.reserve((size_t)std::max<int64_t>(total, 1) * 4));
+    ST_CHECK(launch_stage_emit(d_pts, d_int, b_w2c.as<double>(), b_fos.as<int>(), b_coff.as<int64_t>(), b_win.as<int>(),
+                               S->d_off.as<int64_t>(), nscan, S->d_xyz.as<double>(), S->d_inten.as<float>(), grid,
+                               c->stream, &c->launches));
+  }
+  ST_CHECK(cudaStreamSynchronize(c->stream));
+#undef ST_CHECK
+  release_all();
+  *out = S;
+  return SODSO_OK;
+}
+
+void sodso_staged_destroy(sodso_staged *S) {
+  if (!S) return;
+  if (S->ctx) cudaSetDevice(S->ctx->device);
+  for (Buf *b : {&S->d_off, &S->d_xyz, &S->d_inten}) b->release();
+  delete S;
+}
+int sodso_staged_num_scans(sodso_staged *S) { return S ? (int)S->ids.size() : 0; }
+int64_t sodso_staged_num_points(sodso_staged *S) { return S && !S->off.empty() ? S->off.back() : 0; }
+const double *sodso_staged_xyz(sodso_staged *S) { return S ? S->d_xyz.as<double>() : nullptr; }
+const float *sodso_staged_inten(sodso_staged *S) { return S ? S->d_inten.as<float>() : nullptr; }
+const int64_t *sodso_staged_scan_off(sodso_staged *S) { return S ? S->d_off.as<int64_t>() : nullptr; }
+
+int sodso_staged_copy(sodso_staged *S, int32_t *ids, int64_t *scan_off, double *xyz, float *inten) {
+  if (!S) {
+    set_error("null staged handle");
+    return SODSO_E_ARG;
+  }
+  sodso_ctx *c = S->ctx;
+  CTX_CHECK(c);
+  const size_t ns = S->ids.size();
+  const int64_t total = S->off.empty() ? 0 : S->off.back();
+  auto put = [&](void *dst, const void *host_src, const void *dev_src, size_t bytes) -> cudaError_t {
+    if (!dst || bytes == 0) return cudaSuccess;
+    if (is_device_ptr(dst))
+      return dev_src ? cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToDevice, c->stream)
+                     : cudaMemcpyAsync(dst, host_src, bytes, cudaMemcpyHostToDevice, c->stream);
+    if (host_src) {
+      std::memcpy(dst, host_src, bytes);
+      return cudaSuccess;
+    }
+    return cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToHost, c->stream);
+  };
+  SODSO_CUDA_CHECK(put(ids, S->ids.data(), nullptr, ns * 4));
+  SODSO_CUDA_CHECK(put(scan_off, S->off.data(), nullptr, S->off.size() * 8));
+  SODSO_CUDA_CHECK(put(xyz, nullptr, S->d_xyz.p, (size_t)total * 24));
+  SODSO_CUDA_CHECK(put(inten, nullptr, S->d_inten.p, (size_t)total * 4));
+  return sync_ctx(c);
 }
 
 // ---- resident row-sharded database ---------------------------------------------------------

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 namespace sodso {
 
@@ -105,6 +106,30 @@ cudaError_t launch_sc_match_tc_block(const void *q_buf, int m, int q0, int q1, c
 // d_p / d_i: fp32 m x ldd.  Returns cudaErrorNotSupported if tensor maps cannot be encoded.
 cudaError_t launch_sc_match_tc(const void *q_buf, int m, const void *db_buf, int n, float *d_p,
                                float *d_i, int ldd, int num_sms, cudaStream_t st, int64_t *launches);
+
+// stage_points.cu : pts_preprocess on the GPU
+struct StagePlan {                  // host bookkeeping of the sequential pose walk (pts_preprocess.h:187-216)
+  std::vector<int> scan_of_frame;   // per pose: scan index, -1 for skipped frames
+  std::vector<int> seg_end;         // per pose: first later pose that resets the accumulator (n_pose if none)
+  std::vector<int> entry;           // per point: pose at which it enters nearby_pts, -1 = never
+  std::vector<int> frame_of_scan;   // per scan
+  std::vector<int> ids;             // per scan: incoming id (incoming_id_file.txt)
+  std::vector<int64_t> pt_lo, pt_hi;  // per scan: range of point indices that can be alive
+};
+void stage_plan(const int *pose_id, const double *w2c, int n_pose, const int *pt_id, int64_t n_pts, StagePlan &P);
+cudaError_t launch_stage_lifetime(const double *pt_xyz, const int *entry, int64_t n_pts, const double *w2c,
+                                  const int *scan_of_frame, const int *seg_end, double lidar_range, int *s0,
+                                  int *s1, int *cnt_diff, cudaStream_t st, int64_t *launches);
+size_t stage_dedupe_workspace_bytes(int grid, int maxcand, int *nslots_out);
+cudaError_t launch_stage_dedupe(const double *pt_xyz, const double *w2c, const int *s0, const int *s1,
+                                const int *frame_of_scan, const int64_t *pt_lo, const int64_t *pt_hi,
+                                const int64_t *cand_off, int nscan, int maxcand, double lidar_range, bool polar,
+                                void *workspace, int grid, int *win_list, int *n_out, cudaStream_t st,
+                                int64_t *launches);
+cudaError_t launch_stage_emit(const double *pt_xyz, const float *pt_inten, const double *w2c,
+                              const int *frame_of_scan, const int64_t *cand_off, const int *win_list,
+                              const int64_t *off, int nscan, double *xyz, float *inten, int grid,
+                              cudaStream_t st, int64_t *launches);
 
 // m2dp_match.cu
 cudaError_t launch_m2dp_match(const double *hist1, int m, const double *hist2, int n, float *d_p,

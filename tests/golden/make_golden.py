@@ -11,6 +11,7 @@ Run HERE (the container that has /root/reference); the GPU box only sees the .np
                         signatures for them (parity unpinned: the reference ships no signatures).
 """
 import glob
+import hashlib
 import os
 import sys
 
@@ -64,6 +65,28 @@ def main():
         print(tag, "scans", pick, "points", np.diff(off))
     out["pick"] = np.array(pick)
     np.savez_compressed(os.path.join(HERE, "real_scans_seq06.npz"), **out)
+
+    # staging_seq06_head.npz: the first 110 poses of KITTI seq06 and the points they consume, as parsed from the
+    # reference's committed poses_history_file.txt / pts_history_file.txt (inputs of pts_preprocess), plus the staged
+    # scans of the ORACLE's restatement (both filters) as one SHA-256 per scan over its points sorted lexicographically.
+    po = np.loadtxt(d + "poses_history_file.txt")[:110]
+    pt = np.loadtxt(d + "pts_history_file.txt")
+    pt = pt[pt[:, 0] <= po[-1, 0]]
+    st_in = dict(pose_id=po[:, 0].astype(np.int32), w2c=po[:, 1:13].copy(), pt_id=pt[:, 0].astype(np.int32),
+                 pt_xyz=pt[:, 1:4].copy(), pt_inten=pt[:, 4].astype(np.float32))
+    for tag, polar in (("grid", False), ("polar", True)):
+        r = O.stage_arrays(st_in["pose_id"], st_in["w2c"], st_in["pt_id"], st_in["pt_xyz"], st_in["pt_inten"], 45.0, polar)
+        rows = np.concatenate([r["xyz"], r["inten"][:, None].astype(np.float64)], axis=1)
+        dig = []
+        for s in range(len(r["ids"])):
+            blk = rows[r["off"][s]:r["off"][s + 1]]
+            dig.append(np.frombuffer(hashlib.sha256(np.ascontiguousarray(blk[np.lexsort(blk.T[::-1])]).tobytes()).digest(),
+                                     dtype=np.uint8))
+        st_in[tag + "_ids"] = r["ids"]
+        st_in[tag + "_off"] = r["off"]
+        st_in[tag + "_sha256"] = np.stack(dig)
+        print("staging", tag, len(r["ids"]), "scans", r["off"][-1], "points")
+    np.savez_compressed(os.path.join(HERE, "staging_seq06_head.npz"), **st_in)
 
 
 if __name__ == "__main__":
