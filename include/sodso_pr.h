@@ -155,6 +155,11 @@ int sodso_sc_scans_to_loops(sodso_ctx *ctx, const double *xyz, const float *inte
                             double p_weight, double *hist, int32_t *idx, double *score,
                             double *d_p_at, double *d_i_at);
 
+/* Test hook, not part of the reference surface: the fp32 angle proposal atan2(num, den)/2pi + 1/2 that the generation
+ * kernels use to PROPOSE a polar bin (accepted only outside an error-derived guard band around bin edges, otherwise
+ * SC.cpp:37 / M2DP.cpp:59 in fp64 decides).  Exposed so that tests can check the error bound the guard band rests on. */
+int sodso_debug_fast_turns(sodso_ctx *ctx, const float *num, const float *den, int64_t n, float *out);
+
 /* ---- resident, row-sharded signature database ------------------------ */
 /* A shard holds n_local consecutive DB signatures whose first row has global index
  * global_row0; the signatures stay resident in HBM in MMA operand format. */

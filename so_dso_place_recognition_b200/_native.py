@@ -59,6 +59,7 @@ _PROTOS = {
     "sodso_fuse_top1": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp]),
     "sodso_loop_top1": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _vp]),
     "sodso_sc_scans_to_loops": (_i, [_vp, _vp, _vp, _vp, _i, _d, _i, _d, _vp, _vp, _vp, _vp, _vp]),
+    "sodso_debug_fast_turns": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "sodso_db_create": (_i, [_vp, _i, _vp, _i, _i64, C.POINTER(_vp)]),
     "sodso_db_destroy": (None, [_vp]),
     "sodso_db_reload": (_i, [_vp, _vp]),

@@ -683,6 +683,25 @@ int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten,
   return fuse_top1_tail(c, nscan, nscan, mask_width, p_weight, idx, score, d_p_at, d_i_at);
 }
 
+// test hook (see include/sodso_pr.h)
+int sodso_debug_fast_turns(sodso_ctx *c, const float *num, const float *den, int64_t n, float *out) {
+  CTX_CHECK(c);
+  if (n < 0 || (n > 0 && (!num || !den || !out))) {
+    set_error("bad debug_fast_turns arguments");
+    return SODSO_E_ARG;
+  }
+  if (n == 0) return SODSO_OK;
+  const float *dn, *dd;
+  float *dout;
+  int rc;
+  if ((rc = stage_in(c, num, (size_t)n, c->h1, &dn))) return rc;
+  if ((rc = stage_in(c, den, (size_t)n, c->h2, &dd))) return rc;
+  if ((rc = stage_out(c, out, (size_t)n, c->dp32, &dout))) return rc;
+  SODSO_CUDA_CHECK(launch_fast_turns_probe(dn, dd, n, dout, c->stream));
+  if ((rc = finish_out(c, out, (size_t)n, dout))) return rc;
+  return sync_ctx(c);
+}
+
 // ---- point staging (pts_preprocess.h) ----------------------------------------------------------
 int sodso_stage_points(sodso_ctx *c, const int32_t *pose_id, const double *w2c, int n_pose, const int32_t *pt_id,
                        const double *pt_xyz, const float *pt_inten, int64_t n_pts, double lidar_range,

@@ -69,6 +69,8 @@ cudaError_t launch_sc_generate(const double *xyz, const float *inten, const int6
 cudaError_t launch_align_pca(const double *xyz, const int64_t *off, int nscan, double *out_xyz,
                              double *evec, int num_sms, cudaStream_t st, int64_t *launches);
 
+cudaError_t launch_fast_turns_probe(const float *num, const float *den, int64_t n, float *out, cudaStream_t st);
+
 // m2dp_generate.cu
 cudaError_t launch_m2dp_generate(const double *xyz, const float *inten, const int64_t *off, int nscan,
                                  double max_rho, bool do_align_and_variants, double *hist,

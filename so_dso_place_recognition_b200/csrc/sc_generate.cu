@@ -323,6 +323,21 @@ cudaError_t launch_sc_generate(const double *xyz, const float *inten, const int6
   return cudaGetLastError();
 }
 
+namespace {
+__global__ void fast_turns_probe_kernel(const float *__restrict__ num, const float *__restrict__ den, int64_t n,
+                                        float *__restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = fast_turns(num[i], den[i]);
+}
+}  // namespace
+
+// test hook: the fp32 angle proposal used by the generation kernels, so that its error bound can be checked directly
+cudaError_t launch_fast_turns_probe(const float *num, const float *den, int64_t n, float *out, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  fast_turns_probe_kernel<<<1024, 256, 0, st>>>(num, den, n, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_align_pca(const double *xyz, const int64_t *off, int nscan, double *out_xyz,
                              double *evec, int num_sms, cudaStream_t st, int64_t *launches) {
   if (nscan <= 0) return cudaSuccess;

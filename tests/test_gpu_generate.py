@@ -106,3 +106,28 @@ def test_device_resident_io(gpu_ctx, oracle):
     h = api.sc_generate(torch.from_numpy(xyz).cuda(), torch.from_numpy(inten).cuda(), torch.from_numpy(off).cuda())
     assert h.is_cuda
     _check(h.cpu().numpy(), oracle.sc_generate(xyz, inten, off))
+
+
+def test_fast_turns_error_bound(gpu_ctx):
+    """The fp32 bin proposal rests on |fast_turns(num, den) - (atan2(num, den)/2pi + 1/2)| < 2e-7 turns
+    (so_dso_place_recognition_b200/csrc/common.cuh); the guard bands of the generation kernels are 10x / 3x the
+    resulting bin-coordinate error.  Checked on 4M random directions + the axes, diagonals and tiny / huge ratios."""
+    import ctypes as C
+
+    from so_dso_place_recognition_b200 import _native as N
+
+    rng = np.random.default_rng(11)
+    n = 1 << 22
+    ang = rng.uniform(-np.pi, np.pi, n)
+    rad = np.exp(rng.uniform(np.log(1e-3), np.log(1e3), n))
+    num, den = (rad * np.sin(ang)).astype(np.float32), (rad * np.cos(ang)).astype(np.float32)
+    special = np.array([[0, 1], [1, 0], [0, -1], [-1, 0], [1, 1], [-1, 1], [1, -1], [-1, -1], [1e-30, 1], [1, 1e-30],
+                        [-1e-30, -1], [3e-39, 2e-39], [1e30, -1e30]], dtype=np.float32)
+    num, den = np.concatenate([num, special[:, 0]]), np.concatenate([den, special[:, 1]])
+    out = np.empty_like(num)
+    N.check(N.lib().sodso_debug_fast_turns(gpu_ctx.handle, num.ctypes.data_as(C.c_void_p), den.ctypes.data_as(C.c_void_p),
+                                           len(num), out.ctypes.data_as(C.c_void_p)))
+    ref = np.arctan2(num.astype(np.float64), den.astype(np.float64)) / (2 * np.pi) + 0.5
+    err = np.abs(out.astype(np.float64) - ref)
+    err = np.minimum(err, 1.0 - err)          # -pi and +pi are the same direction (bin edge -> fp64 path anyway)
+    assert err.max() < 2e-7, err.max()
