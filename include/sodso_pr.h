@@ -155,6 +155,22 @@ int sodso_sc_scans_to_loops(sodso_ctx *ctx, const double *xyz, const float *inte
                             double p_weight, double *hist, int32_t *idx, double *score,
                             double *d_p_at, double *d_i_at);
 
+/* ---- evaluation ------------------------------------------------------ */
+/* Ground-truth loop set of run_test.m:3-21.  gt1: m x 3, gt2: n x 3 positions.  nearest[i] = 0-based index of the
+ * closest gt2 position with |i - j| >= mask_width (first one on ties, -1 if none); is_loop[i] = 1 if it is closer than
+ * loop_diff (optional); *n_loops = number of loops (rows of lp_gt). */
+int sodso_gt_loops(sodso_ctx *ctx, const double *gt1, int m, const double *gt2, int n, double loop_diff,
+                   int mask_width, int32_t *nearest, int32_t *is_loop, int *n_loops);
+/* Precision / recall of run_test.m:56-85 from the per-query decision (diff_v, 0-BASED diff_idx) of
+ * sodso_loop_top1 / sodso_fuse_top1: queries ranked by ascending diff_v (stable, NaN last), cumulative true / false
+ * positives by ground-truth distance, AUC = trapz(recall, precision), top_recall = recall at the last rank with
+ * precision 1, top_count = that rank (the first top_count entries of rank_out are lp_detected(:,1) - 1).
+ * n_gt_loops: from sodso_gt_loops (MATLAB's length(lp_gt) quirk for exactly one loop is reproduced).
+ * Host pointers only; rank_out / precision_out / recall_out (m each) are optional. */
+int sodso_pr_curve(const double *diff_v, const int32_t *diff_idx, const double *gt1, int m, const double *gt2, int n,
+                   double loop_diff, int n_gt_loops, double *auc, double *top_recall, int *top_count,
+                   int32_t *rank_out, double *precision_out, double *recall_out);
+
 /* Test hook, not part of the reference surface: the fp32 angle proposal atan2(num, den)/2pi + 1/2 that the generation
  * kernels use to PROPOSE a polar bin (accepted only outside an error-derived guard band around bin edges, otherwise
  * SC.cpp:37 / M2DP.cpp:59 in fp64 decides).  Exposed so that tests can check the error bound the guard band rests on. */

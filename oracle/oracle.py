@@ -270,3 +270,55 @@ def fuse_top1_numpy(d_p, d_i, mask_width, p_weight=2.0):
     f = np.where(np.abs(ii - jj) < mask_width, np.inf, f)
     idx = np.argmin(f, axis=1).astype(np.int32)
     return idx, f[np.arange(m), idx]
+
+
+# ---------------------------------------------------------------------------------------
+# evaluation: run_test.m:2-22 (ground-truth loop set) and :56-85 (precision / recall, AUC, top recall)
+# ---------------------------------------------------------------------------------------
+def gt_loops(gt1, gt2, loop_diff, mask_width):
+    """run_test.m:3-22 -> (lp_gt as 0-based (i, j) rows, total_lp = MATLAB length(lp_gt))."""
+    gt1 = np.asarray(gt1, dtype=np.float64)
+    gt2 = np.asarray(gt2, dtype=np.float64)
+    m, n = gt1.shape[0], gt2.shape[0]
+    lp = []
+    jj = np.arange(n)
+    for i in range(m):
+        ok = np.abs(i - jj) >= mask_width                                  # :8-10
+        if not ok.any():
+            continue
+        d = gt1[i] - gt2                                                   # :11
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]   # :12
+        d2 = np.where(ok & ~np.isnan(d2), d2, np.inf)
+        j = int(np.argmin(d2))                                             # strict '>' at :13 -> first minimum
+        if d2[j] < loop_diff * loop_diff:                                  # :19
+            lp.append((i, j))
+    lp = np.array(lp, dtype=np.int64).reshape(-1, 2)
+    L = lp.shape[0]
+    total_lp = 0 if L == 0 else max(L, 2)                                  # length() of an L x 2 matrix, :22
+    return lp, total_lp
+
+
+def pr_eval(diff_v, diff_idx, gt1, gt2, total_lp, loop_diff):
+    """run_test.m:56-85 from the per-query decision (0-based diff_idx) -> dict(AUC, top_recall, top_count, rank,
+    precision, recall)."""
+    diff_v = np.asarray(diff_v, dtype=np.float64)
+    m = diff_v.shape[0]
+    key = np.where(np.isnan(diff_v), np.inf, diff_v)
+    rank = np.lexsort((np.arange(m), np.isnan(diff_v), key))               # sort: ascending, stable, NaN last (:58)
+    tp = fp = 0
+    precision, recall = np.zeros(m), np.zeros(m)
+    top_recall, top_count = 0.0, 0
+    with np.errstate(all="ignore"):
+        for i in range(m):
+            a, b = rank[i], diff_idx[rank[i]]
+            d = gt1[a] - gt2[b]
+            if (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2] < loop_diff * loop_diff:   # :68-70
+                tp += 1
+            else:
+                fp += 1
+            precision[i] = tp / (tp + fp)
+            recall[i] = np.float64(tp) / np.float64(total_lp)
+            if precision[i] == 1:                                          # :78-81
+                top_count, top_recall = i + 1, recall[i]
+        auc = float(np.sum((recall[1:] - recall[:-1]) * (precision[1:] + precision[:-1]) * 0.5)) if m > 1 else 0.0  # :84
+    return dict(AUC=auc, top_recall=float(top_recall), top_count=top_count, rank=rank, precision=precision, recall=recall)

@@ -59,6 +59,8 @@ _PROTOS = {
     "sodso_fuse_top1": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp]),
     "sodso_loop_top1": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _vp]),
     "sodso_sc_scans_to_loops": (_i, [_vp, _vp, _vp, _vp, _i, _d, _i, _d, _vp, _vp, _vp, _vp, _vp]),
+    "sodso_gt_loops": (_i, [_vp, _vp, _i, _vp, _i, _d, _i, _vp, _vp, C.POINTER(_i)]),
+    "sodso_pr_curve": (_i, [_vp, _vp, _vp, _i, _vp, _i, _d, _i, C.POINTER(_d), C.POINTER(_d), C.POINTER(_i), _vp, _vp, _vp]),
     "sodso_debug_fast_turns": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "sodso_db_create": (_i, [_vp, _i, _vp, _i, _i64, C.POINTER(_vp)]),
     "sodso_db_destroy": (None, [_vp]),

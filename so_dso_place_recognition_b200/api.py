@@ -315,6 +315,43 @@ def run_test(type, hist1, hist2, mask_width, p_weight=2.0, want_channels=False, 
     return (idx, score, dpa, dia) if want_channels else (idx, score)
 
 
+def gt_loops(gt1, gt2, loop_diff, mask_width, ctx=None):
+    """run_test.m:3-22 -> (lp_gt: 0-based (i, j) rows, n_loops)."""
+    gt1 = np.ascontiguousarray(gt1, dtype=np.float64).reshape(-1, 3)
+    gt2 = np.ascontiguousarray(gt2, dtype=np.float64).reshape(-1, 3)
+    m, n = gt1.shape[0], gt2.shape[0]
+    c = _ctx_for(ctx=ctx)
+    near = np.zeros(m, dtype=np.int32)
+    flag = np.zeros(m, dtype=np.int32)
+    cnt = C.c_int(0)
+    N.check(N.lib().sodso_gt_loops(c.handle, _ptr(gt1), m, _ptr(gt2), n, float(loop_diff), int(mask_width), _ptr(near),
+                                   _ptr(flag), C.byref(cnt)))
+    ii = np.nonzero(flag)[0]
+    return np.stack([ii, near[ii]], axis=1).astype(np.int64).reshape(-1, 2), int(cnt.value)
+
+
+def run_test_full(type, hist1, hist2, gt1, gt2, loop_diff, mask_width, p_weight=2.0, ctx=None):
+    """[AUC, top_recall, lp_detected] = run_test(type, hist1, hist2, gt1, gt2, loop_diff, mask_width)
+    (run_test.m:1-85; lp_detected 0-based).  Match / fusion / argmin and the ground-truth loop search run on the
+    GPU, the cumulative precision-recall walk on the host."""
+    gt1 = np.ascontiguousarray(gt1, dtype=np.float64).reshape(-1, 3)
+    gt2 = np.ascontiguousarray(gt2, dtype=np.float64).reshape(-1, 3)
+    lp_gt, n_loops = gt_loops(gt1, gt2, loop_diff, mask_width, ctx=ctx)
+    idx, score = run_test(type, hist1, hist2, mask_width, p_weight, ctx=ctx)
+    if _is_torch(idx):
+        idx, score = idx.cpu().numpy(), score.cpu().numpy()
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    score = np.ascontiguousarray(score, dtype=np.float64)
+    m = idx.shape[0]
+    auc, tr, tc = C.c_double(0), C.c_double(0), C.c_int(0)
+    rank = np.zeros(m, dtype=np.int32)
+    N.check(N.lib().sodso_pr_curve(_ptr(score), _ptr(idx), _ptr(gt1), m, _ptr(gt2), gt2.shape[0], float(loop_diff),
+                                   n_loops, C.byref(auc), C.byref(tr), C.byref(tc), _ptr(rank), None, None))
+    k = int(tc.value)
+    lp_detected = np.stack([rank[:k], idx[rank[:k]]], axis=1).astype(np.int64).reshape(-1, 2)
+    return float(auc.value), float(tr.value), lp_detected
+
+
 def sc_scans_to_loops(xyz, inten, scan_off, mask_width, p_weight=2.0, max_rho=45.0, want_hist=False, ctx=None):
     """test_sc.cpp:36-57 + run_test('sc', hist, hist, ...) (run_test.m:25-57, self-match as in test_kitti.m:28)
     in one call: scans in -> (diff_idx 0-based int32[n], diff_v[n] [, history_sc]).  Host (numpy / pinned torch)

@@ -683,6 +683,100 @@ int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten,
   return fuse_top1_tail(c, nscan, nscan, mask_width, p_weight, idx, score, d_p_at, d_i_at);
 }
 
+// ---- evaluation (run_test.m:2-22, 58-85) -------------------------------------------------------
+int sodso_gt_loops(sodso_ctx *c, const double *gt1, int m, const double *gt2, int n, double loop_diff,
+                   int mask_width, int32_t *nearest, int32_t *is_loop, int *n_loops) {
+  CTX_CHECK(c);
+  if (m < 0 || n < 0 || (m > 0 && !gt1) || (n > 0 && !gt2) || !nearest) {
+    set_error("bad gt_loops arguments");
+    return SODSO_E_ARG;
+  }
+  if (n_loops) *n_loops = 0;
+  if (m == 0) return SODSO_OK;
+  const double *g1, *g2;
+  int rc;
+  if ((rc = stage_in(c, gt1, (size_t)m * 3, c->h1, &g1))) return rc;
+  if ((rc = stage_in(c, gt2, (size_t)n * 3, c->h2, &g2))) return rc;
+  SODSO_CUDA_CHECK(c->idx32.reserve((size_t)m * 4));
+  SODSO_CUDA_CHECK(c->score.reserve((size_t)m * 8));
+  SODSO_CUDA_CHECK(launch_gt_loops(g1, m, g2, n, mask_width, c->idx32.as<int32_t>(), c->score.as<double>(), c->stream,
+                                   &c->launches));
+  std::vector<int32_t> near((size_t)m);
+  std::vector<double> d2((size_t)m);
+  SODSO_CUDA_CHECK(cudaMemcpyAsync(near.data(), c->idx32.p, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
+  SODSO_CUDA_CHECK(cudaMemcpyAsync(d2.data(), c->score.p, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = sync_ctx(c))) return rc;
+  int cnt = 0;
+  std::vector<int32_t> flag((size_t)m);
+  for (int i = 0; i < m; i++) {
+    flag[(size_t)i] = d2[(size_t)i] < loop_diff * loop_diff ? 1 : 0;   // run_test.m:19
+    cnt += flag[(size_t)i];
+  }
+  auto put = [&](int32_t *dst, const std::vector<int32_t> &src) -> cudaError_t {
+    if (!dst) return cudaSuccess;
+    if (is_device_ptr(dst)) return cudaMemcpy(dst, src.data(), src.size() * 4, cudaMemcpyHostToDevice);
+    std::memcpy(dst, src.data(), src.size() * 4);
+    return cudaSuccess;
+  };
+  SODSO_CUDA_CHECK(put(nearest, near));
+  SODSO_CUDA_CHECK(put(is_loop, flag));
+  if (n_loops) *n_loops = cnt;
+  return SODSO_OK;
+}
+
+// run_test.m:56-85 from the per-query decision (host pointers; sequential cumulative counts)
+int sodso_pr_curve(const double *diff_v, const int32_t *diff_idx, const double *gt1, int m, const double *gt2, int n,
+                   double loop_diff, int n_gt_loops, double *auc, double *top_recall, int *top_count,
+                   int32_t *rank_out, double *precision_out, double *recall_out) {
+  if (m < 0 || (m > 0 && (!diff_v || !diff_idx || !gt1 || !gt2))) {
+    set_error("bad pr_curve arguments");
+    return SODSO_E_ARG;
+  }
+  for (const void *p : {(const void *)diff_v, (const void *)diff_idx, (const void *)gt1, (const void *)gt2})
+    if (p && is_device_ptr(p)) {
+      set_error("pr_curve takes host pointers");
+      return SODSO_E_ARG;
+    }
+  // [~, diff_rank] = sort(diff_v): ascending, stable, NaN last (run_test.m:58)
+  std::vector<int32_t> rank((size_t)m);
+  for (int i = 0; i < m; i++) rank[(size_t)i] = i;
+  std::stable_sort(rank.begin(), rank.end(), [&](int32_t a, int32_t b) {
+    const double x = diff_v[a], y = diff_v[b];
+    const bool xn = x != x, yn = y != y;
+    if (xn || yn) return !xn && yn;
+    return x < y;
+  });
+  // length(lp_gt) of an L x 2 matrix (run_test.m:22): L, except that one loop reports 2 and none reports 0
+  const double total_lp = n_gt_loops == 1 ? 2.0 : (double)n_gt_loops;
+  double tp = 0, fp = 0, a = 0.0, tr = 0.0, prev_p = 0.0, prev_r = 0.0;
+  int tc = 0;
+  for (int i = 0; i < m; i++) {
+    const int32_t q = rank[(size_t)i], b = diff_idx[q];
+    bool hit = false;
+    if (b >= 0 && b < n) {
+      const double dx = gt1[3 * (size_t)q] - gt2[3 * (size_t)b], dy = gt1[3 * (size_t)q + 1] - gt2[3 * (size_t)b + 1],
+                   dz = gt1[3 * (size_t)q + 2] - gt2[3 * (size_t)b + 2];
+      hit = (dx * dx + dy * dy) + dz * dz < loop_diff * loop_diff;   // :68-70
+    }
+    if (hit) tp += 1; else fp += 1;                                  // :70-74
+    const double pr = tp / (tp + fp), rc = tp / total_lp;            // :75-76
+    if (precision_out) precision_out[i] = pr;
+    if (recall_out) recall_out[i] = rc;
+    if (pr == 1.0) {                                                 // :78-81
+      tc = i + 1;
+      tr = rc;
+    }
+    if (i > 0) a += (rc - prev_r) * (pr + prev_p) * 0.5;             // trapz(recall, precision), :84
+    prev_p = pr;
+    prev_r = rc;
+  }
+  if (rank_out) std::memcpy(rank_out, rank.data(), (size_t)m * 4);
+  if (auc) *auc = a;
+  if (top_recall) *top_recall = tr;
+  if (top_count) *top_count = tc;
+  return SODSO_OK;
+}
+
 // test hook (see include/sodso_pr.h)
 int sodso_debug_fast_turns(sodso_ctx *c, const float *num, const float *den, int64_t n, float *out) {
   CTX_CHECK(c);

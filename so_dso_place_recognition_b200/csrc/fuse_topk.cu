@@ -250,6 +250,45 @@ cudaError_t launch_fuse_top1_f64(const double *d_p, const double *d_i, int m, in
   return cudaGetLastError();
 }
 
+// Ground-truth loop set of run_test.m:3-21: for every query position the nearest database position outside
+// the temporal mask (first one on ties: the comparison at :13 is strict); a loop if closer than loop_diff.
+// nearest[i] = 0-based j or -1, dist2[i] = squared distance.
+__global__ void __launch_bounds__(FUSE_THREADS)
+gt_loops_kernel(const double *__restrict__ gt1, const double *__restrict__ gt2, int n, int mask_width,
+                int32_t *__restrict__ nearest, double *__restrict__ dist2) {
+  __shared__ double ss[32];
+  __shared__ long long si[32];
+  const int i = blockIdx.x;
+  const double x = gt1[3 * (size_t)i], y = gt1[3 * (size_t)i + 1], z = gt1[3 * (size_t)i + 2];
+  double bs = 0.0;
+  long long bi = -1;
+  for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
+    int dji = i - j;
+    if (dji < 0) dji = -dji;
+    if (dji < mask_width) continue;                              // run_test.m:8-10
+    const double dx = x - gt2[3 * (size_t)j], dy = y - gt2[3 * (size_t)j + 1], dz = z - gt2[3 * (size_t)j + 2];
+    const double d = (dx * dx + dy * dy) + dz * dz;              // diff*diff' (:11-12)
+    if (d != d) continue;                                        // `min_diff > diff` is false for NaN
+    if (cand_less(d, (long long)j, bs, bi)) {
+      bs = d;
+      bi = j;
+    }
+  }
+  block_argmin(bs, bi, ss, si);
+  if (threadIdx.x == 0) {
+    nearest[i] = (int32_t)bi;
+    dist2[i] = bi >= 0 ? bs : INFINITY;
+  }
+}
+
+cudaError_t launch_gt_loops(const double *gt1, int m, const double *gt2, int n, int mask_width, int32_t *nearest,
+                            double *dist2, cudaStream_t st, int64_t *launches) {
+  if (m <= 0) return cudaSuccess;
+  gt_loops_kernel<<<m, FUSE_THREADS, 0, st>>>(gt1, gt2, n, mask_width, nearest, dist2);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_f32_to_f64(const float *src, int rows, int cols, int ld, double *dst,
                               cudaStream_t st, int64_t *launches) {
   if (rows <= 0 || cols <= 0) return cudaSuccess;

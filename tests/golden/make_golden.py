@@ -88,6 +88,28 @@ def main():
         print("staging", tag, len(r["ids"]), "scans", r["off"][-1], "points")
     np.savez_compressed(os.path.join(HERE, "staging_seq06_head.npz"), **st_in)
 
+    # seq06_sc_eval.npz: Scan Context signatures of the whole KITTI seq06 (880 scans) from the oracle on the oracle's
+    # staging, reduced like the reference's text hand-over (history_sc.txt carries 6 significant digits):
+    # structure rounded to 6 significant digits and stored as float32, intensity as packed bits; ground-truth
+    # positions gt.txt(incoming_id + 1, [4 8 12]) (test_kitti.m:23-25); and the oracle's decision + evaluation for
+    # run_test('sc', hist, hist, gt, gt, 10, 100) (test_kitti.m:19-20,28).  Parity unpinned: oracle, not reference, output.
+    st = O.stage(d + "poses_history_file.txt", d + "pts_history_file.txt", 45.0, False)
+    hist = O.sc_generate(st["xyz"], st["inten"], st["off"])
+    struct6 = np.array([float("%.6g" % v) for v in hist[:, :1200].reshape(-1)]).reshape(-1, 1200).astype(np.float32)
+    bits = np.packbits(hist[:, 1200:].astype(np.uint8), axis=1)
+    gt_full = np.loadtxt(d + "gt.txt")
+    gt = gt_full[st["ids"], :][:, [3, 7, 11]]
+    h = np.concatenate([struct6.astype(np.float64), np.unpackbits(bits, axis=1)[:, :1200].astype(np.float64)], axis=1)
+    dp, di = O.sc_match_numpy(h, h)
+    idx, score = O.fuse_top1(dp, di, 100)
+    lp, total_lp = O.gt_loops(gt, gt, 10.0, 100)
+    ev = O.pr_eval(score, idx, gt, gt, total_lp, 10.0)
+    print("seq06 eval: gt loops", lp.shape[0], "AUC", ev["AUC"], "top recall", ev["top_recall"], "top count", ev["top_count"])
+    np.savez_compressed(os.path.join(HERE, "seq06_sc_eval.npz"), structure6=struct6, intensity_bits=bits, gt=gt,
+                        ids=st["ids"], idx=idx.astype(np.int32), score=score, n_gt_loops=np.int32(lp.shape[0]),
+                        lp_gt=lp, AUC=np.float64(ev["AUC"]), top_recall=np.float64(ev["top_recall"]),
+                        top_count=np.int32(ev["top_count"]))
+
 
 if __name__ == "__main__":
     main()
