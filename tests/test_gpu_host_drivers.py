@@ -66,3 +66,67 @@ def test_files_to_loops(gpu_ctx, oracle, tmp_path):
         tol = 1e-6 + 4.0 * 1e-5 * (2.0 / sp + 1.0 / si_)
         err = np.abs(got[:, 1] - rscore)
         assert np.all(err <= tol), (kind, err.max(), tol.min(), sp.min(), si_.min())
+
+
+def _write_two_laps(d, n_pose=170, seed=9):
+    """two laps around a circle through a static landmark field, written in the reference's file formats
+    (PosesPts.h:12-24,35-39) + a ground-truth position file with one 'x y z' row per incoming id"""
+    rng = np.random.default_rng(seed)
+    land = np.stack([rng.uniform(-70, 70, 30000), np.clip(rng.normal(0, 1.5, 30000), -5, 5), rng.uniform(-70, 70, 30000)], 1)
+    land_i = rng.integers(40, 2000, 30000) / 8.0
+    poses, pts, gt = [], [], []
+    for i in range(n_pose):
+        a = 4 * np.pi * i / n_pose
+        cam = np.array([40 * np.cos(a), 0.0, 40 * np.sin(a)])
+        yaw = -a                                               # looking along the track
+        c, s = np.cos(yaw), np.sin(yaw)
+        R = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+        t = -R @ cam
+        poses.append((i, np.hstack([R, t[:, None]])))
+        near = np.nonzero(np.linalg.norm(land - cam, axis=1) < 35)[0]
+        sel = rng.choice(near, min(300, len(near)), replace=False)
+        pts += [(i, land[k], land_i[k]) for k in sel]
+        gt.append(cam)
+    with open(d / "poses.txt", "w") as f:
+        for i, w in poses:
+            f.write(f"{i} " + " ".join("%.9g" % v for v in w.reshape(-1)) + " \n")
+    with open(d / "pts.txt", "w") as f:
+        for i, q, v in pts:
+            f.write(f"{i} {q[0]:.9g} {q[1]:.9g} {q[2]:.9g} {v:g}\n")
+    np.savetxt(d / "gt.txt", np.array(gt), fmt="%.9g")
+    return str(d / "poses.txt"), str(d / "pts.txt"), str(d / "gt.txt"), np.array(gt)
+
+
+def test_place_recognition_end_to_end(gpu_ctx, oracle, tmp_path):
+    """files -> GPU staging -> signatures -> loop candidates -> AUC in ONE C++ process, against the same pipeline
+    assembled from the Python mirror and against the oracle's decision on the same staged scans"""
+    import re
+
+    from so_dso_place_recognition_b200 import api
+
+    subprocess.check_call(["make", "-C", HOST, "-s"])
+    poses_f, pts_f, gt_f, gt_all = _write_two_laps(tmp_path)
+    po, pt = np.loadtxt(poses_f), np.loadtxt(pts_f)
+    for kind, polar in (("sc", False), ("m2dp", True)):
+        loops = str(tmp_path / f"loops_{kind}.txt")
+        out = subprocess.check_output([os.path.join(BIN, "place_recognition"), kind, poses_f, pts_f, "20", loops,
+                                       "--gt", gt_f, "--loop-diff", "6"], text=True)
+        got = np.loadtxt(loops)
+        st = api.pts_preprocess(po[:, 0], po[:, 1:13], pt[:, 0], pt[:, 1:4], pt[:, 4], 45.0, polar)
+        np.testing.assert_array_equal(got[:, 0].astype(int), st["ids"])
+        gen = api.sc_generate if kind == "sc" else api.m2dp_generate
+        hist = gen(st["xyz"], st["inten"], st["off"])
+        gt = gt_all[st["ids"]]
+        auc, tr, lp = api.run_test_full(kind, hist, hist, gt, gt, 6.0, 20)
+        idx, score = api.run_test(kind, hist, hist, 20)
+        np.testing.assert_array_equal(got[:, 1].astype(int) - 1, idx)
+        np.testing.assert_allclose(got[:, 2], score, rtol=1e-12, atol=1e-12)
+        assert abs(float(re.search(r"AUC = ([0-9.eE+-]+|nan)", out).group(1)) - auc) < 1e-5
+        assert abs(float(re.search(r"top_recall = ([0-9.eE+-]+)", out).group(1)) - tr) < 1e-5
+        n_loops = int(re.search(r"total_lp = (\d+)", out).group(1))
+        assert n_loops > 40 and auc > 0.5                       # the second lap is recognised
+        # the oracle's decision on the same staged scans
+        ref = (oracle.sc_generate if kind == "sc" else oracle.m2dp_generate)(st["xyz"], st["inten"], st["off"])
+        dp, di = (oracle.sc_match_numpy if kind == "sc" else oracle.m2dp_match)(ref, ref)
+        ridx, rscore = oracle.fuse_top1(dp, di, 20)
+        np.testing.assert_array_equal(idx, ridx)
