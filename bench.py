@@ -187,8 +187,8 @@ def run_ours(args):
         hq_xyz, hq_inten = pin(xyz_q), pin(inten_q)
         dq_xyz, dq_inten = hq_xyz.to(dev), hq_inten.to(dev)
     h2d_bytes = (h_xyz.numel() * 8 + h_inten.numel() * 4 + h_off.numel() * 8)
-    if rank != 0:
-        h2d_bytes *= 2
+    if world > 1:   # + this rank's 1/N slice of the replicated query scans
+        h2d_bytes += (hq_xyz.numel() * 8 + hq_inten.numel() * 4) // world
 
     kern_ms = []
     db_kernel_ms = [0.0]
@@ -200,6 +200,11 @@ def run_ours(args):
 
     api.SignatureDB.match = _timed_match
     shard_db = [None]
+    if world > 1:
+        shard_db[0] = api.SignatureDB("sc", api.sc_generate(d_xyz, d_inten, d_off, ctx=ctx), global_row0=row0, ctx=ctx)
+        qa, qb = rank * N_SCANS // world, (rank + 1) * N_SCANS // world
+        hq_off_slices = {rank: pin(np.ascontiguousarray(off_q[qa:qb + 1] - off_q[qa]))}
+        dq_off_slice = hq_off_slices[rank].to(dev)
 
     def step(host_inputs: bool):
         """one pass of the hot path; returns (idx, score) of the top-1 on the host"""
@@ -212,27 +217,27 @@ def run_ours(args):
             idx, score = api.sc_scans_to_loops(d_xyz, d_inten, d_off, MASK_WIDTH, P_WEIGHT, ctx=ctx)
             kern_ms.append(ctx.last_kernel_ms)
             return idx.cpu(), score.cpu()
+        # ---- N > 1.  Queries: every rank bins 1/N of the replicated query scans, the signatures are all-gathered
+        # over NVLink.  DB: the rank's shard is a resident sodso_db whose operand buffers are rewritten every step.
+        qa, qb = rank * N_SCANS // world, (rank + 1) * N_SCANS // world
+        pa, pb = int(off_q[qa]), int(off_q[qb])
+        hist_slice = torch.empty((qb - qa, 2400), dtype=torch.float64, device=dev)
         if host_inputs:
-            # C-ABI call with HOST point buffers (copied in by the library), signatures stay in HBM
-            hist_db = torch.empty((n_local, 2400), dtype=torch.float64, device=dev)
-            api.N.check(api.N.lib().sodso_sc_generate(ctx.handle, h_xyz.data_ptr(), h_inten.data_ptr(),
-                                                      h_off.data_ptr(), n_local, 45.0, hist_db.data_ptr()))
-            if rank == 0:
-                hist_q = hist_db
-            else:
-                hist_q = torch.empty((N_SCANS, 2400), dtype=torch.float64, device=dev)
-                api.N.check(api.N.lib().sodso_sc_generate(ctx.handle, hq_xyz.data_ptr(), hq_inten.data_ptr(),
-                                                          h_off.data_ptr(), N_SCANS, 45.0, hist_q.data_ptr()))
+            api.N.check(api.N.lib().sodso_sc_generate(ctx.handle, hq_xyz[pa:pb].data_ptr(), hq_inten[pa:pb].data_ptr(),
+                                                      hq_off_slices[rank].data_ptr(), qb - qa, 45.0, hist_slice.data_ptr()))
         else:
-            hist_db = api.sc_generate(d_xyz, d_inten, d_off)
-            hist_q = hist_db if rank == 0 else api.sc_generate(dq_xyz, dq_inten, d_off)
-        # the rank's resident shard: operand buffers rewritten in place with this step's signatures
-        if shard_db[0] is None:
-            shard_db[0] = api.SignatureDB("sc", hist_db, global_row0=row0, ctx=ctx)
+            hist_slice = api.sc_generate(dq_xyz[pa:pb], dq_inten[pa:pb], dq_off_slice, ctx=ctx)
+        hist_q = sharded.gather_query_signatures(hist_slice)
+        if host_inputs:
+            # HOST point buffers of the shard: streamed in chunks, binned and matched as they land
+            shard_db[0].stream_match(h_xyz, h_inten, h_off, hist_q)
         else:
+            hist_db = api.sc_generate(d_xyz, d_inten, d_off, ctx=ctx)
             shard_db[0].reload(hist_db)
+            shard_db[0].match(hist_q)
         # stats all-reduce + per-shard top-k all-gather + merge (so_dso_place_recognition_b200/sharded.py)
-        mi, ms, mp, md = sharded.sharded_query(shard_db[0], hist_q, n_global, 0, MASK_WIDTH, P_WEIGHT, TOPK, device=dev)
+        mi, ms, mp, md = sharded.sharded_query(shard_db[0], hist_q, n_global, 0, MASK_WIDTH, P_WEIGHT, TOPK, device=dev,
+                                               already_matched=True)
         kern_ms.append(db_kernel_ms[0])
         return torch.from_numpy(mi[:, 0]), torch.from_numpy(ms[:, 0])
 

@@ -185,6 +185,12 @@ void sodso_db_destroy(sodso_db *db);
 /* Replace the shard's signatures by n_local new ones (same size, same global_row0): the operand buffers
  * are rewritten in place, nothing is reallocated. */
 int sodso_db_reload(sodso_db *db, const double *hist2);
+/* sodso_db_reload + sodso_db_match in one streamed pass for a Scan Context shard whose scans are still POINTS:
+ * xyz / inten / scan_off describe the shard's n_local scans (test_sc.cpp:36-57 input).  Host buffers are copied in
+ * 512-scan chunks on a second stream; each chunk is binned, written into the operand buffers in place and matched
+ * against the m query signatures (hist1) as soon as it has landed.  Same state afterwards as reload + match. */
+int sodso_db_stream_match(sodso_db *db, const double *xyz, const float *inten, const int64_t *scan_off,
+                          double max_rho, const double *hist1, int m);
 int sodso_db_size(sodso_db *db);
 /* Distances of m queries against the shard (kept on the device inside the handle). */
 int sodso_db_match(sodso_db *db, const double *hist1, int m);
@@ -204,6 +210,11 @@ int sodso_db_topk(sodso_db *db, const double *global_stats, int64_t n_global,
 int sodso_topk_merge(const int64_t *idx, const double *score, const double *d_p,
                      const double *d_i, int nshards, int m, int k, int64_t *out_idx,
                      double *out_score, double *out_d_p, double *out_d_i);
+/* The same merge on the GPU for gathered lists that live in HBM (what an NCCL all-gather leaves there): device
+ * pointers only, at most 16 shards. */
+int sodso_topk_merge_device(sodso_ctx *ctx, const int64_t *idx, const double *score, const double *d_p,
+                            const double *d_i, int nshards, int m, int k, int64_t *out_idx,
+                            double *out_score, double *out_d_p, double *out_d_i);
 /* Copy the last sodso_db_match result (fp32, m x n_local each; either may be NULL) out. */
 int sodso_db_get_distances(sodso_db *db, float *d_p, float *d_i);
 

@@ -65,11 +65,13 @@ _PROTOS = {
     "sodso_db_create": (_i, [_vp, _i, _vp, _i, _i64, C.POINTER(_vp)]),
     "sodso_db_destroy": (None, [_vp]),
     "sodso_db_reload": (_i, [_vp, _vp]),
+    "sodso_db_stream_match": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _i]),
     "sodso_db_size": (_i, [_vp]),
     "sodso_db_match": (_i, [_vp, _vp, _i]),
     "sodso_db_partial_stats": (_i, [_vp, _vp]),
     "sodso_db_topk": (_i, [_vp, _vp, _i64, _i64, _i, _d, _i, _vp, _vp, _vp, _vp]),
     "sodso_topk_merge": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "sodso_topk_merge_device": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sodso_db_get_distances": (_i, [_vp, _vp, _vp]),
 }
 

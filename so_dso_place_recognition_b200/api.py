@@ -411,6 +411,20 @@ class SignatureDB:
         _ctx_for(hist2, ctx=self.ctx)
         N.check(N.lib().sodso_db_reload(self._h, _ptr(hist2)))
 
+    def stream_match(self, xyz, inten, scan_off, hist1, max_rho=45.0):
+        """reload + match in one streamed pass: the shard's scans as points (host buffers are streamed in chunks,
+        binned and matched against hist1 as they land)"""
+        xyz = _prep(xyz, np.float64, "float64")
+        inten = _prep(inten, np.float32, "float32")
+        scan_off = _prep(scan_off, np.int64, "int64")
+        hist1 = _prep(hist1, np.float64, "float64")
+        assert scan_off.shape[0] - 1 == self.n
+        self.m = hist1.shape[0] // self._rows
+        self._ref = hist1
+        _ctx_for(hist1, xyz, ctx=self.ctx)
+        N.check(N.lib().sodso_db_stream_match(self._h, _ptr(xyz), _ptr(inten), _ptr(scan_off), float(max_rho),
+                                              _ptr(hist1), self.m))
+
     def match(self, hist1):
         hist1 = _prep(hist1, np.float64, "float64")
         _ctx_for(hist1, ctx=self.ctx)
@@ -442,6 +456,20 @@ class SignatureDB:
         di = _empty_like_kind(ref, (self.m, self.n), np.float32, "float32")
         N.check(N.lib().sodso_db_get_distances(self._h, _ptr(dp), _ptr(di)))
         return dp, di
+
+
+def topk_merge_device(idx, score, d_p, d_i, ctx=None):
+    """topk_merge for gathered lists in HBM (R x m x k torch CUDA tensors) -> (m x k) torch CUDA tensors."""
+    import torch
+
+    idx, score, d_p, d_i = (t.contiguous() for t in (idx, score, d_p, d_i))
+    R, m, k = idx.shape
+    c = _ctx_for(idx, score, ctx=ctx)
+    oi = torch.empty((m, k), dtype=torch.int64, device=idx.device)
+    os_, op, od = (torch.empty((m, k), dtype=torch.float64, device=idx.device) for _ in range(3))
+    N.check(N.lib().sodso_topk_merge_device(c.handle, _ptr(idx), _ptr(score), _ptr(d_p), _ptr(d_i), R, m, k, _ptr(oi),
+                                            _ptr(os_), _ptr(op), _ptr(od)))
+    return oi, os_, op, od
 
 
 def topk_merge(idx, score, d_p, d_i):

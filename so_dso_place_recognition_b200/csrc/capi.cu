@@ -1020,6 +1020,111 @@ int sodso_db_reload(sodso_db *db, const double *hist2) {
   return sync_ctx(c);
 }
 
+// reload + match in one streamed pass: the shard's scans arrive as HOST point buffers, are copied in 512-scan chunks
+// on the copy stream, binned and written into the operand buffers in place, and every chunk is matched against the m
+// queries as soon as it has landed.  Afterwards the handle is in the state sodso_db_reload + sodso_db_match leave it in.
+int sodso_db_stream_match(sodso_db *db, const double *xyz, const float *inten, const int64_t *off, double max_rho,
+                          const double *hist1, int m) {
+  if (!db || !xyz || !inten || !off || !hist1 || m <= 0) {
+    set_error("bad db_stream_match arguments");
+    return SODSO_E_ARG;
+  }
+  sodso_ctx *c = db->ctx;
+  CTX_CHECK(c);
+  if (db->type != SODSO_TYPE_SC || db->op_algo != SODSO_ALGO_TC) {
+    set_error("db_stream_match: Scan Context shards with the tensor-core matcher only");
+    return SODSO_E_STATE;
+  }
+  const int n = db->n;
+  int rc;
+  int64_t total = 0;
+  if ((rc = check_offsets_host(off, n, &total))) return rc;
+  db->matched = false;
+  const bool host_pts = !is_device_ptr(xyz) && !is_device_ptr(inten) && !is_device_ptr(off);
+  const int CH = 512;
+  const bool streamed = host_pts && n >= 4 * CH;
+  const int nchunk = streamed ? (n + CH - 1) / CH : 1;
+  // queries: operand first (it gates every block)
+  const double *hq;
+  if ((rc = stage_in(c, hist1, (size_t)m * 2 * SC_SIZE, db->q_in, &hq))) return rc;
+  if ((rc = sc_prepare(c, db->op_algo, hq, m, db->q_op, false))) return rc;
+  const double *xd = xyz;
+  const float *id = inten;
+  const int64_t *od;
+  if (host_pts) {
+    SODSO_CUDA_CHECK(c->in_xyz.reserve((size_t)total * 3 * sizeof(double)));
+    SODSO_CUDA_CHECK(c->in_inten.reserve((size_t)total * sizeof(float)));
+    xd = c->in_xyz.as<double>();
+    id = c->in_inten.as<float>();
+  }
+  if ((rc = stage_in(c, off, (size_t)n + 1, c->in_off, &od))) return rc;
+  SODSO_CUDA_CHECK(c->out_hist.reserve((size_t)n * 2 * SC_SIZE * sizeof(double)));
+  double *hd = c->out_hist.as<double>();
+  const size_t cnt = (size_t)m * n;
+  SODSO_CUDA_CHECK(db->dp.reserve(cnt * 4));
+  SODSO_CUDA_CHECK(db->di.reserve(cnt * 4));
+  SODSO_CUDA_CHECK(db->op.reserve(sc_tc_db_bytes(n)));
+  SODSO_CUDA_CHECK(launch_sc_tc_clear_flags(db->op.p, c->stream));
+  std::vector<cudaEvent_t> evs;
+  if (streamed) {
+    if (!c->copy_stream) SODSO_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    cudaEvent_t e0;
+    SODSO_CUDA_CHECK(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+    SODSO_CUDA_CHECK(cudaEventRecord(e0, c->stream));
+    SODSO_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, e0, 0));
+    cudaEventDestroy(e0);
+    evs.resize(nchunk, nullptr);
+    for (int k = 0; k < nchunk; k++) {
+      const int s0 = k * CH, s1 = std::min(n, s0 + CH);
+      const int64_t p0 = off[s0], p1 = off[s1];
+      if (p1 > p0) {
+        SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_xyz.as<double>() + 3 * p0, xyz + 3 * p0,
+                                         (size_t)(p1 - p0) * 3 * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+        SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_inten.as<float>() + p0, inten + p0, (size_t)(p1 - p0) * sizeof(float),
+                                         cudaMemcpyHostToDevice, c->copy_stream));
+      }
+      SODSO_CUDA_CHECK(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
+      SODSO_CUDA_CHECK(cudaEventRecord(evs[k], c->copy_stream));
+    }
+  } else if (host_pts) {
+    SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_xyz.p, xyz, (size_t)total * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_inten.p, inten, (size_t)total * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  }
+  const int n_pad = sc_tc_db_rows_padded(n);
+  c->kname = "sc_match_tc_kernel";
+  c->ev_valid = false;
+  rc = SODSO_OK;
+  for (int k = 0; k < nchunk && rc == SODSO_OK; k++) {
+    const int s0 = streamed ? k * CH : 0, s1 = streamed ? std::min(n, s0 + CH) : n;
+    const bool last = k == nchunk - 1;
+    cudaError_t e = cudaSuccess;
+    if (streamed) e = cudaStreamWaitEvent(c->stream, evs[k], 0);
+    if (e == cudaSuccess)
+      e = launch_sc_generate(xd, id, od + s0, s1 - s0, max_rho, hd + (size_t)s0 * 2 * SC_SIZE, c->num_sms, c->stream,
+                             &c->launches);
+    if (e == cudaSuccess)
+      e = launch_sc_tc_prep_db_rows(hd, n, s0, last ? n_pad : s1, db->op.p, c->stream, &c->launches);
+    if (!streamed && e == cudaSuccess) c->ev_valid = cudaEventRecord(c->ev0, c->stream) == cudaSuccess;
+    if (e == cudaSuccess)
+      e = launch_sc_match_tc_block(db->q_op.p, m, 0, m, db->op.p, n, s0, s1, db->dp.as<float>(), db->di.as<float>(), n,
+                                   c->num_sms, c->stream, &c->launches);
+    if (!streamed && c->ev_valid) c->ev_valid = cudaEventRecord(c->ev1, c->stream) == cudaSuccess;
+    if (e != cudaSuccess) {
+      set_error(std::string("db_stream_match: ") + cudaGetErrorString(e));
+      rc = SODSO_E_CUDA;
+    }
+  }
+  for (cudaEvent_t ev : evs)
+    if (ev) cudaEventDestroy(ev);
+  if (rc) {
+    cudaStreamSynchronize(c->stream);
+    return rc;
+  }
+  db->m = m;
+  db->matched = true;
+  return sync_ctx(c);
+}
+
 void sodso_db_destroy(sodso_db *db) {
   if (!db) return;
   cudaSetDevice(db->ctx->device);
@@ -1119,6 +1224,24 @@ int sodso_db_topk(sodso_db *db, const double *global_stats, int64_t n_global, in
   if ((rc = finish_out(c, score, cnt, sd))) return rc;
   if ((rc = finish_out(c, d_p, cnt, pa))) return rc;
   if ((rc = finish_out(c, d_i, cnt, ia))) return rc;
+  return sync_ctx(c);
+}
+
+int sodso_topk_merge_device(sodso_ctx *c, const int64_t *idx, const double *score, const double *d_p,
+                            const double *d_i, int nshards, int m, int k, int64_t *out_idx, double *out_score,
+                            double *out_d_p, double *out_d_i) {
+  CTX_CHECK(c);
+  if (!idx || !score || !out_idx || !out_score || nshards <= 0 || nshards > 16 || m < 0 || k <= 0) {
+    set_error("bad topk_merge_device arguments (at most 16 shards)");
+    return SODSO_E_ARG;
+  }
+  for (const void *p : {(const void *)idx, (const void *)score, (const void *)out_idx, (const void *)out_score})
+    if (!is_device_ptr(p)) {
+      set_error("topk_merge_device takes device pointers");
+      return SODSO_E_ARG;
+    }
+  SODSO_CUDA_CHECK(launch_topk_merge(idx, score, d_p, d_i, nshards, m, k, out_idx, out_score, out_d_p, out_d_i,
+                                     c->stream, &c->launches));
   return sync_ctx(c);
 }
 

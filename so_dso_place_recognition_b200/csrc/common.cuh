@@ -152,6 +152,9 @@ cudaError_t launch_fuse_topk(const float *d_p, const float *d_i, int m, int n, i
 cudaError_t launch_fuse_top1_f64(const double *d_p, const double *d_i, int m, int n, int mask_width,
                                  double p_weight, int32_t *idx, double *score, cudaStream_t st,
                                  int64_t *launches);
+cudaError_t launch_topk_merge(const int64_t *idx, const double *score, const double *d_p, const double *d_i,
+                              int nshards, int m, int k, int64_t *out_idx, double *out_score, double *out_d_p,
+                              double *out_d_i, cudaStream_t st, int64_t *launches);
 cudaError_t launch_gt_loops(const double *gt1, int m, const double *gt2, int n, int mask_width,
                             int32_t *nearest, double *dist2, cudaStream_t st, int64_t *launches);
 cudaError_t launch_f32_to_f64(const float *src, int rows, int cols, int ld, double *dst,

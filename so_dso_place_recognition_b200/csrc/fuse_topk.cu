@@ -281,6 +281,55 @@ gt_loops_kernel(const double *__restrict__ gt1, const double *__restrict__ gt2, 
   }
 }
 
+// Merge of R per-shard top-k lists (each ascending by (score, index)) into the global top-k of every query: one
+// thread per query walks the R list heads k times.  idx < 0 marks an exhausted list.
+__global__ void topk_merge_kernel(const int64_t *__restrict__ idx, const double *__restrict__ score,
+                                  const double *__restrict__ d_p, const double *__restrict__ d_i, int nshards, int m,
+                                  int k, int64_t *__restrict__ out_idx, double *__restrict__ out_score,
+                                  double *__restrict__ out_d_p, double *__restrict__ out_d_i) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= m) return;
+  int pos[16];   // list heads (at most 16 shards)
+  for (int s = 0; s < 16; s++) pos[s] = 0;
+  for (int r = 0; r < k; r++) {
+    int best = -1;
+    size_t bo = 0;
+    for (int s = 0; s < nshards; s++) {
+      if (pos[s] >= k) continue;
+      const size_t o = ((size_t)s * m + q) * k + pos[s];
+      if (idx[o] < 0) continue;
+      if (best < 0 || score[o] < score[bo] || (score[o] == score[bo] && idx[o] < idx[bo])) {
+        best = s;
+        bo = o;
+      }
+    }
+    const size_t oo = (size_t)q * k + r;
+    if (best < 0) {
+      out_idx[oo] = -1;
+      out_score[oo] = NAN;
+      if (out_d_p) out_d_p[oo] = NAN;
+      if (out_d_i) out_d_i[oo] = NAN;
+    } else {
+      out_idx[oo] = idx[bo];
+      out_score[oo] = score[bo];
+      if (out_d_p) out_d_p[oo] = d_p ? d_p[bo] : NAN;
+      if (out_d_i) out_d_i[oo] = d_i ? d_i[bo] : NAN;
+      pos[best]++;
+    }
+  }
+}
+
+cudaError_t launch_topk_merge(const int64_t *idx, const double *score, const double *d_p, const double *d_i,
+                              int nshards, int m, int k, int64_t *out_idx, double *out_score, double *out_d_p,
+                              double *out_d_i, cudaStream_t st, int64_t *launches) {
+  if (m <= 0) return cudaSuccess;
+  if (nshards > 16) return cudaErrorInvalidValue;
+  topk_merge_kernel<<<(m + 127) / 128, 128, 0, st>>>(idx, score, d_p, d_i, nshards, m, k, out_idx, out_score, out_d_p,
+                                                     out_d_i);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_gt_loops(const double *gt1, int m, const double *gt2, int n, int mask_width, int32_t *nearest,
                             double *dist2, cudaStream_t st, int64_t *launches) {
   if (m <= 0) return cudaSuccess;

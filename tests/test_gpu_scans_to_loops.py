@@ -56,3 +56,22 @@ def test_streamed_equals_unstreamed(gpu_ctx, nscan):
     pin = lambda a: torch.from_numpy(a).pin_memory()
     idx_p, score_p = api.sc_scans_to_loops(pin(xyz), pin(inten), pin(off), 100)
     assert np.array_equal(idx_p, idx_s) and np.array_equal(score_p, score_s)
+
+
+def test_db_stream_match_equals_reload_match(gpu_ctx):
+    """resident shard: streamed reload + match from HOST point buffers == sodso_db_reload + sodso_db_match"""
+    n, m = 2300, 96
+    xyz, inten, off = synth.make_scan_set(n, 160, planted_loops=True)
+    hist = api.sc_generate(xyz, inten, off)
+    db = api.SignatureDB("sc", hist, global_row0=0)
+    q = hist[n // 2:n // 2 + m]
+    db.match(q)
+    dp0, di0 = db.distances()
+    db.reload(np.zeros_like(hist))                      # wipe the operand
+    db.stream_match(xyz, inten, off, q)                 # host buffers: 5 chunks, the last one ragged
+    dp1, di1 = db.distances()
+    assert np.array_equal(dp0, dp1) and np.array_equal(di0, di1)
+    st = db.partial_stats()
+    idx, score, _, _ = db.topk(st, n, n // 2, 100, 2.0, 4)
+    assert (idx[:, 0] == np.arange(m)).mean() > 0.5     # planted loops (sparse 160-point scans: not all of them)
+    db.close()
