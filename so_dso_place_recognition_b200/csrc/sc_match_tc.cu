@@ -183,7 +183,7 @@ __device__ __forceinline__ unsigned char slot_nibbles(const RowPrep &S, int ch, 
 
 __global__ void __launch_bounds__(256)
 sc_tc_prep_db_kernel(const double *__restrict__ hist, int n, int n_pad, unsigned char *__restrict__ buf,
-                     size_t off_f16, size_t off_f8, size_t off_f4, size_t off_norm, int row0) {
+                     size_t off_f16, size_t off_f8, size_t off_f4, size_t off_norm, int row0, int want_f8) {
   __shared__ RowPrep S;
   const int row = row0 + blockIdx.x;
   prep_row(hist + (size_t)row * 2 * SC_SIZE, row < n, S);
@@ -201,7 +201,7 @@ sc_tc_prep_db_kernel(const double *__restrict__ hist, int n, int n_pad, unsigned
     }
     // k = chunk*960 + sector*16 + t ; slot = chunk*16 + t
     unsigned char *o8 = buf + off_f8 + ((size_t)ch * n_pad + row) * K_F8;
-    for (int k = threadIdx.x; k < K_F8; k += blockDim.x) {
+    for (int k = threadIdx.x; want_f8 && k < K_F8; k += blockDim.x) {
       const int j = k / (UNITS_PER_CHUNK * 16), rem = k - j * (UNITS_PER_CHUNK * 16);
       o8[k] = slot_bits(S, ch, rem >> 4, j * 16 + (rem & 15));
     }
@@ -211,37 +211,54 @@ sc_tc_prep_db_kernel(const double *__restrict__ hist, int n, int n_pad, unsigned
 
 // Query operand: per (channel, base, query pair): [chunk][unit 2u+b][16 B], unit u = sector u % 60 of
 // the base vector of query b of the pair (x: the query image, y: its sector reversal y[c] = x[(60-c)%60]).
+// One CTA prepares a query PAIR, so that the interleaved units are written as one contiguous, fully coalesced
+// stream of 16-byte stores.
 __global__ void __launch_bounds__(256)
 sc_tc_prep_query_kernel(const double *__restrict__ hist, int m, int m_pad, unsigned char *__restrict__ buf,
-                        size_t off_f16, size_t off_f8, size_t off_f4, size_t off_norm, int row0) {
-  __shared__ RowPrep S;
-  const int row = row0 + blockIdx.x;
-  prep_row(hist + (size_t)row * 2 * SC_SIZE, row < m, S);
-  if (threadIdx.x < 2 && S.nonbin[threadIdx.x]) atomicOr(reinterpret_cast<int *>(buf) + threadIdx.x, 1);
-  const int pair = row >> 1, b = row & 1, npairs = m_pad >> 1;
+                        size_t off_f16, size_t off_f8, size_t off_f4, size_t off_norm, int pair0, int want_f8) {
+  __shared__ RowPrep S[2];
+  const int pair = pair0 + blockIdx.x, npairs = m_pad >> 1;
+  for (int b = 0; b < 2; b++) {
+    const int row = 2 * pair + b;
+    prep_row(hist + (size_t)row * 2 * SC_SIZE, row < m, S[b]);
+    if (threadIdx.x < 2 && S[b].nonbin[threadIdx.x]) atomicOr(reinterpret_cast<int *>(buf) + threadIdx.x, 1);
+    if (threadIdx.x < 2)
+      reinterpret_cast<float *>(buf + off_norm)[(size_t)threadIdx.x * m_pad + row] = S[b].inv_norm[threadIdx.x];
+  }
   for (int ch = 0; ch < 2; ch++)
     for (int base = 0; base < 2; base++) {
-      __half *o = reinterpret_cast<__half *>(buf + off_f16 +
-                                             (((size_t)ch * 2 + base) * npairs + pair) * F16_CHUNKS * CHUNK_BYTES);
-      for (int e = threadIdx.x; e < F16_CHUNKS * 128 * 8; e += blockDim.x) {
-        const int t = e & 7, u = (e >> 3) & 127, j = e >> 10;
+      const size_t pb = ((size_t)ch * 2 + base) * npairs + pair;
+      // fp16: 8 chunks x 256 units of 8 halves
+      uint4 *o = reinterpret_cast<uint4 *>(buf + off_f16 + pb * F16_CHUNKS * CHUNK_BYTES);
+      for (int e = threadIdx.x; e < F16_CHUNKS * Q_UNITS; e += blockDim.x) {
+        const int b = e & 1, u = (e >> 1) & 127, j = e >> 8;
         const int cs = u % SC_NUM_S, c = base == 0 ? cs : (SC_NUM_S - cs) % SC_NUM_S;
-        o[((size_t)j * Q_UNITS + 2 * u + b) * 8 + t] = slot_value(S, ch, c, j * 8 + t, false);
+        __align__(16) __half v[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) v[t] = slot_value(S[b], ch, c, j * 8 + t, false);
+        o[e] = *reinterpret_cast<const uint4 *>(v);
       }
-      unsigned char *o8 = buf + off_f8 + (((size_t)ch * 2 + base) * npairs + pair) * F8_CHUNKS * CHUNK_BYTES;
-      for (int e = threadIdx.x; e < F8_CHUNKS * 128 * 16; e += blockDim.x) {
-        const int t = e & 15, u = (e >> 4) & 127, j = e >> 11;
-        const int cs = u % SC_NUM_S, c = base == 0 ? cs : (SC_NUM_S - cs) % SC_NUM_S;
-        o8[((size_t)j * Q_UNITS + 2 * u + b) * 16 + t] = slot_bits(S, ch, c, j * 16 + t);
+      if (want_f8) {
+        uint4 *o8 = reinterpret_cast<uint4 *>(buf + off_f8 + pb * F8_CHUNKS * CHUNK_BYTES);
+        for (int e = threadIdx.x; e < F8_CHUNKS * Q_UNITS; e += blockDim.x) {
+          const int b = e & 1, u = (e >> 1) & 127, j = e >> 8;
+          const int cs = u % SC_NUM_S, c = base == 0 ? cs : (SC_NUM_S - cs) % SC_NUM_S;
+          __align__(16) unsigned char v[16];
+#pragma unroll
+          for (int t = 0; t < 16; t++) v[t] = slot_bits(S[b], ch, c, j * 16 + t);
+          o8[e] = *reinterpret_cast<const uint4 *>(v);
+        }
       }
-      unsigned char *o4 = buf + off_f4 + (((size_t)ch * 2 + base) * npairs + pair) * CHUNK_BYTES;
-      for (int e = threadIdx.x; e < 128 * 16; e += blockDim.x) {
-        const int t = e & 15, u = e >> 4;
+      uint4 *o4 = reinterpret_cast<uint4 *>(buf + off_f4 + pb * CHUNK_BYTES);
+      for (int e = threadIdx.x; e < Q_UNITS; e += blockDim.x) {
+        const int b = e & 1, u = e >> 1;
         const int cs = u % SC_NUM_S, c = base == 0 ? cs : (SC_NUM_S - cs) % SC_NUM_S;
-        o4[((size_t)2 * u + b) * 16 + t] = slot_nibbles(S, ch, c, t);
+        __align__(16) unsigned char v[16];
+#pragma unroll
+        for (int t = 0; t < 16; t++) v[t] = slot_nibbles(S[b], ch, c, t);
+        o4[e] = *reinterpret_cast<const uint4 *>(v);
       }
     }
-  if (threadIdx.x < 2) reinterpret_cast<float *>(buf + off_norm)[(size_t)threadIdx.x * m_pad + row] = S.inv_norm[threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -738,6 +755,12 @@ PFN_encodeTiled get_encode() {
 
 }  // namespace
 
+// debug flags (SODSO_TC_FLAGS): 1 skip epilogue loads, 2 skip MMAs, 4 force generic mode, 8 binary channel in e4m3
+static int tc_flags() {
+  const char *e = getenv("SODSO_TC_FLAGS");
+  return e ? atoi(e) : 0;
+}
+
 size_t sc_tc_db_bytes(int n) { return DbLayout(n).total; }
 size_t sc_tc_query_bytes(int m) { return QLayout(m).total; }
 
@@ -756,7 +779,7 @@ cudaError_t launch_sc_tc_prep_db_rows(const double *hist, int n, int row0, int r
   if (row1 <= row0) return cudaSuccess;
   DbLayout L(n);
   sc_tc_prep_db_kernel<<<row1 - row0, 256, 0, st>>>(hist, n, L.n_pad, reinterpret_cast<unsigned char *>(db_buf),
-                                                    L.off_f16, L.off_f8, L.off_f4, L.off_norm, row0);
+                                                    L.off_f16, L.off_f8, L.off_f4, L.off_norm, row0, tc_flags() & 8);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -765,8 +788,10 @@ cudaError_t launch_sc_tc_prep_query_rows(const double *hist, int m, int row0, in
                                          int64_t *launches) {
   if (row1 <= row0) return cudaSuccess;
   QLayout L(m);
-  sc_tc_prep_query_kernel<<<row1 - row0, 256, 0, st>>>(hist, m, L.m_pad, reinterpret_cast<unsigned char *>(q_buf),
-                                                       L.off_f16, L.off_f8, L.off_f4, L.off_norm, row0);
+  if (row0 & 1) return cudaErrorInvalidValue;   // one CTA per query pair
+  sc_tc_prep_query_kernel<<<(row1 - row0 + 1) / 2, 256, 0, st>>>(hist, m, L.m_pad, reinterpret_cast<unsigned char *>(q_buf),
+                                                                 L.off_f16, L.off_f8, L.off_f4, L.off_norm, row0 / 2,
+                                                                 tc_flags() & 8);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -830,8 +855,7 @@ cudaError_t launch_sc_match_tc_block(const void *q_buf, int m, int q0, int q1, c
   P.tile0 = r0 / TILE_M;
   P.n_units = 2 * ((q1 - q0 + QG - 1) / QG);
   P.n_tiles = (r1 - r0 + TILE_M - 1) / TILE_M;
-  P.flags = 0;
-  if (const char *e = getenv("SODSO_TC_FLAGS")) P.flags = atoi(e);
+  P.flags = tc_flags();
   const long long W = (long long)P.n_units * P.n_tiles;
   int npairs = num_sms / 2;
   if (npairs > W) npairs = (int)W;
