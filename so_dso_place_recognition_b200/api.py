@@ -135,6 +135,40 @@ def _ctx_for(*arrays, ctx=None):
 
 
 # ----------------------------------------------------------------------------------------------
+# signature files: the reference's text matrices (test_sc.cpp:63-66 / test_kitti.m:26) and the binary container of
+# so_dso_place_recognition_b200/host/sodso_host.hpp (SURVEY.md §8f N2)
+# ----------------------------------------------------------------------------------------------
+_HIST_MAGIC = b"SODSOHST"
+
+
+def save_history(path, hist):
+    """.bin -> binary container (64-byte header + row-major little-endian f64), anything else -> text, 6 significant
+    digits like Eigen's operator<< (column alignment is cosmetic and not reproduced here)."""
+    hist = np.ascontiguousarray(hist.cpu().numpy() if _is_torch(hist) else hist, dtype=np.float64)
+    if str(path).endswith(".bin"):
+        with open(path, "wb") as f:
+            f.write(_HIST_MAGIC + np.array([1, 0], dtype="<u4").tobytes() + np.array(hist.shape, dtype="<u8").tobytes() + bytes(32))
+            f.write(hist.astype("<f8").tobytes())
+    else:
+        np.savetxt(path, hist, fmt="%.6g")
+
+
+def load_history(path, mmap=True):
+    """text matrix (numpy.loadtxt, like MATLAB load) or binary container (memory-mapped by default)."""
+    with open(path, "rb") as f:
+        head = f.read(64)
+    if head[:8] != _HIST_MAGIC:
+        return np.loadtxt(path, ndmin=2)
+    version, dtype = np.frombuffer(head[8:16], dtype="<u4")
+    rows, cols = (int(v) for v in np.frombuffer(head[16:32], dtype="<u8"))
+    if version != 1 or dtype != 0:
+        raise ValueError(f"{path}: unsupported signature container version {version} / dtype {dtype}")
+    if mmap:
+        return np.memmap(path, dtype="<f8", mode="r", offset=64, shape=(rows, cols))
+    return np.fromfile(path, dtype="<f8", offset=64, count=rows * cols).reshape(rows, cols)
+
+
+# ----------------------------------------------------------------------------------------------
 # point staging
 # ----------------------------------------------------------------------------------------------
 def pts_preprocess(pose_id, w2c, pt_id, pt_xyz, pt_inten, lidar_range=45.0, polar_filter=False, device=False, ctx=None):

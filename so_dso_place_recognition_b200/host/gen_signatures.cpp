@@ -1,6 +1,7 @@
 // gen_signatures: the batch drivers test_sc.cpp / test_m2dp.cpp without ROS.
 //   gen_signatures sc|m2dp <poses_history_file> <pts_history_file> <out_history_file> <incoming_id_file>
 //                  [lidarRange=45] [--full-precision] [--stage-only]
+// An output name ending in .bin selects the binary signature container (sodso_host.hpp) instead of text.
 // Same inputs / outputs as lidar.launch:15-21: reads the two SO-DSO text files, writes
 // incoming_id_file.txt and history_sc.txt (N x 2400) or history_m2dp.txt (4N x 384).
 // --stage-only stops after pts_preprocess (no GPU needed): used by the incoming-id known-answer test.
@@ -14,7 +15,7 @@ int main(int argc, char **argv) {
   if (argc == 4 && !std::strcmp(argv[1], "reformat")) {   // read a text matrix, write it back Eigen-style
     size_t r, c;
     std::vector<double> m = read_history(argv[2], r, c);
-    write_history(argv[3], m.data(), r, c);
+    write_history_auto(argv[3], m.data(), r, c);   // .bin -> binary container, else Eigen-style text
     return 0;
   }
   if (argc < 6) {
@@ -64,7 +65,7 @@ int main(int argc, char **argv) {
     std::printf("%s average time: %.6f ms (kernel %s: %.3f ms for the batch)\n", type == "sc" ? "SC" : "M2DP",
                 scans.empty() ? 0.0 : 1e3 * std::chrono::duration<double>(g1 - g0).count() / scans.size(),
                 sodso_ctx_last_kernel_name(ctx.get()), sodso_ctx_last_kernel_ms(ctx.get()));
-    write_history(argv[4], hist.data(), rows, cols, full);
+    write_history_auto(argv[4], hist.data(), rows, cols, full);
   } catch (const std::exception &e) {
     std::fprintf(stderr, "gen_signatures: %s\n", e.what());
     return 2;

@@ -91,7 +91,7 @@ int main(int argc, char **argv) {
     auto t3 = std::chrono::steady_clock::now();
     sodso_staged_destroy(st);
     std::printf("%s\ntm = %.6f ms per query (signatures + %d x %d pairs)\n", type.c_str(), 1e3 * secs(t2, t3) / n, n, n);
-    if (!hist_file.empty()) write_history(hist_file, hist.data(), rows, cols);
+    if (!hist_file.empty()) write_history_auto(hist_file, hist.data(), rows, cols);
     {
       std::ofstream f(argv[5]);
       f << std::setprecision(17);

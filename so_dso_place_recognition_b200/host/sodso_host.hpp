@@ -7,6 +7,7 @@
 //   class SC, class M2DP                <- .../src/SC/SC.h:10-23, .../src/M2DP/M2DP.h:12-30
 //   align_points_PCA                    <- .../src/utils/pts_align.h:7-9
 //   write_history / read_history        <- test_sc.cpp:63-66 (Eigen operator<<), test_kitti.m:26 (load)
+//   write/read/append_history_bin       <- (new) mmap-able binary container for the same matrices, SURVEY §8f N2
 //
 // All descriptor arithmetic happens in libsodso_pr.so on the GPU; this header only marshals.
 #pragma once
@@ -15,6 +16,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
@@ -217,8 +219,81 @@ inline void write_history(const std::string &path, const double *m, size_t rows,
   }
 }
 
-// MATLAB load() of a whitespace text matrix (test_kitti.m:26)
+// ---- binary signature container ---------------------------------------------------------------
+// The text hand-over costs 6 significant digits and, at 50 k scans, a gigabyte of decimal text.  The container is the
+// same matrix as raw little-endian doubles behind a 64-byte header, so that it can be mmap-ed (the payload is 64-byte
+// aligned) and appended to scan by scan:
+//   bytes 0..7 "SODSOHST", u32 version = 1, u32 dtype = 0 (f64), u64 rows, u64 cols, 32 bytes reserved (zero).
+struct HistoryBinHeader {
+  char magic[8];
+  uint32_t version, dtype;
+  uint64_t rows, cols;
+  unsigned char reserved[32];
+};
+static_assert(sizeof(HistoryBinHeader) == 64, "header layout");
+constexpr char kHistoryMagic[9] = "SODSOHST";
+
+inline bool is_history_bin(const std::string &path) {
+  std::ifstream f(path, std::ios::binary);
+  char m[8] = {};
+  return f.read(m, 8) && !std::memcmp(m, kHistoryMagic, 8);
+}
+
+inline void write_history_bin(const std::string &path, const double *m, size_t rows, size_t cols) {
+  HistoryBinHeader h{};
+  std::memcpy(h.magic, kHistoryMagic, 8);
+  h.version = 1;
+  h.dtype = 0;
+  h.rows = rows;
+  h.cols = cols;
+  std::ofstream f(path, std::ios::binary | std::ios::trunc);
+  if (!f) throw std::runtime_error("cannot open " + path);
+  f.write(reinterpret_cast<const char *>(&h), sizeof(h));
+  f.write(reinterpret_cast<const char *>(m), (std::streamsize)(rows * cols * sizeof(double)));
+}
+
+// append rows (a new scan's signature rows) to an existing container, or create it
+inline void append_history_bin(const std::string &path, const double *m, size_t rows, size_t cols) {
+  if (!is_history_bin(path)) {
+    write_history_bin(path, m, rows, cols);
+    return;
+  }
+  std::fstream f(path, std::ios::binary | std::ios::in | std::ios::out);
+  HistoryBinHeader h{};
+  f.read(reinterpret_cast<char *>(&h), sizeof(h));
+  if (h.version != 1 || h.dtype != 0 || h.cols != cols) throw std::runtime_error("append: container shape mismatch in " + path);
+  f.seekp((std::streamoff)(sizeof(h) + h.rows * h.cols * sizeof(double)));
+  f.write(reinterpret_cast<const char *>(m), (std::streamsize)(rows * cols * sizeof(double)));
+  h.rows += rows;
+  f.seekp(0);
+  f.write(reinterpret_cast<const char *>(&h), sizeof(h));
+}
+
+inline std::vector<double> read_history_bin(const std::string &path, size_t &rows, size_t &cols) {
+  std::ifstream f(path, std::ios::binary);
+  HistoryBinHeader h{};
+  if (!f.read(reinterpret_cast<char *>(&h), sizeof(h)) || std::memcmp(h.magic, kHistoryMagic, 8) || h.version != 1 || h.dtype != 0)
+    throw std::runtime_error("not a signature container: " + path);
+  rows = h.rows;
+  cols = h.cols;
+  std::vector<double> v(rows * cols);
+  if (!f.read(reinterpret_cast<char *>(v.data()), (std::streamsize)(v.size() * sizeof(double))))
+    throw std::runtime_error("truncated signature container: " + path);
+  return v;
+}
+
+inline bool has_suffix(const std::string &s, const std::string &suf) {
+  return s.size() >= suf.size() && !s.compare(s.size() - suf.size(), suf.size(), suf);
+}
+// text (Eigen layout) unless the file name ends in ".bin"
+inline void write_history_auto(const std::string &path, const double *m, size_t rows, size_t cols, bool full_precision = false) {
+  if (has_suffix(path, ".bin")) write_history_bin(path, m, rows, cols);
+  else write_history(path, m, rows, cols, full_precision);
+}
+
+// MATLAB load() of a whitespace text matrix (test_kitti.m:26); a binary container is recognised by its magic
 inline std::vector<double> read_history(const std::string &path, size_t &rows, size_t &cols) {
+  if (is_history_bin(path)) return read_history_bin(path, rows, cols);
   std::ifstream f(path);
   if (!f) throw std::runtime_error("cannot open " + path);
   std::vector<double> v;

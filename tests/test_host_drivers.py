@@ -60,3 +60,29 @@ def test_history_text_layout_is_eigen_style(drivers, tmp_path):
     assert out.read_text() == expect
     back = np.loadtxt(out)                                     # MATLAB load / numpy.loadtxt accept it
     np.testing.assert_allclose(back, m, rtol=1e-5)
+
+
+def test_binary_signature_container(drivers, tmp_path):
+    """the binary container written by the C++ side is lossless, mmap-able from Python, recognised by
+    the C++ reader in place of a text file, and Python-written containers read back in C++."""
+    from so_dso_place_recognition_b200 import api
+
+    rng = np.random.default_rng(1)
+    m = rng.normal(size=(9, 2400)) * 10.0 ** rng.integers(-12, 3, size=(9, 2400))
+    src = tmp_path / "in.txt"
+    np.savetxt(src, m, fmt="%.17g")
+    out = tmp_path / "hist.bin"
+    subprocess.check_call([drivers[0], "reformat", str(src), str(out)])      # text -> container
+    assert os.path.getsize(out) == 64 + m.size * 8
+    back = api.load_history(str(out))
+    assert isinstance(back, np.memmap) and back.shape == m.shape
+    np.testing.assert_array_equal(np.asarray(back), m)                      # lossless (17 digits round-trip)
+    txt = tmp_path / "again.txt"
+    subprocess.check_call([drivers[0], "reformat", str(out), str(txt)])      # container -> text (6 digits)
+    np.testing.assert_allclose(np.loadtxt(txt), m, rtol=1e-5)
+    py = tmp_path / "py.bin"
+    api.save_history(str(py), m)
+    assert py.read_bytes() == out.read_bytes()                               # same format from both sides
+    np.testing.assert_array_equal(api.load_history(str(py), mmap=False), m)
+    api.save_history(str(tmp_path / "py.txt"), m)
+    np.testing.assert_allclose(api.load_history(str(tmp_path / "py.txt")), m, rtol=1e-5)
