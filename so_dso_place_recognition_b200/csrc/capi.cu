@@ -216,9 +216,15 @@ int match_to_device(sodso_ctx *c, int type, const double *hist1, int m, const do
     if ((rc = sc_prepare(c, c->algo, h1d, m, c->q_op, false))) return rc;
     return sc_match_core(c, c->algo, c->q_op, m, c->db_op, n, dp, di, n);
   }
-  SODSO_CUDA_CHECK(c->m2dp_ws.reserve(m2dp_match_workspace_bytes(m, n)));
-  TimedRegion tr(c, "m2dp_match_kernel");
-  SODSO_CUDA_CHECK(launch_m2dp_match(h1d, m, h2d, n, dp, di, n, c->m2dp_ws.p, c->stream, &c->launches));
+  if (c->algo == SODSO_ALGO_SIMT) {
+    SODSO_CUDA_CHECK(c->m2dp_ws.reserve(m2dp_match_workspace_bytes(m, n)));
+    TimedRegion tr(c, "m2dp_match_kernel");
+    SODSO_CUDA_CHECK(launch_m2dp_match(h1d, m, h2d, n, dp, di, n, c->m2dp_ws.p, c->stream, &c->launches));
+  } else {
+    SODSO_CUDA_CHECK(c->m2dp_ws.reserve(m2dp_match_tc_workspace_bytes(m, n)));
+    TimedRegion tr(c, "m2dp_match_tc_kernel");
+    SODSO_CUDA_CHECK(launch_m2dp_match_tc(h1d, m, h2d, n, dp, di, n, c->m2dp_ws.p, c->num_sms, c->stream, &c->launches));
+  }
   return SODSO_OK;
 }
 
@@ -1163,10 +1169,17 @@ int sodso_db_match(sodso_db *db, const double *hist1, int m) {
                             db->n)))
       return rc;
   } else {
-    SODSO_CUDA_CHECK(db->ws.reserve(m2dp_match_workspace_bytes(m, db->n)));
-    TimedRegion tr(c, "m2dp_match_kernel");
-    SODSO_CUDA_CHECK(launch_m2dp_match(hd, m, db->op.as<double>(), db->n, db->dp.as<float>(),
-                                       db->di.as<float>(), db->n, db->ws.p, c->stream, &c->launches));
+    if (db->op_algo == SODSO_ALGO_SIMT) {
+      SODSO_CUDA_CHECK(db->ws.reserve(m2dp_match_workspace_bytes(m, db->n)));
+      TimedRegion tr(c, "m2dp_match_kernel");
+      SODSO_CUDA_CHECK(launch_m2dp_match(hd, m, db->op.as<double>(), db->n, db->dp.as<float>(),
+                                         db->di.as<float>(), db->n, db->ws.p, c->stream, &c->launches));
+    } else {
+      SODSO_CUDA_CHECK(db->ws.reserve(m2dp_match_tc_workspace_bytes(m, db->n)));
+      TimedRegion tr(c, "m2dp_match_tc_kernel");
+      SODSO_CUDA_CHECK(launch_m2dp_match_tc(hd, m, db->op.as<double>(), db->n, db->dp.as<float>(), db->di.as<float>(),
+                                            db->n, db->ws.p, c->num_sms, c->stream, &c->launches));
+    }
   }
   db->m = m;
   db->matched = true;

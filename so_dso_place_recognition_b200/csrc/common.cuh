@@ -138,6 +138,10 @@ cudaError_t launch_m2dp_match(const double *hist1, int m, const double *hist2, i
                               float *d_i, int ldd, void *workspace, cudaStream_t st,
                               int64_t *launches);
 size_t m2dp_match_workspace_bytes(int m, int n);
+// m2dp_match_tc.cu : tcgen05 path (the product path; the fp32 kernel above is the on-GPU cross-check)
+size_t m2dp_match_tc_workspace_bytes(int m, int n);
+cudaError_t launch_m2dp_match_tc(const double *hist1, int m, const double *hist2, int n, float *d_p, float *d_i,
+                                 int ldd, void *workspace, int num_sms, cudaStream_t st, int64_t *launches);
 
 // fuse_topk.cu
 cudaError_t launch_row_stats(const float *d_p, const float *d_i, int m, int n, int ldd, double *stats,

@@ -1,7 +1,8 @@
 // M2DP all-pairs match: processM2DP.m:12-22.  diff_full = (1 - hist1 * hist2') / 2 on the 4m x 4n
 // variant rows (NO normalisation, processM2DP.m:15), then the minimum of every 4 x 4 block.
 //
-// fp32 CUDA-core tiled contraction: a 16 x 16 thread block owns a 64 x 64 tile of variant rows
+// This fp32 CUDA-core kernel is the on-GPU cross-check (SODSO_ALGO_SIMT) of the tensor-core matcher in
+// m2dp_match_tc.cu, which is the product path.  Tiled contraction: a 16 x 16 thread block owns a 64 x 64 tile of variant rows
 // (16 queries x 16 DB entries), every thread accumulates the 4 x 4 block of ONE (query, DB) pair
 // in registers over K = 192 and reduces it with the NaN-ignoring min (MATLAB min).  12 288 FLOP per
 // pair: ~0.3 TFLOP for 5k x 5k, three orders of magnitude below the Scan Context matcher, and the

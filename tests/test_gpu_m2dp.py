@@ -48,10 +48,14 @@ def test_m2dp_real_scans_and_ragged(gpu_ctx, oracle, real_scans):
                                rtol=0, atol=TOL_SIG)
 
 
-def test_m2dp_match_and_top1(gpu_ctx, oracle):
+@pytest.mark.parametrize("algo", [api.SODSO_ALGO_TC, api.SODSO_ALGO_SIMT])
+def test_m2dp_match_and_top1(gpu_ctx, oracle, algo):
+    """tcgen05 matcher (product path) and the fp32 CUDA-core cross-check against the oracle"""
+    gpu_ctx.set_match_algo(algo)
     xyz, inten, off = synth.make_scan_set(96, 1024, planted_loops=True)
     sig = oracle.m2dp_generate(xyz, inten, off, nthreads=16)
     dp, di = api.processM2DP(sig[:4 * 37], sig)
+    assert gpu_ctx.last_kernel_name == ("m2dp_match_tc_kernel" if algo == api.SODSO_ALGO_TC else "m2dp_match_kernel")
     rp, ri = oracle.m2dp_match(sig[:4 * 37], sig, nthreads=8)
     assert dp.shape == (37, 96)
     assert np.abs(dp - rp).max() < TOL_D and np.abs(di - ri).max() < TOL_D
@@ -60,6 +64,30 @@ def test_m2dp_match_and_top1(gpu_ctx, oracle):
     idx, sc = api.run_test("m2dp", sig, sig, 5)
     np.testing.assert_array_equal(idx, ridx)
     np.testing.assert_allclose(sc, rsc, atol=2e-3)
+    gpu_ctx.set_match_algo(api.SODSO_ALGO_TC)
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (3, 70), (65, 64), (130, 257)])
+def test_m2dp_match_ragged_shapes_tc_vs_simt(gpu_ctx, m, n):
+    """tile edges of the tensor-core matcher (256 variant rows = 64 scans per tile) against the fp32 kernel"""
+    rng = np.random.default_rng(m * 1000 + n)
+
+    def sigs(k):     # rows like real signatures: non-negative unit vectors [u(64) v(128)] per channel
+        a = rng.random((4 * k, 2, 192))
+        a[..., :64] /= np.linalg.norm(a[..., :64], axis=-1, keepdims=True)
+        a[..., 64:] /= np.linalg.norm(a[..., 64:], axis=-1, keepdims=True)
+        return a.reshape(4 * k, 384)
+
+    h1, h2 = sigs(m), sigs(n)
+    gpu_ctx.set_match_algo(api.SODSO_ALGO_TC)
+    dp, di = api.processM2DP(h1, h2)
+    gpu_ctx.set_match_algo(api.SODSO_ALGO_SIMT)
+    sp, si = api.processM2DP(h1, h2)
+    gpu_ctx.set_match_algo(api.SODSO_ALGO_TC)
+    assert dp.shape == (m, n)
+    ref = (1.0 - np.einsum("ivk,jwk->ijvw", h1[:, :192].reshape(m, 4, 192), h2[:, :192].reshape(n, 4, 192))) / 2
+    assert np.abs(dp - ref.min(axis=(2, 3))).max() < TOL_D                  # processM2DP.m:15-21 in numpy
+    assert np.abs(dp - sp).max() < TOL_D and np.abs(di - si).max() < TOL_D
 
 
 def test_m2dp_end_to_end_planted_loops(gpu_ctx):
