@@ -66,6 +66,7 @@ struct ScanRef {
   const float *gi;
   const double *bc;   // mean + eigenvectors (identity for pre-aligned input)
   int n, nst;
+  int identity;       // class contract (M2DP.h:18-20): the input is used as it is (signed zeros included)
   double dx, dy, dz;  // sign variant
   double S_res_inv, R_res_inv;
 };
@@ -73,6 +74,15 @@ struct ScanRef {
 // aligned + sign-flipped fp64 point i (pts_align.h:37-45, test_m2dp.cpp:49-53)
 __device__ __forceinline__ void aligned_point64(const ScanRef &R, int i, double &px, double &py, double &pz) {
   double ax, ay, az;
+  if (R.identity) {
+    ax = R.g[3 * (size_t)i + 0];
+    ay = R.g[3 * (size_t)i + 1];
+    az = R.g[3 * (size_t)i + 2];
+    px = ax;   // (dx = dy = dz = 1; no multiplication either)
+    py = ay;
+    pz = az;
+    return;
+  }
   pca_rotate(R.bc, R.g[3 * (size_t)i + 0], R.g[3 * (size_t)i + 1], R.g[3 * (size_t)i + 2], ax, ay, az);
   px = R.dx * ax;
   py = R.dy * ay;
@@ -342,7 +352,13 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
     // ---- pass 2 (L2): aligned points -> shared memory as fp32 (the proposal path only needs fp32)
     for (int i = threadIdx.x; i < nst; i += M2_THREADS) {
       double ax, ay, az;
-      pca_rotate(S.bc, g[3 * (size_t)i + 0], g[3 * (size_t)i + 1], g[3 * (size_t)i + 2], ax, ay, az);
+      if (variants) {
+        pca_rotate(S.bc, g[3 * (size_t)i + 0], g[3 * (size_t)i + 1], g[3 * (size_t)i + 2], ax, ay, az);
+      } else {
+        ax = g[3 * (size_t)i + 0];
+        ay = g[3 * (size_t)i + 1];
+        az = g[3 * (size_t)i + 2];
+      }
       S.ax[i] = (float)ax;
       S.ay[i] = (float)ay;
       S.az[i] = (float)az;
@@ -357,6 +373,7 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
       R.bc = S.bc;
       R.n = n;
       R.nst = nst;
+      R.identity = variants ? 0 : 1;
       R.dx = variants ? ((var >> 1) ? 1.0 : -1.0) : 1.0;
       R.dy = variants ? ((var & 1) ? 1.0 : -1.0) : 1.0;
       R.dz = R.dx * R.dy;

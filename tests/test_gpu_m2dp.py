@@ -97,3 +97,27 @@ def test_m2dp_end_to_end_planted_loops(gpu_ctx):
     sig = api.m2dp_generate(xyz, inten, off)
     idx, sc = api.run_test("m2dp", sig, sig, 3)
     assert (idx == (np.arange(n) + n // 2) % n).mean() > 0.8
+
+
+def test_m2dp_points_in_the_guard_band(gpu_ctx, oracle):
+    """The fp32 bin proposal is only trusted away from bin edges; everything closer takes M2DP.cpp:56-63 in fp64.
+    Pre-aligned points (class contract, identity transform) placed within 1e-12 .. 1e-4 of sector / ring edges of the
+    x-z projection plane (p=0, q=0), plus points on the axes, at the origin and just inside / outside max_rho: the
+    histograms must come out exactly as the oracle's, which shows in the singular vectors at 1e-9."""
+    rng = np.random.default_rng(17)
+    n = 4000
+    k = rng.integers(0, 16, n)
+    j = rng.integers(1, 8, n)
+    eps_t = rng.choice([-1, 1], n) * 10.0 ** rng.uniform(-12, -4, n)
+    eps_r = rng.choice([-1, 1], n) * 10.0 ** rng.uniform(-12, -4, n)
+    theta = -np.pi + k * (2 * np.pi / 16) + eps_t * (rng.random(n) < 0.7)
+    r = np.where(rng.random(n) < 0.5, j * 45.0 / 8 + eps_r, rng.uniform(0.2, 44, n))
+    pts = np.stack([r * np.cos(theta), rng.normal(0, 1.0, n), r * np.sin(theta)], axis=1)
+    special = np.array([[0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 0, 1], [0, 0, -1], [0, 3, 0], [0, -3, 0], [-2, -2, -2],
+                        [44.9999999, 0, 0], [45.0000001, 0, 0], [1e-300, 0, 1e-300], [-0.0, 0.0, -0.0]], dtype=float)
+    pts = np.concatenate([pts, special])
+    inten = (rng.integers(0, 2041, len(pts)) / 8.0).astype(np.float32)
+    c_ref, i_ref = oracle.m2dp_signature(pts, inten)
+    c, i = api.M2DP(45.0).getSignature(pts, inten)
+    np.testing.assert_allclose(c, c_ref, rtol=0, atol=TOL_SIG)
+    np.testing.assert_allclose(i, i_ref, rtol=0, atol=TOL_SIG)
