@@ -155,6 +155,22 @@ int sodso_sc_scans_to_loops(sodso_ctx *ctx, const double *xyz, const float *inte
                             double p_weight, double *hist, int32_t *idx, double *score,
                             double *d_p_at, double *d_i_at);
 
+/* ---- DELIGHT -------------------------------------------------------- */
+/* DELIGHT::getSignatureSize (DELIGHT.cpp:4) */
+int sodso_delight_signature_size(void);
+/* DELIGHT::getSignature (DELIGHT.cpp:6-24) over a batch, output in the history_delight layout of
+ * test_delight.cpp:42-56: rows 16s..16s+15 = the 16 intensity histograms (8 octants x inside / outside 10 m) of scan s,
+ * 16*nscan x 256 doubles.  A point whose int(intensity) falls outside [0, 255] (out of the matrix in the reference) is
+ * dropped. */
+int sodso_delight_generate(sodso_ctx *ctx, const double *xyz, const float *inten, const int64_t *scan_off,
+                           int nscan, double *hist);
+/* dist = processDELIGHT(hist1, hist2) (processDELIGHT.m:1-38): hist1 16m x 256, hist2 16n x 256, dist m x n. */
+int sodso_delight_match(sodso_ctx *ctx, const double *hist1, int m, const double *hist2, int n, double *dist);
+/* run_test.m:47-57 for ONE distance matrix (the delight / gist / bow branch of run_test.m:26-37: no fusion): mask
+ * |i - j| < mask_width, first minimum per row (NaN skipped).  idx 0-based. */
+int sodso_top1_single(sodso_ctx *ctx, const double *dist, int m, int n, int mask_width, int32_t *idx,
+                      double *score);
+
 /* ---- evaluation ------------------------------------------------------ */
 /* Ground-truth loop set of run_test.m:3-21.  gt1: m x 3, gt2: n x 3 positions.  nearest[i] = 0-based index of the
  * closest gt2 position with |i - j| >= mask_width (first one on ties, -1 if none); is_loop[i] = 1 if it is closer than

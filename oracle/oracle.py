@@ -322,3 +322,39 @@ def pr_eval(diff_v, diff_idx, gt1, gt2, total_lp, loop_diff):
                 top_count, top_recall = i + 1, recall[i]
         auc = float(np.sum((recall[1:] - recall[:-1]) * (precision[1:] + precision[:-1]) * 0.5)) if m > 1 else 0.0  # :84
     return dict(AUC=auc, top_recall=float(top_recall), top_count=top_count, rank=rank, precision=precision, recall=recall)
+
+
+# ---------------------------------------------------------------------------------------
+# DELIGHT
+# ---------------------------------------------------------------------------------------
+def delight_generate(xyz, inten, off, nthreads=1):
+    """test_delight.cpp:38-56 -> history_delight (16*nscan x 256)."""
+    xyz = _f64(xyz).reshape(-1, 3)
+    inten = _f32(inten)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    ns = off.shape[0] - 1
+    hist = np.zeros((16 * ns, 256))
+    lib().orc_delight_generate(_p(xyz, C.c_double), _p(inten, C.c_float), _p(off, C.c_int64), C.c_int(ns),
+                               _p(hist, C.c_double), C.c_int(nthreads))
+    return hist
+
+
+def delight_match(hist1, hist2, nthreads=1):
+    """dist = processDELIGHT(hist1, hist2) (processDELIGHT.m:1-38)."""
+    h1, h2 = _f64(hist1), _f64(hist2)
+    m, n = h1.shape[0] // 16, h2.shape[0] // 16
+    d = np.zeros((m, n))
+    lib().orc_delight_match(_p(h1, C.c_double), C.c_int(m), _p(h2, C.c_double), C.c_int(n), _p(d, C.c_double),
+                            C.c_int(nthreads))
+    return d
+
+
+def top1_single(d, mask_width):
+    """run_test.m:47-57 on one distance matrix -> (idx 0-based, score)."""
+    d = _f64(d)
+    m, n = d.shape
+    idx = np.zeros(m, dtype=np.int32)
+    score = np.zeros(m)
+    lib().orc_top1_single(_p(d, C.c_double), C.c_int(m), C.c_int(n), C.c_int(mask_width), _p(idx, C.c_int32),
+                          _p(score, C.c_double))
+    return idx, score

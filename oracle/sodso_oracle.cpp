@@ -664,6 +664,83 @@ static StageResult* stage_core(const std::vector<PoseI>& poses, const std::vecto
 }
 
 
+// =============================================================================
+// DELIGHT: DELIGHT.cpp:6-24 (generation), test_delight.cpp:38-66 (driver), processDELIGHT.m:1-38 (chi-square match)
+// =============================================================================
+constexpr int DELIGHT_BINS = 256;      // DELIGHT.h:10
+constexpr double DELIGHT_RADIUS = 10.0;  // DELIGHT.h:9
+
+// DELIGHT::getSignature: 16 (8 octants x inside / outside RADIUS) histograms of the intensity, 256 bins.
+// out: 16 x 256 row-major.  A point whose int(intensity) is outside [0, 255] indexes out of the Eigen matrix in the
+// reference (undefined behaviour); it is dropped here.
+void orc_delight_signature(const double* xyz, const float* inten, int n, double* out) {
+  std::vector<double> al(3 * (size_t)std::max(n, 1));
+  align_pca(xyz, n, al.data(), nullptr, nullptr);                         // DELIGHT.cpp:10-11
+  std::fill(out, out + 16 * DELIGHT_BINS, 0.0);                           // :13
+  for (int i = 0; i < n; i++) {                                           // :14-23
+    const double* p = &al[3 * (size_t)i];
+    float x = (float)p[0], y = (float)p[1], z = (float)p[2];
+    float d = (float)std::sqrt((p[0] * p[0] + p[1] * p[1]) + p[2] * p[2]);   // p.first.norm()
+    float clr = inten[i];
+    int hist = 8 * (d > DELIGHT_RADIUS) + 4 * (z > 0) + 2 * (y > 0) + 1 * (x > 0);
+    if (!(clr > -1.0f && clr < 256.0f)) continue;
+    out[hist * DELIGHT_BINS + (int)clr] += 1.0;
+  }
+}
+
+// test_delight.cpp:42-56: history_delight (16 N x 256)
+void orc_delight_generate(const double* xyz, const float* inten, const int64_t* off, int nscan, double* hist, int nthreads) {
+#pragma omp parallel for schedule(dynamic) num_threads(nthreads > 0 ? nthreads : 1)
+  for (int s = 0; s < nscan; s++)
+    orc_delight_signature(xyz + 3 * off[s], inten + off[s], (int)(off[s + 1] - off[s]), hist + (size_t)s * 16 * DELIGHT_BINS);
+}
+
+// processDELIGHT.m:1-38.  hist1: 16 m x 256, hist2: 16 n x 256 -> dist m x n
+void orc_delight_match(const double* hist1, int m, const double* hist2, int n, double* dist, int nthreads) {
+  static const int Mut[4][16] = {{1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16},        // :2-5 (1-based)
+                                 {6, 5, 8, 7, 2, 1, 4, 3, 14, 13, 16, 15, 10, 9, 12, 11},
+                                 {7, 8, 5, 6, 3, 4, 1, 2, 15, 16, 13, 14, 11, 12, 9, 10},
+                                 {4, 3, 2, 1, 8, 7, 6, 5, 12, 11, 10, 9, 16, 15, 14, 13}};
+#pragma omp parallel for schedule(dynamic) num_threads(nthreads > 0 ? nthreads : 1)
+  for (int i = 0; i < m; i++) {
+    const double* A = hist1 + (size_t)i * 16 * DELIGHT_BINS;
+    for (int j = 0; j < n; j++) {
+      const double* B = hist2 + (size_t)j * 16 * DELIGHT_BINS;
+      double min_dist = std::numeric_limits<double>::infinity();          // :16
+      for (int k = 0; k < 4; k++) {                                       // :17
+        double ts = 0.0, tc = 0.0;
+        for (int c = 0; c < DELIGHT_BINS; c++)                            // A(:), Bk(:) are column-major: bins outer,
+          for (int r = 0; r < 16; r++) {                                  // histogram rows inner (:18-30)
+            const double a = A[r * DELIGHT_BINS + c], b = B[(Mut[k][r] - 1) * DELIGHT_BINS + c];
+            const double ab = a + b;
+            if (ab > 0) {
+              ts = ts + 2 * (a - b) * (a - b) / ab;                       // :26-27
+              tc = tc + 1;
+            }
+          }
+        ts = ts / tc;                                                     // :31 (0/0 = NaN when both are empty)
+        if (min_dist > ts) min_dist = ts;                                 // :32-34 (false for NaN)
+      }
+      dist[(size_t)i * n + j] = min_dist;
+    }
+  }
+}
+
+// run_test.m:47-57 for a single distance matrix (the 'delight' / 'gist' / 'bow' branch: no fusion)
+void orc_top1_single(const double* d, int m, int n, int mask_width, int32_t* idx, double* score) {
+  for (int i = 0; i < m; i++) {
+    int bi = 0;
+    double bv = std::numeric_limits<double>::quiet_NaN();
+    for (int j = 0; j < n; j++) {
+      double v = std::abs(i - j) < mask_width ? std::numeric_limits<double>::infinity() : d[(size_t)i * n + j];
+      if (v != v) continue;
+      if (bv != bv || v < bv) { bv = v; bi = j; }
+    }
+    idx[i] = bi;
+    score[i] = bv;
+  }
+}
+
 void* orc_stage_run(const char* poses_file, const char* pts_file, double lidar_range, int polar_filter) {
   std::vector<PoseI> poses;
   std::vector<PtI> pts;

@@ -59,6 +59,10 @@ _PROTOS = {
     "sodso_fuse_top1": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp]),
     "sodso_loop_top1": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _vp]),
     "sodso_sc_scans_to_loops": (_i, [_vp, _vp, _vp, _vp, _i, _d, _i, _d, _vp, _vp, _vp, _vp, _vp]),
+    "sodso_delight_signature_size": (_i, []),
+    "sodso_delight_generate": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
+    "sodso_delight_match": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "sodso_top1_single": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "sodso_gt_loops": (_i, [_vp, _vp, _i, _vp, _i, _d, _i, _vp, _vp, C.POINTER(_i)]),
     "sodso_pr_curve": (_i, [_vp, _vp, _vp, _i, _vp, _i, _d, _i, C.POINTER(_d), C.POINTER(_d), C.POINTER(_i), _vp, _vp, _vp]),
     "sodso_debug_fast_turns": (_i, [_vp, _vp, _vp, _i64, _vp]),

@@ -333,6 +333,9 @@ def fuse_top1(d_p, d_i, mask_width, p_weight=2.0, ctx=None):
 def run_test(type, hist1, hist2, mask_width, p_weight=2.0, want_channels=False, ctx=None):
     """The timed + decision part of run_test(type, hist1, hist2, gt1, gt2, loop_diff, mask_width)
     (run_test.m:25-57): -> (diff_idx 0-based int32[m], diff_v[m] [, d_p_at, d_i_at])."""
+    if type == "delight":     # run_test.m:31-32: one distance matrix, no fusion
+        idx, score = top1_single(processDELIGHT(hist1, hist2, ctx=ctx), mask_width, ctx=ctx)
+        return (idx, score, None, None) if want_channels else (idx, score)
     t = {"sc": SODSO_TYPE_SC, "m2dp": SODSO_TYPE_M2DP}[type]
     rows = 1 if t == SODSO_TYPE_SC else 4
     hist1 = _prep(hist1, np.float64, "float64")
@@ -347,6 +350,44 @@ def run_test(type, hist1, hist2, mask_width, p_weight=2.0, want_channels=False, 
     N.check(N.lib().sodso_loop_top1(c.handle, t, _ptr(hist1), m, _ptr(hist2), n, int(mask_width), float(p_weight),
                                     _ptr(idx), _ptr(score), _ptr(dpa), _ptr(dia)))
     return (idx, score, dpa, dia) if want_channels else (idx, score)
+
+
+# ----------------------------------------------------------------------------------------------
+# DELIGHT
+# ----------------------------------------------------------------------------------------------
+def delight_generate(xyz, inten, off, ctx=None):
+    """test_delight.cpp:38-56: history_delight (16*nscan x 256)."""
+    xyz = _prep(xyz, np.float64, "float64")
+    inten = _prep(inten, np.float32, "float32")
+    off = _prep(off, np.int64, "int64")
+    nscan = off.shape[0] - 1
+    c = _ctx_for(xyz, ctx=ctx)
+    hist = _empty_like_kind(xyz, (16 * nscan, 256), np.float64, "float64")
+    N.check(N.lib().sodso_delight_generate(c.handle, _ptr(xyz), _ptr(inten), _ptr(off), nscan, _ptr(hist)))
+    return hist
+
+
+def processDELIGHT(hist1, hist2, ctx=None):
+    """dist = processDELIGHT(hist1, hist2)  (processDELIGHT.m:1-38)."""
+    hist1 = _prep(hist1, np.float64, "float64")
+    hist2 = _prep(hist2, np.float64, "float64")
+    m, n = hist1.shape[0] // 16, hist2.shape[0] // 16
+    c = _ctx_for(hist1, hist2, ctx=ctx)
+    ref = hist1 if _is_torch(hist1) else hist2
+    d = _empty_like_kind(ref, (m, n), np.float64, "float64")
+    N.check(N.lib().sodso_delight_match(c.handle, _ptr(hist1), m, _ptr(hist2), n, _ptr(d)))
+    return d
+
+
+def top1_single(dist, mask_width, ctx=None):
+    """run_test.m:47-57 on one distance matrix -> (diff_idx 0-based int32[m], diff_v[m])."""
+    dist = _prep(dist, np.float64, "float64")
+    m, n = dist.shape
+    c = _ctx_for(dist, ctx=ctx)
+    idx = _empty_like_kind(dist, (m,), np.int32, "int32")
+    score = _empty_like_kind(dist, (m,), np.float64, "float64")
+    N.check(N.lib().sodso_top1_single(c.handle, _ptr(dist), m, n, int(mask_width), _ptr(idx), _ptr(score)))
+    return idx, score
 
 
 def gt_loops(gt1, gt2, loop_diff, mask_width, ctx=None):

@@ -689,6 +689,75 @@ int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten,
   return fuse_top1_tail(c, nscan, nscan, mask_width, p_weight, idx, score, d_p_at, d_i_at);
 }
 
+// ---- DELIGHT --------------------------------------------------------------------
+int sodso_delight_signature_size(void) { return 256; }
+
+int sodso_delight_generate(sodso_ctx *c, const double *xyz, const float *inten, const int64_t *off, int nscan,
+                           double *hist) {
+  CTX_CHECK(c);
+  const double *xd;
+  const float *id = nullptr;
+  const int64_t *od;
+  int rc;
+  if (nscan > 0 && (!inten || !hist)) {
+    set_error("inten / hist is null");
+    return SODSO_E_ARG;
+  }
+  if ((rc = generate_common(c, xyz, inten, off, nscan, &xd, &id, &od))) return rc;
+  if (nscan == 0) return SODSO_OK;
+  double *h;
+  const size_t cnt = (size_t)nscan * 16 * 256;
+  if ((rc = stage_out(c, hist, cnt, c->out_hist, &h))) return rc;
+  {
+    TimedRegion tr(c, "delight_generate_kernel");
+    SODSO_CUDA_CHECK(launch_delight_generate(xd, id, od, nscan, h, c->num_sms, c->stream, &c->launches));
+  }
+  if ((rc = finish_out(c, hist, cnt, h))) return rc;
+  return sync_ctx(c);
+}
+
+int sodso_delight_match(sodso_ctx *c, const double *hist1, int m, const double *hist2, int n, double *dist) {
+  CTX_CHECK(c);
+  if (m < 0 || n < 0 || (m > 0 && !hist1) || (n > 0 && !hist2) || !dist) {
+    set_error("bad delight_match arguments");
+    return SODSO_E_ARG;
+  }
+  if (m == 0 || n == 0) return SODSO_OK;
+  const double *h1d, *h2d;
+  double *dd;
+  int rc;
+  if ((rc = stage_in(c, hist1, (size_t)m * 16 * 256, c->h1, &h1d))) return rc;
+  if ((rc = stage_in(c, hist2, (size_t)n * 16 * 256, c->h2, &h2d))) return rc;
+  if ((rc = stage_out(c, dist, (size_t)m * n, c->dp64, &dd))) return rc;
+  SODSO_CUDA_CHECK(c->m2dp_ws.reserve(delight_match_workspace_bytes(m, n)));
+  {
+    TimedRegion tr(c, "delight_match_kernel");
+    SODSO_CUDA_CHECK(launch_delight_match(h1d, m, h2d, n, dd, c->m2dp_ws.p, c->stream, &c->launches));
+  }
+  if ((rc = finish_out(c, dist, (size_t)m * n, dd))) return rc;
+  return sync_ctx(c);
+}
+
+int sodso_top1_single(sodso_ctx *c, const double *dist, int m, int n, int mask_width, int32_t *idx, double *score) {
+  CTX_CHECK(c);
+  if (m < 0 || n <= 0 || !dist || !idx || !score) {
+    set_error("bad top1_single arguments");
+    return SODSO_E_ARG;
+  }
+  if (m == 0) return SODSO_OK;
+  const double *dd;
+  int32_t *id;
+  double *sd;
+  int rc;
+  if ((rc = stage_in(c, dist, (size_t)m * n, c->dp64, &dd))) return rc;
+  if ((rc = stage_out(c, idx, (size_t)m, c->idx32, &id))) return rc;
+  if ((rc = stage_out(c, score, (size_t)m, c->score, &sd))) return rc;
+  SODSO_CUDA_CHECK(launch_top1_single(dd, m, n, mask_width, id, sd, c->stream, &c->launches));
+  if ((rc = finish_out(c, idx, (size_t)m, id))) return rc;
+  if ((rc = finish_out(c, score, (size_t)m, sd))) return rc;
+  return sync_ctx(c);
+}
+
 // ---- evaluation (run_test.m:2-22, 58-85) -------------------------------------------------------
 int sodso_gt_loops(sodso_ctx *c, const double *gt1, int m, const double *gt2, int n, double loop_diff,
                    int mask_width, int32_t *nearest, int32_t *is_loop, int *n_loops) {

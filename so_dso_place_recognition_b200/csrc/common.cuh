@@ -133,6 +133,15 @@ cudaError_t launch_stage_emit(const double *pt_xyz, const float *pt_inten, const
                               const int64_t *off, int nscan, double *xyz, float *inten, int grid,
                               cudaStream_t st, int64_t *launches);
 
+// delight.cu : DELIGHT descriptor
+cudaError_t launch_delight_generate(const double *xyz, const float *inten, const int64_t *off, int nscan,
+                                    double *hist, int num_sms, cudaStream_t st, int64_t *launches);
+size_t delight_match_workspace_bytes(int m, int n);
+cudaError_t launch_delight_match(const double *hist1, int m, const double *hist2, int n, double *dist,
+                                 void *workspace, cudaStream_t st, int64_t *launches);
+cudaError_t launch_top1_single(const double *d, int m, int n, int mask_width, int32_t *idx, double *score,
+                               cudaStream_t st, int64_t *launches);
+
 // m2dp_match.cu
 cudaError_t launch_m2dp_match(const double *hist1, int m, const double *hist2, int n, float *d_p,
                               float *d_i, int ldd, void *workspace, cudaStream_t st,

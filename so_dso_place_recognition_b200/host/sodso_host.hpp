@@ -4,7 +4,7 @@
 //   IDPose / IDPtIntensity + text I/O   <- PosesPts.h:5-40 (same token order / default precision)
 //   read_poses_pts, pts_preprocess      <- place_recognition/generate_signatures/src/utils/pts_preprocess.h
 //                                          (CPU staging; SURVEY.md §8f row N1 keeps it on the host)
-//   class SC, class M2DP                <- .../src/SC/SC.h:10-23, .../src/M2DP/M2DP.h:12-30
+//   class SC, class M2DP, class DELIGHT <- .../src/SC/SC.h:10-23, .../src/M2DP/M2DP.h:12-30, .../src/DELIGHT/DELIGHT.h:12-20
 //   align_points_PCA                    <- .../src/utils/pts_align.h:7-9
 //   write_history / read_history        <- test_sc.cpp:63-66 (Eigen operator<<), test_kitti.m:26 (load)
 //   write/read/append_history_bin       <- (new) mmap-able binary container for the same matrices, SURVEY §8f N2
@@ -386,6 +386,31 @@ class M2DP {
  private:
   Context &ctx_;
   double max_rho_;
+};
+
+// DELIGHT.h:12-20 (getSignature aligns by PCA itself, DELIGHT.cpp:10-11)
+class DELIGHT {
+ public:
+  explicit DELIGHT(Context &ctx) : ctx_(ctx) {}
+  unsigned int getSignatureSize() const { return (unsigned)sodso_delight_signature_size(); }
+  // 16 x 256 row-major (Eigen::MatrixXd output(16, BINS))
+  void getSignature(const Scan &pts_clr_raw, std::vector<double> &output) {
+    FlatScans f = flatten({pts_clr_raw});
+    output.assign((size_t)16 * getSignatureSize(), 0.0);
+    check(sodso_delight_generate(ctx_.get(), f.xyz.data(), f.inten.data(), f.off.data(), 1, output.data()),
+          "sodso_delight_generate");
+  }
+  // test_delight.cpp:38-56 for a batch: 16*nscan x 256 row-major
+  std::vector<double> getHistory(const std::vector<Scan> &scans) {
+    FlatScans f = flatten(scans);
+    std::vector<double> hist((size_t)f.nscan() * 16 * getSignatureSize());
+    check(sodso_delight_generate(ctx_.get(), f.xyz.data(), f.inten.data(), f.off.data(), f.nscan(), hist.data()),
+          "sodso_delight_generate");
+    return hist;
+  }
+
+ private:
+  Context &ctx_;
 };
 
 }  // namespace sodso_host

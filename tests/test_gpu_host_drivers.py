@@ -42,21 +42,27 @@ def test_files_to_loops(gpu_ctx, oracle, tmp_path):
     subprocess.check_call(["make", "-C", HOST, "-s"])
     gen, match = os.path.join(BIN, "gen_signatures"), os.path.join(BIN, "match_signatures")
     poses, pts = _write_sequence(tmp_path)
-    for kind, polar, width in (("sc", False, 2400), ("m2dp", True, 384)):
+    for kind, polar, width in (("sc", False, 2400), ("m2dp", True, 384), ("delight", True, 256)):
         hist_file, ids_file = str(tmp_path / f"history_{kind}.txt"), str(tmp_path / "incoming_id_file.txt")
         subprocess.check_call([gen, kind, poses, pts, hist_file, ids_file, "45"], stdout=subprocess.DEVNULL)
         st = oracle.stage(poses, pts, 45.0, polar)
         np.testing.assert_array_equal(np.loadtxt(ids_file, dtype=np.int64), st["ids"])
         n = len(st["ids"])
         assert n == 16
-        ref = (oracle.sc_generate if kind == "sc" else oracle.m2dp_generate)(st["xyz"], st["inten"], st["off"])
+        ogen = {"sc": oracle.sc_generate, "m2dp": oracle.m2dp_generate, "delight": oracle.delight_generate}[kind]
+        ref = ogen(st["xyz"], st["inten"], st["off"])
         hist = np.loadtxt(hist_file)
-        assert hist.shape == ((n if kind == "sc" else 4 * n), width)
+        assert hist.shape == ({"sc": n, "m2dp": 4 * n, "delight": 16 * n}[kind], width)
         np.testing.assert_allclose(hist, ref, rtol=1e-5, atol=1e-9)      # 6 significant digits in the text file
         # match on the text round-tripped signatures (what MATLAB would load)
         loops = str(tmp_path / "loops.txt")
         subprocess.check_call([match, kind, hist_file, hist_file, "3", loops], stdout=subprocess.DEVNULL)
         got = np.loadtxt(loops)
+        if kind == "delight":
+            ridx, rscore = oracle.top1_single(oracle.delight_match(hist, hist), 3)
+            np.testing.assert_array_equal(got[:, 0].astype(int) - 1, ridx)
+            np.testing.assert_allclose(got[:, 1], rscore, rtol=1e-5)
+            continue
         dp, di = (oracle.sc_match_numpy if kind == "sc" else oracle.m2dp_match)(hist, hist)
         ridx, rscore = oracle.fuse_top1(dp, di, 3)
         np.testing.assert_array_equal(got[:, 0].astype(int) - 1, ridx)     # file holds MATLAB's 1-based index
