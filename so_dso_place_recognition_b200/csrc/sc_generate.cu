@@ -43,7 +43,7 @@ struct ScSmem {
   int ibc[4];                               // [emin, -, float sum bits, -]
   int next_chunk;
 };
-static_assert(sizeof(ScSmem) * GEN_CTAS_PER_SM <= 200 * 1024, "four CTAs per SM");
+static_assert((sizeof(ScSmem) + 1024) * GEN_CTAS_PER_SM <= 228 * 1024, "resident CTAs per SM");
 
 __device__ __forceinline__ void gen_prefetch_l2(const void *p, int64_t bytes) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(p);
