@@ -581,9 +581,16 @@ int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten,
   if ((rc = check_offsets_host(off, nscan, &total))) return rc;
   const bool host_pts = !is_device_ptr(xyz), host_int = !is_device_ptr(inten), host_off = !is_device_ptr(off);
   // scans are streamed in chunks (a multiple of the 256-row DB tile) when the points live in host memory
+  // chunk boundaries (multiples of the 256-row DB tile): two 256-scan chunks first so that matching starts early --
+  // the work that can be done grows with the square of what has arrived -- then 512-scan chunks
   const int CH = 512;
   const bool streamed = host_pts && host_int && host_off && nscan >= 4 * CH;
-  const int nchunk = streamed ? (nscan + CH - 1) / CH : 1;
+  std::vector<int> bounds{0};
+  if (streamed) {
+    for (int b = 256; b < nscan; b += b < 512 ? 256 : CH) bounds.push_back(b);
+  }
+  bounds.push_back(nscan);
+  const int nchunk = (int)bounds.size() - 1;
 
   const double *xd = xyz;
   const float *id = inten;
@@ -625,7 +632,7 @@ int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten,
     SODSO_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, e0, 0));
     cudaEventDestroy(e0);
     for (int k = 0; k < nchunk; k++) {
-      const int s0 = k * CH, s1 = std::min(nscan, s0 + CH);
+      const int s0 = bounds[k], s1 = bounds[k + 1];
       const int64_t p0 = off[s0], p1 = off[s1];
       if (p1 > p0) {
         SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_xyz.as<double>() + 3 * p0, xyz + 3 * p0,
@@ -651,7 +658,7 @@ int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten,
   c->kname = "sc_match_tc_kernel";
   c->ev_valid = false;
   for (int k = 0; k < nchunk && rc == SODSO_OK; k++) {
-    const int s0 = streamed ? k * CH : 0, s1 = streamed ? std::min(nscan, s0 + CH) : nscan;
+    const int s0 = bounds[k], s1 = bounds[k + 1];
     const bool last = k == nchunk - 1;
     cudaError_t e = cudaSuccess;
     if (streamed) e = cudaStreamWaitEvent(c->stream, evs[k], 0);
@@ -667,12 +674,9 @@ int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten,
     // processSC.m:22-33 for every (query, DB) pair that has become available: new queries x all DB rows so far,
     // old queries x new DB rows
     if (!streamed && e == cudaSuccess) c->ev_valid = cudaEventRecord(c->ev0, c->stream) == cudaSuccess;
-    if (e == cudaSuccess)
-      e = launch_sc_match_tc_block(c->q_op.p, nscan, s0, s1, c->db_op.p, nscan, 0, s1, dp, di, nscan, c->num_sms,
-                                   c->stream, &c->launches);
-    if (e == cudaSuccess && s0 > 0)
-      e = launch_sc_match_tc_block(c->q_op.p, nscan, 0, s0, c->db_op.p, nscan, s0, s1, dp, di, nscan, c->num_sms,
-                                   c->stream, &c->launches);
+    if (e == cudaSuccess)   // one launch for the L-shaped region
+      e = launch_sc_match_tc_blocks(c->q_op.p, nscan, c->db_op.p, nscan, s0, s1, 0, s1, 0, s0, s0, s1, dp, di, nscan,
+                                    c->num_sms, c->stream, &c->launches);
     if (!streamed && c->ev_valid) c->ev_valid = cudaEventRecord(c->ev1, c->stream) == cudaSuccess;
     if (e != cudaSuccess) {
       set_error(std::string("scans_to_loops: ") + cudaGetErrorString(e));

@@ -269,8 +269,11 @@ struct TcParams {
   size_t q_off_f16, q_off_f8, q_off_f4, q_off_norm, db_off_norm;
   float *d_out[2];              // per channel, m x ldd
   int m, n, m_pad, n_pad, ldd;
-  int n_units, n_tiles;         // units = 2 channels x query groups of 4; tiles of 256 DB rows (of this launch)
-  int qg0, tile0;               // first query group / DB tile of this launch (block launches of the streamed path)
+  // Work of one launch: up to two rectangles of (query group, DB tile) items (the streamed path matches an L-shaped
+  // region per chunk: new queries x all DB rows so far + old queries x new DB rows).  Per rectangle: units = 2 channels x
+  // query groups of 4, tiles of 256 DB rows, first query group / first tile.  w0 = number of items of rectangle 0.
+  int n_units[2], n_tiles[2], qg0[2], tile0[2];
+  long long w0, w_total;
   int flags;                    // debug: 1 skip epilogue loads, 2 skip MMAs, 4 force generic mode, 8 binary channel in e4m3
 };
 
@@ -332,6 +335,18 @@ __device__ __forceinline__ void issue_k_loop(TcBarriers *bars, uint32_t sA, uint
   }
 }
 
+// work item -> (unit id unique within the launch, channel, query group, DB tile)
+__device__ __forceinline__ void tc_decode(const TcParams &P, long long it, int &unit_id, int &ch, int &qg, int &tile) {
+  const int r = it >= P.w0;
+  const long long l = it - (r ? P.w0 : 0);
+  const int nt = P.n_tiles[r];
+  const int unit = (int)(l / nt);
+  tile = P.tile0[r] + (int)(l - (long long)unit * nt);
+  ch = unit & 1;
+  qg = P.qg0[r] + (unit >> 1);
+  unit_id = unit | (r << 28);
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
@@ -359,7 +374,7 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
   for (int ch = 0; ch < 2; ch++) binary[ch] = !(P.flags & 4) && qf[ch] == 0 && df[ch] == 0;
 
   // work items of this CTA pair: contiguous range in unit-major order
-  const long long W = (long long)P.n_units * P.n_tiles;
+  const long long W = P.w_total;
   const long long it_begin = W * pair_id / npairs, it_end = W * (pair_id + 1) / npairs;
 
   if (threadIdx.x == 0) {
@@ -405,14 +420,14 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       for (long long it = it_begin; it < it_end; ++it) {
-        const int unit = (int)(it / P.n_tiles), tile = (int)(it - (long long)unit * P.n_tiles);
-        const int ch = unit & 1;
+        int unit, ch, qg, tile;
+        tc_decode(P, it, unit, ch, qg, tile);
         const bool bin = binary[ch];
         const CUtensorMap *map = bin ? (use_f4 ? (ch == 0 ? &map_f4_0 : &map_f4_1) : (ch == 0 ? &map_f8_0 : &map_f8_1))
                                      : (ch == 0 ? &map_f16_0 : &map_f16_1);
         const int num_kb = bin ? (use_f4 ? F4_KB : F8_CHUNKS * UNITS_PER_CHUNK / KB_UNITS) : F16_CHUNKS * UNITS_PER_CHUNK / KB_UNITS;
         const int kb_elems = bin ? 128 : 64;
-        const int row0 = (P.tile0 + tile) * TILE_M + (int)rank * CTA_M;
+        const int row0 = tile * TILE_M + (int)rank * CTA_M;
         for (int kb = 0; kb < num_kb; kb++) {
           mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1, 1);
           if (leader) mbar_expect_tx(smem_u32(&bars->full[stage]), 2 * A_STAGE_BYTES);
@@ -440,10 +455,10 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
       int prev_unit = -1;
       const int qpairs = P.m_pad >> 1;
       for (long long it = it_begin; it < it_end; ++it) {
-        const int unit = (int)(it / P.n_tiles);
+        int unit, ch, qg, tile;
+        tc_decode(P, it, unit, ch, qg, tile);
         if (unit == prev_unit) continue;
         prev_unit = unit;
-        const int ch = unit & 1, qg = P.qg0 + (unit >> 1);
         const bool bin = binary[ch];
         const uint32_t pair_bytes = (bin ? (use_f4 ? 1 : F8_CHUNKS) : F16_CHUNKS) * CHUNK_BYTES;
         mbar_wait(smem_u32(&bars->b_empty), phase ^ 1, 2);
@@ -469,8 +484,8 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
       int prev_unit = -1;
       const bool skip = (P.flags & 2) != 0;
       for (long long it = it_begin; it < it_end; ++it) {
-        const int unit = (int)(it / P.n_tiles);
-        const int ch = unit & 1;
+        int unit, ch, qg, tile;
+        tc_decode(P, it, unit, ch, qg, tile);
         if (unit != prev_unit) {
           prev_unit = unit;
           mbar_wait(smem_u32(&bars->b_full), b_phase, 4);
@@ -485,7 +500,12 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
           issue_k_loop<2>(bars, sA, sB, tmem_base, tmem_sf, stage, phase, skip);
         else
           issue_k_loop<1>(bars, sA, sB, tmem_base, tmem_sf, stage, phase, skip);
-        const bool last_of_unit = (it + 1 == it_end) || ((int)((it + 1) / P.n_tiles) != unit);
+        bool last_of_unit = it + 1 == it_end;
+        if (!last_of_unit) {
+          int u2, c2, g2, t2;
+          tc_decode(P, it + 1, u2, c2, g2, t2);
+          last_of_unit = u2 != unit;
+        }
         if (elect_one()) {
           umma_commit_2sm(smem_u32(&bars->tmem_full));
           if (last_of_unit) umma_commit_2sm(smem_u32(&bars->b_empty));
@@ -502,8 +522,8 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
     const float *db_norm = reinterpret_cast<const float *>(P.db_buf + P.db_off_norm);
     uint32_t t_phase = 0;
     for (long long it = it_begin; it < it_end; ++it) {
-      const int unit = (int)(it / P.n_tiles), tile = P.tile0 + (int)(it - (long long)unit * P.n_tiles);
-      const int ch = unit & 1, qg = P.qg0 + (unit >> 1);
+      int unit, ch, qg, tile;
+      tc_decode(P, it, unit, ch, qg, tile);
       const bool bin = binary[ch];
       mbar_wait(smem_u32(&bars->tmem_full), t_phase, 8);
       tc_fence_after();
@@ -631,8 +651,22 @@ cudaError_t launch_sc_match_tc(const void *q_buf, int m, const void *db_buf, int
 cudaError_t launch_sc_match_tc_block(const void *q_buf, int m, int q0, int q1, const void *db_buf, int n, int r0, int r1,
                                      float *d_p, float *d_i, int ldd, int num_sms, cudaStream_t st,
                                      int64_t *launches) {
-  if (m <= 0 || n <= 0 || q1 <= q0 || r1 <= r0) return cudaSuccess;
-  if ((q0 % QG) || (r0 % TILE_M)) return cudaErrorInvalidValue;
+  return launch_sc_match_tc_blocks(q_buf, m, db_buf, n, q0, q1, r0, r1, 0, 0, 0, 0, d_p, d_i, ldd, num_sms, st, launches);
+}
+
+// two rectangles [qa0, qa1) x [ra0, ra1) and [qb0, qb1) x [rb0, rb1) in one launch (either may be empty)
+cudaError_t launch_sc_match_tc_blocks(const void *q_buf, int m, const void *db_buf, int n, int qa0, int qa1, int ra0, int ra1,
+                                      int qb0, int qb1, int rb0, int rb1, float *d_p, float *d_i, int ldd, int num_sms,
+                                      cudaStream_t st, int64_t *launches) {
+  if (m <= 0 || n <= 0) return cudaSuccess;
+  const int q0s[2] = {qa0, qb0}, q1s[2] = {qa1, qb1}, r0s[2] = {ra0, rb0}, r1s[2] = {ra1, rb1};
+  long long wr[2];
+  for (int r = 0; r < 2; r++) {
+    const bool empty = q1s[r] <= q0s[r] || r1s[r] <= r0s[r];
+    if (!empty && ((q0s[r] % QG) || (r0s[r] % TILE_M))) return cudaErrorInvalidValue;
+    wr[r] = empty ? 0 : 2LL * ((q1s[r] - q0s[r] + QG - 1) / QG) * ((r1s[r] - r0s[r] + TILE_M - 1) / TILE_M);
+  }
+  if (wr[0] + wr[1] == 0) return cudaSuccess;
   PFN_encodeTiled enc = get_encode();
   if (!enc) return cudaErrorNotSupported;
   DbLayout DL(n);
@@ -667,12 +701,16 @@ cudaError_t launch_sc_match_tc_block(const void *q_buf, int m, int q0, int q1, c
   P.m_pad = QL.m_pad;
   P.n_pad = DL.n_pad;
   P.ldd = ldd;
-  P.qg0 = q0 / QG;
-  P.tile0 = r0 / TILE_M;
-  P.n_units = 2 * ((q1 - q0 + QG - 1) / QG);
-  P.n_tiles = (r1 - r0 + TILE_M - 1) / TILE_M;
+  for (int r = 0; r < 2; r++) {
+    P.qg0[r] = q0s[r] / QG;
+    P.tile0[r] = r0s[r] / TILE_M;
+    P.n_units[r] = wr[r] ? 2 * ((q1s[r] - q0s[r] + QG - 1) / QG) : 0;
+    P.n_tiles[r] = wr[r] ? (r1s[r] - r0s[r] + TILE_M - 1) / TILE_M : 1;
+  }
+  P.w0 = wr[0];
+  P.w_total = wr[0] + wr[1];
   P.flags = tc_flags();
-  const long long W = (long long)P.n_units * P.n_tiles;
+  const long long W = P.w_total;
   int npairs = num_sms / 2;
   if (npairs > W) npairs = (int)W;
   if (npairs < 1) npairs = 1;
