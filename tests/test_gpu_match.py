@@ -116,3 +116,29 @@ def test_tc_equals_simt_at_scale(gpu_ctx, oracle):
     assert np.abs(dp[rows] - rp).max() < TOL_D and np.abs(di[rows] - ri).max() < TOL_D
     # symmetry-like property: d(q, q) == 0 on the diagonal (shift 0 variant)
     assert np.abs(np.diag(dp)).max() < 2e-6
+
+
+def test_channel_modes_binary_and_generic(gpu_ctx, oracle, sigs):
+    """The matcher picks its arithmetic per channel on the device: e2m1 exact counts when every value of a channel is 0 / 1
+    on both sides, the 3-term fp16 split otherwise.  All four combinations, including a real-valued 'intensity' channel,
+    a binary 'structure' channel and a binary query against a non-binary database, against the oracle."""
+    rng = np.random.default_rng(8)
+    base = sigs[:150].copy()
+    real_i = base.copy()
+    real_i[:, 1200:] *= rng.uniform(0.5, 3.0, (150, 1200))            # intensity channel no longer binary
+    bin_s = base.copy()
+    bin_s[:, :1200] = (base[:, :1200] > 0.5).astype(float)             # structure channel binary too
+    mixed_db = base.copy()
+    mixed_db[7, 1200 + 5] = 0.25                                        # one non-binary value in the whole database
+    for q, db in ((real_i[:33], real_i), (bin_s[:33], bin_s), (base[:33], mixed_db), (mixed_db[:33], base)):
+        dp, di = api.processSC(q, db)
+        rp, ri = oracle.sc_match_numpy(q, db)
+        assert np.nanmax(np.abs(dp - rp)) < TOL_D and np.nanmax(np.abs(di - ri)) < TOL_D
+    # a single non-zero bin per signature: the worst case for any reduced-precision scheme (no averaging of rounding errors)
+    one = np.zeros((60, 2400))
+    k = rng.integers(0, 1200, 60)
+    one[np.arange(60), k] = rng.uniform(0.1, 9.0, 60)
+    one[np.arange(60), 1200 + k] = 1.0
+    dp, di = api.processSC(one, one)
+    rp, ri = oracle.sc_match_numpy(one, one)
+    assert np.abs(dp - rp).max() < 1e-6 and np.abs(di - ri).max() < 1e-6
