@@ -3,7 +3,9 @@
 //
 //   IDPose / IDPtIntensity + text I/O   <- PosesPts.h:5-40 (same token order / default precision)
 //   read_poses_pts, pts_preprocess      <- place_recognition/generate_signatures/src/utils/pts_preprocess.h
-//                                          (CPU staging; SURVEY.md §8f row N1 keeps it on the host)
+//                                          (CPU staging in the reference's own container order, so that the point
+//                                          order and incoming_id_file.txt are byte-identical; the GPU staging is
+//                                          sodso_stage_points, used by host/place_recognition.cpp)
 //   class SC, class M2DP, class DELIGHT <- .../src/SC/SC.h:10-23, .../src/M2DP/M2DP.h:12-30, .../src/DELIGHT/DELIGHT.h:12-20
 //   align_points_PCA                    <- .../src/utils/pts_align.h:7-9
 //   write_history / read_history        <- test_sc.cpp:63-66 (Eigen operator<<), test_kitti.m:26 (load)
