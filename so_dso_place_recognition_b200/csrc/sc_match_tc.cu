@@ -4,37 +4,40 @@
 // (processSC.m:24-31).  The 120 variants are the 60 circular sector shifts of the query image x
 // and the 60 circular sector shifts of its sector-reversed image y (reverse shift k of x ==
 // forward shift (61-k) mod 60 of y).  So per (query, DB row) we need the 2 x 60 correlations
-//      corr_b[s] = sum_{c, r} b[(c + s) mod 60][r] * h[c][r],        b in {x, y}
-// i.e. a dense contraction  D[j, (b, s)] = sum_k A[j, k] * B[(b, s), k]  with
-//      A = DB signatures           (M side: 256 DB rows per CTA pair, TMA-fed, SWIZZLE_128B)
-//      B = Hankel matrix of shifts (N side, never materialised)
+//      corr_b[s] = sum_{c < 60, r} b[(c + s) mod 60][r] * h[c][r],        b in {x, y}.
 //
-// The Hankel operand.  K is ordered so that one 16-byte "unit" holds slots of ONE sector, and a
-// base vector is stored doubled ([b, b], unit u = sector u mod 60).  In the canonical K-major
-// no-swizzle UMMA layout ((8,n),2):((16 B, SBO), LBO) rows inside an 8-row core matrix are 16 B
-// apart, so a descriptor with SBO = 128 B reads row r at unit (base + r): overlapping windows of one
-// small buffer ARE the shifted copies.  Two queries are interleaved unit-wise (Z[2u + b] = q_b[u]);
-// with LBO = 32 B, row r = 2 s + b then is shift s of query b, and one N = 256 MMA of a CTA pair
-// (cta_group::2, M = 256, N = 240; CTA 0 supplies the 120 x-rows, CTA 1 the 120 y-rows of B)
-// produces exactly the 120 variants of two queries against 256 DB rows.  A query costs 16 KB (fp16) or
-// 4 KB (fp8) of shared memory per CTA instead of a 120 x 1200 expanded tile per K-block.
+// Even / odd halving.  With  e[u] = b[u] + b[(u+30) mod 60],  o[u] = b[u] - b[(u+30) mod 60]  (u = 0..59; e is
+// 30-periodic, o 30-antiperiodic) and  he[c] = h[c] + h[c+30],  ho[c] = h[c] - h[c+30]  (c = 0..29),
+//      E[s] = sum_{c < 30, r} e[c + s][r] he[c][r] = corr[s] + corr[s + 30]
+//      O[s] = sum_{c < 30, r} o[c + s][r] ho[c][r] = corr[s] - corr[s + 30]          s = 0..29
+// so  max_s corr[s] = max_{s < 30} (E[s] + |O[s]|) / 2 : two contractions of 30 shifts x K = 600 instead of one of
+// 60 shifts x K = 1200 -- half the multiply-adds for the same 120 outputs per (query, DB row).
+// Each is a dense contraction  D[j, (b, s)] = sum_k A[j, k] * B[(b, s), k]  with
+//      A = transformed DB signatures (M side: 256 DB rows per CTA pair, TMA-fed, SWIZZLE_128B)
+//      B = Hankel matrix of shifts   (N side, never materialised)
+//
+// The Hankel operand.  K is ordered so that one 16-byte "unit" holds slots of ONE sector; the 60 units of e (or o)
+// already contain every window of 30 sectors.  In the canonical K-major no-swizzle UMMA layout
+// ((8,n),2):((16 B, SBO), LBO) rows inside an 8-row core matrix are 16 B apart, so a descriptor with SBO = 128 B reads
+// row r at unit (base + r): overlapping windows of one small buffer ARE the shifted copies.  Four queries are
+// interleaved unit-wise (Z[4u + b] = q_b[u]); with LBO = 64 B, row r = 4 s + b then is shift s of query b, and one
+// N = 240 MMA of a CTA pair (cta_group::2, M = 256; CTA 0 supplies the 120 x-rows, CTA 1 the 120 y-rows of B)
+// produces E (TMEM columns 0..239) or O (columns 256..495) of four queries against 256 DB rows.
 //
 // Two arithmetic modes, chosen per channel on the device:
-//  * generic (any real values): rows are normalised in fp64 (processSC.m:15-20), scaled by 64 and
-//    split v = hi + lo into two fp16; the product is evaluated as hi*lo + lo*hi + hi*hi (lo*lo ~
-//    2^-22 dropped) with fp32 accumulation in TMEM.  The three terms are interleaved per sector
-//    into 64 fp16 slots (20 + 20 + 20 + 4 pad), cross terms first so that the large hi*hi partial
-//    sums come last.  |d - d_ref| ~ 1e-6 (measured), bar 1e-5.
-//  * binary (every value 0 or 1 on both sides -- the intensity channel, SC.cpp:67-72): the raw bits
-//    go in as e2m1 under kind::mxf4 (32 slots per 16-byte unit; block scales all 1.0, parked in the
-//    TMEM columns the N = 240 accumulators leave free), TMEM accumulates exact integer overlap
-//    counts, and the epilogue applies 1/(|q| |h|).  7.5x fewer MMAs, exact up to the final fp32
-//    rounding.  (An e4m3 kind::f8f6f4 variant of the same path is kept behind debug flag 8.)
+//  * generic (any real values): rows are normalised in fp64 (processSC.m:15-20), scaled by 64, transformed to e / o in
+//    fp64 and split v = hi + lo into two fp16; the product is evaluated as hi*lo + lo*hi + hi*hi (lo*lo ~ 2^-22
+//    dropped) with fp32 accumulation in TMEM.  The three terms are interleaved per sector into 64 fp16 slots
+//    (20 + 20 + 20 + 4 pad), cross terms first so that the large hi*hi partial sums come last.
+//    |d - d_ref| ~ 1e-6 (measured), bar 1e-5.
+//  * binary (every value 0 or 1 on both sides -- the intensity channel, SC.cpp:67-72): e in {0,1,2} and o in {-1,0,1}
+//    go in as e2m1 under kind::mxf4 (32 slots per 16-byte unit; block scales all 1.0, parked in the TMEM columns the
+//    N = 240 accumulators leave free), TMEM accumulates exact integers, and the epilogue applies 1/(|q| |h|).
 //
 // Roles per CTA (256 threads): warp 0 TMA producer (DB tiles), warp 1 MMA issuer (leader CTA; the
 // warp runs its loop uniformly, one elected lane issues; K loop specialised per operand format),
-// warp 2 TMEM allocator, warp 3 query-operand loader, warps 4-7 epilogue (tcgen05.ld -> max over
-// the shift columns -> (1 - x)/2 -> coalesced fp32 stores).
+// warp 2 TMEM allocator, warp 3 query-operand loader, warps 4-7 epilogue (tcgen05.ld of E and O -> max of E + |O|
+// over the shift columns -> (1 - x/2)/2 -> coalesced fp32 stores).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -48,25 +51,27 @@ namespace sodso {
 namespace {
 using namespace tc;
 
-constexpr int UNITS_PER_CHUNK = SC_NUM_S;            // 60 units (16 B) of K per chunk
-constexpr int F16_CHUNKS = 8;                        // 64 fp16 slots per sector
-constexpr int F8_CHUNKS = 2;                         // 32 fp8 slots per sector
-constexpr int K_F16 = F16_CHUNKS * UNITS_PER_CHUNK * 8;    // 3840 elements
-constexpr int K_F8 = F8_CHUNKS * UNITS_PER_CHUNK * 16;     // 1920 elements (bytes)
-constexpr int F4_ROW_BYTES = 1024;                   // e2m1: 60 units x 32 slots (20 rings + 12 pad) + 4 zero units
+constexpr int HALF_S = SC_NUM_S / 2;                 // 30 sectors per contraction, 30 shifts
+constexpr int F16_CHUNKS = 8;                        // 64 fp16 slots per sector = 8 units of 8
+constexpr int NCOMP = 2;                             // E, O
+constexpr int K_F16 = NCOMP * F16_CHUNKS * HALF_S * 8;     // 3840 elements per DB row: [comp][chunk][sector][8]
+constexpr int F4_ROW_BYTES = 1024;                   // e2m1: [E: 30 units][O: 30 units][4 zero units], 32 slots per unit
 constexpr int F4_KB = F4_ROW_BYTES / 128;            // 8 K-blocks
 constexpr int KB_UNITS = 8;                          // units per K-block (128 B TMA box row)
-constexpr int Q_UNITS = 256;                         // units per (query pair, base, chunk): 2 x doubled vector
-constexpr int CHUNK_BYTES = Q_UNITS * 16;            // 4 KB
-constexpr int QG = 4;                                // queries per tile = 2 interleaved pairs
+constexpr int F16_KB = K_F16 / (KB_UNITS * 8);       // 60 K-blocks
+constexpr int QG = 4;                                // queries per tile, interleaved unit-wise
+constexpr int Q_UNITS = QG * SC_NUM_S;               // 240 units per (query group, base, comp, chunk)
+constexpr int BLOCK_BYTES = Q_UNITS * 16;            // 3840 B
+constexpr int Q_F16_BYTES = NCOMP * F16_CHUNKS * BLOCK_BYTES;   // 61 440 B per (query group, base, channel)
+constexpr int Q_F4_BYTES = NCOMP * BLOCK_BYTES;                 // 7 680 B
 constexpr int TILE_M = 256, CTA_M = 128;             // DB rows per CTA pair / per CTA
-constexpr int N_MMA = 256;                           // TMEM column stride between the two query pairs
-constexpr int N_INST = 240;                          // MMA N: 2 bases x 60 shifts x 2 interleaved queries
+constexpr int N_MMA = 256;                           // TMEM column stride between the E and the O accumulators
+constexpr int N_INST = 240;                          // MMA N: 2 bases x 30 shifts x 4 interleaved queries
 constexpr int A_STAGE_BYTES = CTA_M * 128;           // 16 KB
 constexpr int NSTAGE = 8;
-constexpr int B_BYTES = 2 * F16_CHUNKS * CHUNK_BYTES;   // 64 KB (two pairs, generic mode)
+constexpr int B_BYTES = Q_F16_BYTES;
 constexpr float VAL_SCALE = 64.0f;                   // operand scale (generic mode)
-constexpr float ACC_SCALE = 1.0f / (VAL_SCALE * VAL_SCALE);
+constexpr float ACC_SCALE = 0.5f / (VAL_SCALE * VAL_SCALE);   // (E + |O|) / 2, unscaled
 constexpr int TC_THREADS = 256;
 constexpr int HEADER_BYTES = 256;
 
@@ -82,26 +87,24 @@ inline int pad_to(int v, int a) { return (v + a - 1) / a * a; }
 
 // Operand buffers in HBM.  header: int nonbinary[2] (per channel: some value is not 0/1).
 struct DbLayout {
-  size_t off_f16, off_f8, off_f4, off_norm, total;
+  size_t off_f16, off_f4, off_norm, total;
   int n_pad;
   explicit DbLayout(int n) {
     n_pad = pad_to(n, TILE_M);
     off_f16 = HEADER_BYTES;                                      // [ch][n_pad][3840] fp16
-    off_f8 = off_f16 + (size_t)2 * n_pad * K_F16 * 2;            // [ch][n_pad][1920] e4m3
-    off_f4 = off_f8 + (size_t)2 * n_pad * K_F8;                  // [ch][n_pad][1024 B] e2m1, two per byte
+    off_f4 = off_f16 + (size_t)2 * n_pad * K_F16 * 2;            // [ch][n_pad][1024 B] e2m1, two per byte
     off_norm = off_f4 + (size_t)2 * n_pad * F4_ROW_BYTES;        // [ch][n_pad] float 1/|h|
     total = off_norm + (size_t)2 * n_pad * 4;
   }
 };
 struct QLayout {
-  size_t off_f16, off_f8, off_f4, off_norm, total;
+  size_t off_f16, off_f4, off_norm, total;
   int m_pad;
   explicit QLayout(int m) {
     m_pad = pad_to(m, QG);
-    off_f16 = HEADER_BYTES;                                      // [ch][base][m_pad/2][8][256][16 B]
-    off_f8 = off_f16 + (size_t)2 * 2 * (m_pad / 2) * F16_CHUNKS * CHUNK_BYTES;
-    off_f4 = off_f8 + (size_t)2 * 2 * (m_pad / 2) * F8_CHUNKS * CHUNK_BYTES;     // [ch][base][m_pad/2][256][16 B]
-    off_norm = off_f4 + (size_t)2 * 2 * (m_pad / 2) * CHUNK_BYTES;               // [ch][m_pad] float
+    off_f16 = HEADER_BYTES;                                      // [ch][base][m_pad/4][comp][chunk][240][16 B]
+    off_f4 = off_f16 + (size_t)2 * 2 * (m_pad / QG) * Q_F16_BYTES;   // [ch][base][m_pad/4][comp][240][16 B]
+    off_norm = off_f4 + (size_t)2 * 2 * (m_pad / QG) * Q_F4_BYTES;   // [ch][m_pad] float
     total = off_norm + (size_t)2 * m_pad * 4;
   }
 };
@@ -114,10 +117,11 @@ __device__ __forceinline__ void split_fp16(double v, __half &hi, __half &lo) {
   lo = __float2half_rn((float)(v - (double)__half2float(hi)));
 }
 
-// per-row preparation shared by both operands: norms, fp16 split, binary test
+// per-row preparation shared by both operands: norms, even / odd transform, fp16 split, binary test.
+// Index [u * 20 + r]: e / o at sector u = 0..59 (the DB operand uses u < 30, the query windows all 60).
 struct RowPrep {
-  __half hi[2][SC_SIZE], lo[2][SC_SIZE];
-  unsigned char bits[2][SC_SIZE];   // e4m3 encoding of the raw value when it is 0 or 1
+  __half hi[2][NCOMP][SC_SIZE], lo[2][NCOMP][SC_SIZE];
+  unsigned char nib[2][NCOMP][SC_SIZE];   // e2m1 code of e in {0,1,2} / o in {-1,0,1} when the raw values are 0 or 1
   double red[64];
   int nonbin[2];
   float inv_norm[2];
@@ -148,15 +152,23 @@ __device__ inline void prep_row(const double *h, bool valid, RowPrep &S) {
     for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += S.red[ch * 32 + w];
     nrm[ch] = sqrt(s);  // processSC.m:16,19
   }
+  const __half zero = __float2half(0.0f);
   for (int ch = 0; ch < 2; ch++)
     for (int k = threadIdx.x; k < SC_SIZE; k += blockDim.x) {
       if (valid) {
-        double v = h[ch * SC_SIZE + k];
-        split_fp16(v / nrm[ch] * (double)VAL_SCALE, S.hi[ch][k], S.lo[ch][k]);
-        S.bits[ch][k] = v == 1.0 ? 0x38 : 0x00;  // e4m3 1.0 / 0.0
+        const int k2 = k < SC_SIZE / 2 ? k + SC_SIZE / 2 : k - SC_SIZE / 2;      // sector (u + 30) mod 60, same ring
+        const double r1 = h[ch * SC_SIZE + k], r2 = h[ch * SC_SIZE + k2];
+        const double v1 = r1 / nrm[ch] * (double)VAL_SCALE, v2 = r2 / nrm[ch] * (double)VAL_SCALE;
+        split_fp16(v1 + v2, S.hi[ch][0][k], S.lo[ch][0][k]);
+        split_fp16(v1 - v2, S.hi[ch][1][k], S.lo[ch][1][k]);
+        const int b1 = r1 == 1.0, b2 = r2 == 1.0;
+        S.nib[ch][0][k] = (unsigned char)(b1 + b2 == 2 ? 0x4 : (b1 + b2 == 1 ? 0x2 : 0x0));   // e2m1 2.0 / 1.0 / 0
+        S.nib[ch][1][k] = (unsigned char)(b1 == b2 ? 0x0 : (b1 ? 0x2 : 0xA));                 // 0 / +1.0 / -1.0
       } else {
-        S.hi[ch][k] = S.lo[ch][k] = __float2half(0.0f);
-        S.bits[ch][k] = 0;
+        for (int comp = 0; comp < NCOMP; comp++) {
+          S.hi[ch][comp][k] = S.lo[ch][comp][k] = zero;
+          S.nib[ch][comp][k] = 0;
+        }
       }
     }
   if (threadIdx.x < 2) S.inv_norm[threadIdx.x] = valid ? (float)(1.0 / nrm[threadIdx.x]) : 0.0f;
@@ -166,62 +178,56 @@ __device__ inline void prep_row(const double *h, bool valid, RowPrep &S) {
 // fp16 slot s of a sector: which part of the split value an operand supplies
 //   DB   : slots 0..19 hi, 20..39 lo, 40..59 hi, 60..63 zero
 //   query: slots 0..19 lo, 20..39 hi, 40..59 hi, 60..63 zero          (hi*lo + lo*hi + hi*hi)
-__device__ __forceinline__ __half slot_value(const RowPrep &S, int ch, int sector, int s, bool is_db) {
+__device__ __forceinline__ __half slot_value(const RowPrep &S, int ch, int comp, int sector, int s, bool is_db) {
   if (s >= 60) return __float2half(0.0f);
   const int r = s < 20 ? s : (s < 40 ? s - 20 : s - 40);
   const bool use_lo = is_db ? (s >= 20 && s < 40) : (s < 20);
-  return use_lo ? S.lo[ch][sector * SC_NUM_R + r] : S.hi[ch][sector * SC_NUM_R + r];
+  return use_lo ? S.lo[ch][comp][sector * SC_NUM_R + r] : S.hi[ch][comp][sector * SC_NUM_R + r];
 }
-// fp8 slot s (0..31) of a sector: rings 0..19, then zero padding
-__device__ __forceinline__ unsigned char slot_bits(const RowPrep &S, int ch, int sector, int s) {
-  return s < SC_NUM_R ? S.bits[ch][sector * SC_NUM_R + s] : (unsigned char)0;
-}
-
-// e2m1 byte t (0..15) of a sector's unit: slots 2t (low nibble) and 2t + 1 (high nibble), 1.0 = 0b0010
-__device__ __forceinline__ unsigned char slot_nibbles(const RowPrep &S, int ch, int sector, int t) {
-  const unsigned lo = slot_bits(S, ch, sector, 2 * t) ? 0x2u : 0u, hi = slot_bits(S, ch, sector, 2 * t + 1) ? 0x20u : 0u;
-  return (unsigned char)(lo | hi);
+// e2m1 byte t (0..15) of a sector's unit: slots 2t (low nibble) and 2t + 1 (high nibble); rings 0..19, then zero padding
+__device__ __forceinline__ unsigned char slot_nibbles(const RowPrep &S, int ch, int comp, int sector, int t) {
+  const unsigned lo = 2 * t < SC_NUM_R ? S.nib[ch][comp][sector * SC_NUM_R + 2 * t] : 0u;
+  const unsigned hi = 2 * t + 1 < SC_NUM_R ? S.nib[ch][comp][sector * SC_NUM_R + 2 * t + 1] : 0u;
+  return (unsigned char)(lo | (hi << 4));
 }
 
 __global__ void __launch_bounds__(256)
 sc_tc_prep_db_kernel(const double *__restrict__ hist, int n, int n_pad, unsigned char *__restrict__ buf,
-                     size_t off_f16, size_t off_f8, size_t off_f4, size_t off_norm, int row0, int want_f8) {
+                     size_t off_f16, size_t off_f4, size_t off_norm, int row0) {
   __shared__ RowPrep S;
   const int row = row0 + blockIdx.x;
   prep_row(hist + (size_t)row * 2 * SC_SIZE, row < n, S);
   if (threadIdx.x < 2 && S.nonbin[threadIdx.x]) atomicOr(reinterpret_cast<int *>(buf) + threadIdx.x, 1);
   for (int ch = 0; ch < 2; ch++) {
-    // byte k = unit * 16 + t ; unit = sector (units 60..63: zero padding of the 1024-byte row)
+    // byte k = unit * 16 + t ; units 0..29 E sectors, 30..59 O sectors, 60..63 zero padding of the 1024-byte row
     unsigned char *o4 = buf + off_f4 + ((size_t)ch * n_pad + row) * F4_ROW_BYTES;
-    for (int k = threadIdx.x; k < F4_ROW_BYTES; k += blockDim.x)
-      o4[k] = (k >> 4) < SC_NUM_S ? slot_nibbles(S, ch, k >> 4, k & 15) : (unsigned char)0;
-    // k = chunk*480 + sector*8 + t ; slot = chunk*8 + t
+    for (int k = threadIdx.x; k < F4_ROW_BYTES; k += blockDim.x) {
+      const int unit = k >> 4;
+      o4[k] = unit < 2 * HALF_S ? slot_nibbles(S, ch, unit >= HALF_S, unit >= HALF_S ? unit - HALF_S : unit, k & 15)
+                                : (unsigned char)0;
+    }
+    // k = ((comp*8 + chunk)*30 + sector)*8 + t ; slot = chunk*8 + t
     __half *o = reinterpret_cast<__half *>(buf + off_f16) + ((size_t)ch * n_pad + row) * K_F16;
     for (int k = threadIdx.x; k < K_F16; k += blockDim.x) {
-      const int j = k / (UNITS_PER_CHUNK * 8), rem = k - j * (UNITS_PER_CHUNK * 8);
-      o[k] = slot_value(S, ch, rem >> 3, j * 8 + (rem & 7), true);
-    }
-    // k = chunk*960 + sector*16 + t ; slot = chunk*16 + t
-    unsigned char *o8 = buf + off_f8 + ((size_t)ch * n_pad + row) * K_F8;
-    for (int k = threadIdx.x; want_f8 && k < K_F8; k += blockDim.x) {
-      const int j = k / (UNITS_PER_CHUNK * 16), rem = k - j * (UNITS_PER_CHUNK * 16);
-      o8[k] = slot_bits(S, ch, rem >> 4, j * 16 + (rem & 15));
+      const int blk = k / (HALF_S * 8), rem = k - blk * (HALF_S * 8);
+      o[k] = slot_value(S, ch, blk >> 3, rem >> 3, (blk & 7) * 8 + (rem & 7), true);
     }
     if (threadIdx.x == 0) reinterpret_cast<float *>(buf + off_norm)[(size_t)ch * n_pad + row] = S.inv_norm[ch];
   }
 }
 
-// Query operand: per (channel, base, query pair): [chunk][unit 2u+b][16 B], unit u = sector u % 60 of
-// the base vector of query b of the pair (x: the query image, y: its sector reversal y[c] = x[(60-c)%60]).
-// One CTA prepares a query PAIR, so that the interleaved units are written as one contiguous, fully coalesced
-// stream of 16-byte stores.
+// Query operand: per (channel, base, query group of 4): [comp][chunk][unit 4u+b][16 B], unit u = sector u (0..59) of
+// the e / o sequence of the base vector of query b of the group (x: the query image, y: its sector reversal
+// y[c] = x[(60-c)%60]; e and o of y are the reversals of e and o of x).  One CTA prepares a query GROUP, so that the
+// interleaved units are written as one contiguous, fully coalesced stream of 16-byte stores.
 __global__ void __launch_bounds__(256)
 sc_tc_prep_query_kernel(const double *__restrict__ hist, int m, int m_pad, unsigned char *__restrict__ buf,
-                        size_t off_f16, size_t off_f8, size_t off_f4, size_t off_norm, int pair0, int want_f8) {
-  __shared__ RowPrep S[2];
-  const int pair = pair0 + blockIdx.x, npairs = m_pad >> 1;
-  for (int b = 0; b < 2; b++) {
-    const int row = 2 * pair + b;
+                        size_t off_f16, size_t off_f4, size_t off_norm, int group0) {
+  extern __shared__ __align__(16) unsigned char prep_smem[];
+  RowPrep *S = reinterpret_cast<RowPrep *>(prep_smem);
+  const int group = group0 + blockIdx.x, ngroups = m_pad / QG;
+  for (int b = 0; b < QG; b++) {
+    const int row = QG * group + b;
     prep_row(hist + (size_t)row * 2 * SC_SIZE, row < m, S[b]);
     if (threadIdx.x < 2 && S[b].nonbin[threadIdx.x]) atomicOr(reinterpret_cast<int *>(buf) + threadIdx.x, 1);
     if (threadIdx.x < 2)
@@ -229,35 +235,25 @@ sc_tc_prep_query_kernel(const double *__restrict__ hist, int m, int m_pad, unsig
   }
   for (int ch = 0; ch < 2; ch++)
     for (int base = 0; base < 2; base++) {
-      const size_t pb = ((size_t)ch * 2 + base) * npairs + pair;
-      // fp16: 8 chunks x 256 units of 8 halves
-      uint4 *o = reinterpret_cast<uint4 *>(buf + off_f16 + pb * F16_CHUNKS * CHUNK_BYTES);
-      for (int e = threadIdx.x; e < F16_CHUNKS * Q_UNITS; e += blockDim.x) {
-        const int b = e & 1, u = (e >> 1) & 127, j = e >> 8;
-        const int cs = u % SC_NUM_S, c = base == 0 ? cs : (SC_NUM_S - cs) % SC_NUM_S;
+      const size_t gb = ((size_t)ch * 2 + base) * ngroups + group;
+      uint4 *o = reinterpret_cast<uint4 *>(buf + off_f16 + gb * Q_F16_BYTES);
+      for (int e = threadIdx.x; e < NCOMP * F16_CHUNKS * Q_UNITS; e += blockDim.x) {
+        const int blk = e / Q_UNITS, w = e - blk * Q_UNITS;
+        const int b = w & 3, u = w >> 2;
+        const int c = base == 0 ? u : (SC_NUM_S - u) % SC_NUM_S;
         __align__(16) __half v[8];
 #pragma unroll
-        for (int t = 0; t < 8; t++) v[t] = slot_value(S[b], ch, c, j * 8 + t, false);
+        for (int t = 0; t < 8; t++) v[t] = slot_value(S[b], ch, blk >> 3, c, (blk & 7) * 8 + t, false);
         o[e] = *reinterpret_cast<const uint4 *>(v);
       }
-      if (want_f8) {
-        uint4 *o8 = reinterpret_cast<uint4 *>(buf + off_f8 + pb * F8_CHUNKS * CHUNK_BYTES);
-        for (int e = threadIdx.x; e < F8_CHUNKS * Q_UNITS; e += blockDim.x) {
-          const int b = e & 1, u = (e >> 1) & 127, j = e >> 8;
-          const int cs = u % SC_NUM_S, c = base == 0 ? cs : (SC_NUM_S - cs) % SC_NUM_S;
-          __align__(16) unsigned char v[16];
-#pragma unroll
-          for (int t = 0; t < 16; t++) v[t] = slot_bits(S[b], ch, c, j * 16 + t);
-          o8[e] = *reinterpret_cast<const uint4 *>(v);
-        }
-      }
-      uint4 *o4 = reinterpret_cast<uint4 *>(buf + off_f4 + pb * CHUNK_BYTES);
-      for (int e = threadIdx.x; e < Q_UNITS; e += blockDim.x) {
-        const int b = e & 1, u = e >> 1;
-        const int cs = u % SC_NUM_S, c = base == 0 ? cs : (SC_NUM_S - cs) % SC_NUM_S;
+      uint4 *o4 = reinterpret_cast<uint4 *>(buf + off_f4 + gb * Q_F4_BYTES);
+      for (int e = threadIdx.x; e < NCOMP * Q_UNITS; e += blockDim.x) {
+        const int comp = e / Q_UNITS, w = e - comp * Q_UNITS;
+        const int b = w & 3, u = w >> 2;
+        const int c = base == 0 ? u : (SC_NUM_S - u) % SC_NUM_S;
         __align__(16) unsigned char v[16];
 #pragma unroll
-        for (int t = 0; t < 16; t++) v[t] = slot_nibbles(S[b], ch, c, t);
+        for (int t = 0; t < 16; t++) v[t] = slot_nibbles(S[b], ch, comp, c, t);
         o4[e] = *reinterpret_cast<const uint4 *>(v);
       }
     }
@@ -266,7 +262,7 @@ sc_tc_prep_query_kernel(const double *__restrict__ hist, int m, int m_pad, unsig
 struct TcParams {
   const unsigned char *q_buf;   // QLayout
   const unsigned char *db_buf;  // DbLayout
-  size_t q_off_f16, q_off_f8, q_off_f4, q_off_norm, db_off_norm;
+  size_t q_off_f16, q_off_f4, q_off_norm, db_off_norm;
   float *d_out[2];              // per channel, m x ldd
   int m, n, m_pad, n_pad, ldd;
   // Work of one launch: up to two rectangles of (query group, DB tile) items (the streamed path matches an L-shaped
@@ -274,26 +270,29 @@ struct TcParams {
   // query groups of 4, tiles of 256 DB rows, first query group / first tile.  w0 = number of items of rectangle 0.
   int n_units[2], n_tiles[2], qg0[2], tile0[2];
   long long w0, w_total;
-  int flags;                    // debug: 1 skip epilogue loads, 2 skip MMAs, 4 force generic mode, 8 binary channel in e4m3
+  int flags;                    // debug: 1 skip epilogue loads, 2 skip MMAs, 4 force generic mode
 };
 
 // One work item's K loop on the issuing thread, specialised per operand format so that the loop body is
 // straight-line: descriptors are advanced by integer adds on their 16-byte address field.
-//   MODE 0: fp16 3-term split (kind::f16), 1: e4m3 (kind::f8f6f4), 2: e2m1 (kind::mxf4, block scales = 1)
+//   MODE 0: fp16 3-term split (kind::f16), 2: e2m1 (kind::mxf4, block scales = 1)
+// K runs over [E: chunks x 30 sectors][O: chunks x 30 sectors]; an MMA covers 2 sectors (2 units of the DB row, 8 units of
+// the 4-way interleaved Hankel buffer); after the 15 MMAs of a 30-sector run the Hankel offset skips the 120 units the
+// windows of that block extend over, and after the last E run the destination switches to the O accumulators.
 template <int MODE>
 __device__ __forceinline__ void issue_k_loop(TcBarriers *bars, uint32_t sA, uint32_t sB, uint32_t tmem_base,
                                              uint32_t tmem_sf, int &stage, uint32_t &phase, bool skip) {
-  constexpr int NCHUNK = MODE == 0 ? F16_CHUNKS : (MODE == 1 ? F8_CHUNKS : 1);
-  constexpr int NUM_KB = MODE == 2 ? F4_KB : NCHUNK * UNITS_PER_CHUNK / KB_UNITS;
-  constexpr uint32_t PAIR_UNITS = NCHUNK * CHUNK_BYTES / 16;     // second query pair, in 16-byte descriptor units
+  constexpr int NUM_KB = MODE == 2 ? F4_KB : F16_KB;
+  constexpr int RUNS_E = MODE == 2 ? 1 : F16_CHUNKS;            // 30-sector runs of the E contraction
   constexpr uint32_t idesc = MODE == 2 ? make_idesc_mxf4(TILE_M, N_INST) : make_idesc(TILE_M, N_INST);
   // A: SWIZZLE_128B K-major, 8-row groups 1024 B apart; a K-step advances the start by 32 B (2 units)
   const uint64_t adesc0 = make_desc(sA, 16, 1024, 2);
-  // B: Hankel view, no swizzle: row r = 2 s + b, k-group g -> unit 2 (c + s + g) + b of chunk j
-  const uint64_t bdesc0 = make_desc(sB, 32, 128, 0);
-  uint32_t boff = 0;    // (chunk j) * 256 + 2 * (sector c): the K position of the next MMA in the Hankel buffer
-  uint32_t c2 = 0;      // 2 * c
-  uint32_t acc = 0;
+  // B: Hankel view, no swizzle: row r = 4 s + b, k-group g -> unit 4 (c + s + g) + b of block (comp, chunk)
+  const uint64_t bdesc0 = make_desc(sB, 64, 128, 0);
+  uint32_t boff = 0;    // block * 240 + 4 * (sector c): the K position of the next MMA in the Hankel buffer
+  uint32_t c4 = 0;      // 4 * c
+  int run = 0;
+  uint32_t acc = 0, dst = tmem_base;
 #pragma unroll 1
   for (int kb = 0; kb < NUM_KB; kb++) {
     mbar_wait(smem_u32(&bars->full[stage]), phase, 7);
@@ -302,26 +301,23 @@ __device__ __forceinline__ void issue_k_loop(TcBarriers *bars, uint32_t sA, uint
     if (!skip) {
 #pragma unroll
       for (int kk = 0; kk < 4; kk++) {
+        if (MODE == 2 && run >= 2 * RUNS_E) break;   // e2m1: units 60..63 of the DB row are zero padding
         const uint64_t a = ad + (uint64_t)(kk * 2), b = bdesc0 + (uint64_t)boff;
         if (elect_one()) {
-          if (MODE == 0) {
-            umma_f16_2sm(tmem_base, a, b, idesc, acc);
-            umma_f16_2sm(tmem_base + N_MMA, a, b + PAIR_UNITS, idesc, acc);
-          } else if (MODE == 1) {
-            umma_f8_2sm(tmem_base, a, b, idesc, acc);
-            umma_f8_2sm(tmem_base + N_MMA, a, b + PAIR_UNITS, idesc, acc);
-          } else {
-            umma_mxf4_2sm(tmem_base, a, b, idesc, acc, tmem_sf, tmem_sf + 8);
-            umma_mxf4_2sm(tmem_base + N_MMA, a, b + PAIR_UNITS, idesc, acc, tmem_sf, tmem_sf + 8);
-          }
+          if (MODE == 0)
+            umma_f16_2sm(dst, a, b, idesc, acc);
+          else
+            umma_mxf4_2sm(dst, a, b, idesc, acc, tmem_sf, tmem_sf + 8);
         }
         acc = 1;
-        boff += 4;
-        if (MODE != 2) {   // e2m1: one chunk; units 60..63 of the DB row are zero, what the view reads there is moot
-          c2 += 4;
-          if (c2 >= 2 * UNITS_PER_CHUNK) {
-            c2 -= 2 * UNITS_PER_CHUNK;
-            boff += CHUNK_BYTES / 16 - 2 * UNITS_PER_CHUNK;
+        boff += 2 * QG;
+        c4 += 2 * QG;
+        if (c4 >= (uint32_t)(QG * HALF_S)) {
+          c4 = 0;
+          boff += Q_UNITS - QG * HALF_S;
+          if (++run == RUNS_E) {
+            dst = tmem_base + N_MMA;
+            acc = 0;
           }
         }
       }
@@ -352,7 +348,6 @@ __device__ __forceinline__ void tc_decode(const TcParams &P, long long it, int &
 // ---------------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_constant__ CUtensorMap map_f16_1,
-                   const __grid_constant__ CUtensorMap map_f8_0, const __grid_constant__ CUtensorMap map_f8_1,
                    const __grid_constant__ CUtensorMap map_f4_0, const __grid_constant__ CUtensorMap map_f4_1,
                    const TcParams P) {
   extern __shared__ unsigned char smem_dyn[];
@@ -360,7 +355,7 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
   const uint32_t base = (base_raw + 1023u) & ~1023u;
   unsigned char *smem = smem_dyn + (base - base_raw);
   const uint32_t sA = base;                               // NSTAGE x 16 KB (1024-aligned)
-  const uint32_t sB = base + NSTAGE * A_STAGE_BYTES;      // 64 KB
+  const uint32_t sB = base + NSTAGE * A_STAGE_BYTES;      // 60 KB
   TcBarriers *bars = reinterpret_cast<TcBarriers *>(smem + NSTAGE * A_STAGE_BYTES + B_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -400,9 +395,8 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_ptr;
-  // binary channels run as e2m1 under kind::mxf4 (2x the e4m3 rate); its block scales (ue8m0, all 1.0 = 0x7f)
-  // live in the 16 TMEM columns that the N = 240 accumulators leave free in each 256-column slot
-  const bool use_f4 = !(P.flags & 8);
+  // binary channels run as e2m1 under kind::mxf4; its block scales (ue8m0, all 1.0 = 0x7f) live in the 16 TMEM
+  // columns that the N = 240 accumulators leave free in each 256-column slot
   const uint32_t tmem_sf = tmem_base + (uint32_t)N_INST;
   if (warp >= 4) {
     tmem_st16_const(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)N_INST, 0x7f7f7f7fu);
@@ -423,9 +417,8 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
         int unit, ch, qg, tile;
         tc_decode(P, it, unit, ch, qg, tile);
         const bool bin = binary[ch];
-        const CUtensorMap *map = bin ? (use_f4 ? (ch == 0 ? &map_f4_0 : &map_f4_1) : (ch == 0 ? &map_f8_0 : &map_f8_1))
-                                     : (ch == 0 ? &map_f16_0 : &map_f16_1);
-        const int num_kb = bin ? (use_f4 ? F4_KB : F8_CHUNKS * UNITS_PER_CHUNK / KB_UNITS) : F16_CHUNKS * UNITS_PER_CHUNK / KB_UNITS;
+        const CUtensorMap *map = bin ? (ch == 0 ? &map_f4_0 : &map_f4_1) : (ch == 0 ? &map_f16_0 : &map_f16_1);
+        const int num_kb = bin ? F4_KB : F16_KB;
         const int kb_elems = bin ? 128 : 64;
         const int row0 = tile * TILE_M + (int)rank * CTA_M;
         for (int kb = 0; kb < num_kb; kb++) {
@@ -449,24 +442,24 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
         }
     }
   } else if (warp == 3) {
-    // ===== query operand loader: 2 interleaved query pairs of this CTA's base (x: rank 0, y: rank 1) =====
+    // ===== query operand loader: the 4 interleaved queries of this CTA's base (x: rank 0, y: rank 1) =====
     if (lane == 0) {
       uint32_t phase = 0;
       int prev_unit = -1;
-      const int qpairs = P.m_pad >> 1;
+      const int qgroups = P.m_pad / QG;
       for (long long it = it_begin; it < it_end; ++it) {
         int unit, ch, qg, tile;
         tc_decode(P, it, unit, ch, qg, tile);
         if (unit == prev_unit) continue;
         prev_unit = unit;
         const bool bin = binary[ch];
-        const uint32_t pair_bytes = (bin ? (use_f4 ? 1 : F8_CHUNKS) : F16_CHUNKS) * CHUNK_BYTES;
+        const uint32_t half_bytes = (bin ? Q_F4_BYTES : Q_F16_BYTES) / 2;
         mbar_wait(smem_u32(&bars->b_empty), phase ^ 1, 2);
-        mbar_expect_tx(smem_u32(&bars->b_full), 2 * pair_bytes);
-        const unsigned char *src = P.q_buf + (bin ? (use_f4 ? P.q_off_f4 : P.q_off_f8) : P.q_off_f16) +
-                                   (((size_t)ch * 2 + rank) * qpairs + (size_t)qg * 2) * pair_bytes;
+        mbar_expect_tx(smem_u32(&bars->b_full), 2 * half_bytes);
+        const unsigned char *src = P.q_buf + (bin ? P.q_off_f4 : P.q_off_f16) +
+                                   (((size_t)ch * 2 + rank) * qgroups + (size_t)qg) * (2 * half_bytes);
         for (int p = 0; p < 2; p++)
-          bulk_load_1d(sB + p * pair_bytes, src + (size_t)p * pair_bytes, pair_bytes, smem_u32(&bars->b_full));
+          bulk_load_1d(sB + p * half_bytes, src + (size_t)p * half_bytes, half_bytes, smem_u32(&bars->b_full));
         if (!leader) {
           mbar_wait(smem_u32(&bars->b_full), phase, 3);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -496,10 +489,8 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
         tc_fence_after();
         if (!binary[ch])
           issue_k_loop<0>(bars, sA, sB, tmem_base, tmem_sf, stage, phase, skip);
-        else if (use_f4)
-          issue_k_loop<2>(bars, sA, sB, tmem_base, tmem_sf, stage, phase, skip);
         else
-          issue_k_loop<1>(bars, sA, sB, tmem_base, tmem_sf, stage, phase, skip);
+          issue_k_loop<2>(bars, sA, sB, tmem_base, tmem_sf, stage, phase, skip);
         bool last_of_unit = it + 1 == it_end;
         if (!last_of_unit) {
           int u2, c2, g2, t2;
@@ -531,43 +522,44 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
       float *out = P.d_out[ch];
       const float rd = bin ? db_norm[(size_t)ch * P.n_pad + row] : 0.0f;
       if (!(P.flags & 1)) {
-#pragma unroll 1
-        for (int p = 0; p < 2; p++) {
-          // column 120 h + 2 s + b : base h, shift s, query b of the pair
-          float best0 = __int_as_float(0x7fc00000), best1 = best0;  // NaN: min ignores NaN (processSC.m:31)
-          const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(p * N_MMA);
-#pragma unroll 1
-          for (int cb = 0; cb + 32 <= N_INST; cb += 32) {
-            uint32_t r[32];
-            tmem_ld32(tcol + (uint32_t)cb, r);
-            tmem_ld_wait();
+        // column 120 h + 4 s + b of E (slot 0) and of O (slot 1): base h, shift s, query b of the group;
+        // max over (h, s) of E + |O| = 2 max over the 120 variants.  The loads of block i + 1 are in flight while
+        // block i is reduced.
+        float best[QG];
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              best0 = fmaxf(best0, __uint_as_float(r[i]));
-              best1 = fmaxf(best1, __uint_as_float(r[i + 1]));
-            }
-          }
-          {
-            static_assert(N_INST % 32 == 16, "tail of 16 columns");
-            uint32_t r[16];
-            tmem_ld16(tcol + (uint32_t)(N_INST - 16), r);
-            tmem_ld_wait();
+        for (int b = 0; b < QG; b++) best[b] = __int_as_float(0x7fc00000);  // NaN: min ignores NaN (processSC.m:31)
+        const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16);
+        static_assert(N_INST == 7 * 32 + 16, "7 blocks of 32 columns + a tail of 16");
+        uint32_t e[2][32], o[2][32];
+        tmem_ld32(tcol, e[0]);
+        tmem_ld32(tcol + (uint32_t)N_MMA, o[0]);
+        tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              best0 = fmaxf(best0, __uint_as_float(r[i]));
-              best1 = fmaxf(best1, __uint_as_float(r[i + 1]));
-            }
+        for (int blk = 0; blk < 7; blk++) {
+          const int cur = blk & 1, nxt = cur ^ 1;
+          if (blk + 1 < 7) {
+            tmem_ld32(tcol + (uint32_t)((blk + 1) * 32), e[nxt]);
+            tmem_ld32(tcol + (uint32_t)(N_MMA + (blk + 1) * 32), o[nxt]);
+          } else {
+            tmem_ld16(tcol + (uint32_t)(N_INST - 16), reinterpret_cast<uint32_t(&)[16]>(e[nxt]));
+            tmem_ld16(tcol + (uint32_t)(N_MMA + N_INST - 16), reinterpret_cast<uint32_t(&)[16]>(o[nxt]));
           }
-          const int qi = qg * QG + p * 2;
-          if (row < P.n && out) {
-            if (bin) {
-              if (qi < P.m) out[(size_t)qi * P.ldd + row] = (1.0f - best0 * q_norm[(size_t)ch * P.m_pad + qi] * rd) * 0.5f;
-              if (qi + 1 < P.m)
-                out[(size_t)(qi + 1) * P.ldd + row] = (1.0f - best1 * q_norm[(size_t)ch * P.m_pad + qi + 1] * rd) * 0.5f;
-            } else {
-              if (qi < P.m) out[(size_t)qi * P.ldd + row] = (1.0f - best0 * ACC_SCALE) * 0.5f;
-              if (qi + 1 < P.m) out[(size_t)(qi + 1) * P.ldd + row] = (1.0f - best1 * ACC_SCALE) * 0.5f;
-            }
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            best[i & 3] = fmaxf(best[i & 3], __uint_as_float(e[cur][i]) + fabsf(__uint_as_float(o[cur][i])));
+          tmem_ld_wait();
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+          best[i & 3] = fmaxf(best[i & 3], __uint_as_float(e[1][i]) + fabsf(__uint_as_float(o[1][i])));
+        if (row < P.n && out) {
+#pragma unroll
+          for (int b = 0; b < QG; b++) {
+            const int qi = qg * QG + b;
+            if (qi < P.m)
+              out[(size_t)qi * P.ldd + row] =
+                  bin ? (1.0f - 0.5f * best[b] * q_norm[(size_t)ch * P.m_pad + qi] * rd) * 0.5f
+                      : (1.0f - best[b] * ACC_SCALE) * 0.5f;
           }
         }
       }
@@ -591,7 +583,7 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
 // ---------------------------------------------------------------------------------------------
 }  // namespace
 
-// debug flags (SODSO_TC_FLAGS): 1 skip epilogue loads, 2 skip MMAs, 4 force generic mode, 8 binary channel in e4m3
+// debug flags (SODSO_TC_FLAGS): 1 skip epilogue loads, 2 skip MMAs, 4 force generic mode
 static int tc_flags() {
   const char *e = getenv("SODSO_TC_FLAGS");
   return e ? atoi(e) : 0;
@@ -615,7 +607,7 @@ cudaError_t launch_sc_tc_prep_db_rows(const double *hist, int n, int row0, int r
   if (row1 <= row0) return cudaSuccess;
   DbLayout L(n);
   sc_tc_prep_db_kernel<<<row1 - row0, 256, 0, st>>>(hist, n, L.n_pad, reinterpret_cast<unsigned char *>(db_buf),
-                                                    L.off_f16, L.off_f8, L.off_f4, L.off_norm, row0, tc_flags() & 8);
+                                                    L.off_f16, L.off_f4, L.off_norm, row0);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -624,10 +616,12 @@ cudaError_t launch_sc_tc_prep_query_rows(const double *hist, int m, int row0, in
                                          int64_t *launches) {
   if (row1 <= row0) return cudaSuccess;
   QLayout L(m);
-  if (row0 & 1) return cudaErrorInvalidValue;   // one CTA per query pair
-  sc_tc_prep_query_kernel<<<(row1 - row0 + 1) / 2, 256, 0, st>>>(hist, m, L.m_pad, reinterpret_cast<unsigned char *>(q_buf),
-                                                                 L.off_f16, L.off_f8, L.off_f4, L.off_norm, row0 / 2,
-                                                                 tc_flags() & 8);
+  if (row0 % QG) return cudaErrorInvalidValue;   // one CTA per query group
+  const int smem = QG * (int)sizeof(RowPrep);
+  cudaError_t e = cudaFuncSetAttribute(sc_tc_prep_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  sc_tc_prep_query_kernel<<<(row1 - row0 + QG - 1) / QG, 256, smem, st>>>(
+      hist, m, L.m_pad, reinterpret_cast<unsigned char *>(q_buf), L.off_f16, L.off_f4, L.off_norm, row0 / QG);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -672,15 +666,15 @@ cudaError_t launch_sc_match_tc_blocks(const void *q_buf, int m, const void *db_b
   DbLayout DL(n);
   QLayout QL(m);
   const unsigned char *dbb = reinterpret_cast<const unsigned char *>(db_buf);
-  CUtensorMap maps[6];
-  for (int fmt = 0; fmt < 3; fmt++)
+  CUtensorMap maps[4];
+  for (int fmt = 0; fmt < 2; fmt++)
     for (int ch = 0; ch < 2; ch++) {
-      const size_t kbytes = fmt == 0 ? (size_t)K_F16 * 2 : (fmt == 1 ? (size_t)K_F8 : (size_t)F4_ROW_BYTES);
-      cuuint64_t dims[2] = {(cuuint64_t)(fmt == 0 ? K_F16 : (fmt == 1 ? K_F8 : F4_ROW_BYTES)), (cuuint64_t)DL.n_pad};
+      const size_t kbytes = fmt == 0 ? (size_t)K_F16 * 2 : (size_t)F4_ROW_BYTES;
+      cuuint64_t dims[2] = {(cuuint64_t)(fmt == 0 ? K_F16 : F4_ROW_BYTES), (cuuint64_t)DL.n_pad};
       cuuint64_t strides[1] = {(cuuint64_t)kbytes};
       cuuint32_t box[2] = {(cuuint32_t)(fmt == 0 ? 64 : 128), (cuuint32_t)CTA_M};
       cuuint32_t estr[2] = {1, 1};
-      void *gaddr = (void *)(dbb + (fmt == 0 ? DL.off_f16 : (fmt == 1 ? DL.off_f8 : DL.off_f4)) + (size_t)ch * DL.n_pad * kbytes);
+      void *gaddr = (void *)(dbb + (fmt == 0 ? DL.off_f16 : DL.off_f4) + (size_t)ch * DL.n_pad * kbytes);
       CUresult r = enc(&maps[fmt * 2 + ch], fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
                        gaddr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -690,7 +684,6 @@ cudaError_t launch_sc_match_tc_blocks(const void *q_buf, int m, const void *db_b
   P.q_buf = reinterpret_cast<const unsigned char *>(q_buf);
   P.db_buf = dbb;
   P.q_off_f16 = QL.off_f16;
-  P.q_off_f8 = QL.off_f8;
   P.q_off_f4 = QL.off_f4;
   P.q_off_norm = QL.off_norm;
   P.db_off_norm = DL.off_norm;
@@ -716,7 +709,7 @@ cudaError_t launch_sc_match_tc_blocks(const void *q_buf, int m, const void *db_b
   if (npairs < 1) npairs = 1;
   cudaError_t e = cudaFuncSetAttribute(sc_match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  sc_match_tc_kernel<<<2 * npairs, TC_THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], P);
+  sc_match_tc_kernel<<<2 * npairs, TC_THREADS, SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], P);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
