@@ -583,8 +583,12 @@ int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten,
   // scans are streamed in chunks (a multiple of the 256-row DB tile) when the points live in host memory
   // chunk boundaries (multiples of the 256-row DB tile): two 256-scan chunks first so that matching starts early --
   // the work that can be done grows with the square of what has arrived -- then 512-scan chunks
-  const int CH = 512;
-  const bool streamed = host_pts && host_int && host_off && nscan >= 4 * CH;
+  static const int CH = [] {
+    const char *e = getenv("SODSO_STREAM_CHUNK");
+    const int v = e ? atoi(e) : 512;
+    return v >= 256 && v % 256 == 0 ? v : 512;
+  }();
+  const bool streamed = host_pts && host_int && host_off && nscan >= 2048;
   std::vector<int> bounds{0};
   if (streamed) {
     for (int b = 256; b < nscan; b += b < 512 ? 256 : CH) bounds.push_back(b);

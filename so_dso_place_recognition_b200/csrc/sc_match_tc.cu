@@ -549,6 +549,10 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
             best[i & 3] = fmaxf(best[i & 3], __uint_as_float(e[cur][i]) + fabsf(__uint_as_float(o[cur][i])));
           tmem_ld_wait();
         }
+        // every accumulator of this item is in registers: hand TMEM back before the last reduction and the stores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(leader_tmem_empty);
 #pragma unroll
         for (int i = 0; i < 16; i++)
           best[i & 3] = fmaxf(best[i & 3], __uint_as_float(e[1][i]) + fabsf(__uint_as_float(o[1][i])));
@@ -562,10 +566,11 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
                       : (1.0f - best[b] * ACC_SCALE) * 0.5f;
           }
         }
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(leader_tmem_empty);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(leader_tmem_empty);
       t_phase ^= 1;
     }
   }
