@@ -117,146 +117,147 @@ __device__ __forceinline__ void split_fp16(double v, __half &hi, __half &lo) {
   lo = __float2half_rn((float)(v - (double)__half2float(hi)));
 }
 
-// per-row preparation shared by both operands: norms, even / odd transform, fp16 split, binary test.
-// Index [u * 20 + r]: e / o at sector u = 0..59 (the DB operand uses u < 30, the query windows all 60).
-struct RowPrep {
-  __half hi[2][NCOMP][SC_SIZE], lo[2][NCOMP][SC_SIZE];
-  unsigned char nib[2][NCOMP][SC_SIZE];   // e2m1 code of e in {0,1,2} / o in {-1,0,1} when the raw values are 0 or 1
-  double red[64];
-  int nonbin[2];
-  float inv_norm[2];
+// One (row, channel) as the operands want it: per contraction (E, O) and sequence position u = 0..59 (sector indices
+// mod 60; the DB operand uses u < 30, the query windows all 60) the 64 fp16 slots of that sector and its 16 e2m1 bytes.
+//   fp16 slots   DB   : 0..19 hi, 20..39 lo, 40..59 hi, 60..63 zero
+//                query: 0..19 lo, 20..39 hi, 40..59 hi, 60..63 zero          (hi*lo + lo*hi + hi*hi)
+//   e2m1 byte t: rings 2t (low nibble) and 2t + 1 (high nibble) of e in {0,1,2} / o in {-1,0,1}; bytes 10..15 zero
+// Sectors are 144 B apart and images 96 B (mod 128) so that the 16-byte reads of the copy-out loops (consecutive lanes:
+// consecutive queries of a group, then consecutive sectors) are free of bank conflicts.
+constexpr int IMG_SECTOR_HALVES = 72;
+struct __align__(16) RowImg {
+  __half f16[NCOMP][SC_NUM_S][IMG_SECTOR_HALVES];
+  unsigned char f4[NCOMP][SC_NUM_S][16];
+  double red[8];
+  float inv_norm;
+  int nonbin;
+  int pad[6];
 };
+static_assert(sizeof(RowImg) % 128 == 96, "bank staggering of consecutive images: b * 96 mod 128 = 0, 96, 64, 32");
 
-__device__ inline void prep_row(const double *h, bool valid, RowPrep &S) {
-  if (threadIdx.x < 2) S.nonbin[threadIdx.x] = 0;
-  double ss[2] = {0.0, 0.0};
-  int nb[2] = {0, 0};
+// builds the image of channel ch of one signature row (nsect = 30 for the DB operand, 60 for queries)
+__device__ inline void build_img(const double *h, bool valid, int ch, bool is_db, int nsect, RowImg &S) {
+  const double *hc = h + ch * SC_SIZE;
+  double ss = 0.0;
+  int nb = 0;
   if (valid)
-    for (int ch = 0; ch < 2; ch++)
-      for (int k = threadIdx.x; k < SC_SIZE; k += blockDim.x) {
-        double v = h[ch * SC_SIZE + k];
-        ss[ch] += v * v;
-        if (v != 0.0 && v != 1.0) nb[ch] = 1;
-      }
-  for (int ch = 0; ch < 2; ch++) {
-    double s = ss[ch];
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) S.red[ch * 32 + (threadIdx.x >> 5)] = s;
-  }
-  __syncthreads();
-  for (int ch = 0; ch < 2; ch++)
-    if (nb[ch]) atomicOr(&S.nonbin[ch], 1);
-  double nrm[2];
-  for (int ch = 0; ch < 2; ch++) {
-    double s = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += S.red[ch * 32 + w];
-    nrm[ch] = sqrt(s);  // processSC.m:16,19
-  }
-  const __half zero = __float2half(0.0f);
-  for (int ch = 0; ch < 2; ch++)
     for (int k = threadIdx.x; k < SC_SIZE; k += blockDim.x) {
-      if (valid) {
-        const int k2 = k < SC_SIZE / 2 ? k + SC_SIZE / 2 : k - SC_SIZE / 2;      // sector (u + 30) mod 60, same ring
-        const double r1 = h[ch * SC_SIZE + k], r2 = h[ch * SC_SIZE + k2];
-        const double v1 = r1 / nrm[ch] * (double)VAL_SCALE, v2 = r2 / nrm[ch] * (double)VAL_SCALE;
-        split_fp16(v1 + v2, S.hi[ch][0][k], S.lo[ch][0][k]);
-        split_fp16(v1 - v2, S.hi[ch][1][k], S.lo[ch][1][k]);
-        const int b1 = r1 == 1.0, b2 = r2 == 1.0;
-        S.nib[ch][0][k] = (unsigned char)(b1 + b2 == 2 ? 0x4 : (b1 + b2 == 1 ? 0x2 : 0x0));   // e2m1 2.0 / 1.0 / 0
-        S.nib[ch][1][k] = (unsigned char)(b1 == b2 ? 0x0 : (b1 ? 0x2 : 0xA));                 // 0 / +1.0 / -1.0
-      } else {
-        for (int comp = 0; comp < NCOMP; comp++) {
-          S.hi[ch][comp][k] = S.lo[ch][comp][k] = zero;
-          S.nib[ch][comp][k] = 0;
-        }
-      }
+      const double v = hc[k];
+      ss += v * v;
+      if (v != 0.0 && v != 1.0) nb = 1;
     }
-  if (threadIdx.x < 2) S.inv_norm[threadIdx.x] = valid ? (float)(1.0 / nrm[threadIdx.x]) : 0.0f;
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_down_sync(0xffffffffu, ss, o);
+  if (threadIdx.x == 0) S.nonbin = 0;
+  if ((threadIdx.x & 31) == 0) S.red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (nb) atomicOr(&S.nonbin, 1);
+  double s = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += S.red[w];
+  const double nrm = sqrt(s);  // processSC.m:16,19
+  const __half2 zero2 = __floats2half2_rn(0.0f, 0.0f);
+  // one work item = rings 2t, 2t + 1 of sequence position u
+  for (int it = threadIdx.x; it < nsect * (SC_NUM_R / 2); it += blockDim.x) {
+    const int u = it / (SC_NUM_R / 2), t = it - u * (SC_NUM_R / 2);
+    const int u2 = u < HALF_S ? u + HALF_S : u - HALF_S;      // sector (u + 30) mod 60
+    __half2 hi[NCOMP], lo[NCOMP];
+    unsigned nib[NCOMP] = {0u, 0u};
+    if (valid) {
+      __half h_hi[NCOMP][2], h_lo[NCOMP][2];
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const double r1 = hc[u * SC_NUM_R + 2 * t + q], r2 = hc[u2 * SC_NUM_R + 2 * t + q];
+        const double v1 = r1 / nrm * (double)VAL_SCALE, v2 = r2 / nrm * (double)VAL_SCALE;
+        split_fp16(v1 + v2, h_hi[0][q], h_lo[0][q]);
+        split_fp16(v1 - v2, h_hi[1][q], h_lo[1][q]);
+        const int b1 = r1 == 1.0, b2 = r2 == 1.0;
+        nib[0] |= (b1 + b2 == 2 ? 0x4u : (b1 + b2 == 1 ? 0x2u : 0x0u)) << (4 * q);   // e2m1 2.0 / 1.0 / 0
+        nib[1] |= (b1 == b2 ? 0x0u : (b1 ? 0x2u : 0xAu)) << (4 * q);                 // 0 / +1.0 / -1.0
+      }
+#pragma unroll
+      for (int comp = 0; comp < NCOMP; comp++) {
+        hi[comp] = __halves2half2(h_hi[comp][0], h_hi[comp][1]);
+        lo[comp] = __halves2half2(h_lo[comp][0], h_lo[comp][1]);
+      }
+    } else {
+#pragma unroll
+      for (int comp = 0; comp < NCOMP; comp++) hi[comp] = lo[comp] = zero2;
+    }
+#pragma unroll
+    for (int comp = 0; comp < NCOMP; comp++) {
+      __half2 *dst = reinterpret_cast<__half2 *>(&S.f16[comp][u][0]);
+      dst[t] = is_db ? hi[comp] : lo[comp];
+      dst[10 + t] = is_db ? lo[comp] : hi[comp];
+      dst[20 + t] = hi[comp];
+      if (t < 2) dst[30 + t] = zero2;                          // slots 60..63
+      S.f4[comp][u][t] = (unsigned char)nib[comp];
+      if (t < 6) S.f4[comp][u][10 + t] = 0;                    // rings 20..31: padding
+    }
+  }
+  if (threadIdx.x == 0) S.inv_norm = valid ? (float)(1.0 / nrm) : 0.0f;
   __syncthreads();
 }
 
-// fp16 slot s of a sector: which part of the split value an operand supplies
-//   DB   : slots 0..19 hi, 20..39 lo, 40..59 hi, 60..63 zero
-//   query: slots 0..19 lo, 20..39 hi, 40..59 hi, 60..63 zero          (hi*lo + lo*hi + hi*hi)
-__device__ __forceinline__ __half slot_value(const RowPrep &S, int ch, int comp, int sector, int s, bool is_db) {
-  if (s >= 60) return __float2half(0.0f);
-  const int r = s < 20 ? s : (s < 40 ? s - 20 : s - 40);
-  const bool use_lo = is_db ? (s >= 20 && s < 40) : (s < 20);
-  return use_lo ? S.lo[ch][comp][sector * SC_NUM_R + r] : S.hi[ch][comp][sector * SC_NUM_R + r];
-}
-// e2m1 byte t (0..15) of a sector's unit: slots 2t (low nibble) and 2t + 1 (high nibble); rings 0..19, then zero padding
-__device__ __forceinline__ unsigned char slot_nibbles(const RowPrep &S, int ch, int comp, int sector, int t) {
-  const unsigned lo = 2 * t < SC_NUM_R ? S.nib[ch][comp][sector * SC_NUM_R + 2 * t] : 0u;
-  const unsigned hi = 2 * t + 1 < SC_NUM_R ? S.nib[ch][comp][sector * SC_NUM_R + 2 * t + 1] : 0u;
-  return (unsigned char)(lo | (hi << 4));
-}
-
-__global__ void __launch_bounds__(256)
+// one CTA per (DB row, channel)
+__global__ void __launch_bounds__(128)
 sc_tc_prep_db_kernel(const double *__restrict__ hist, int n, int n_pad, unsigned char *__restrict__ buf,
                      size_t off_f16, size_t off_f4, size_t off_norm, int row0) {
-  __shared__ RowPrep S;
-  const int row = row0 + blockIdx.x;
-  prep_row(hist + (size_t)row * 2 * SC_SIZE, row < n, S);
-  if (threadIdx.x < 2 && S.nonbin[threadIdx.x]) atomicOr(reinterpret_cast<int *>(buf) + threadIdx.x, 1);
-  for (int ch = 0; ch < 2; ch++) {
-    // byte k = unit * 16 + t ; units 0..29 E sectors, 30..59 O sectors, 60..63 zero padding of the 1024-byte row
-    unsigned char *o4 = buf + off_f4 + ((size_t)ch * n_pad + row) * F4_ROW_BYTES;
-    for (int k = threadIdx.x; k < F4_ROW_BYTES; k += blockDim.x) {
-      const int unit = k >> 4;
-      o4[k] = unit < 2 * HALF_S ? slot_nibbles(S, ch, unit >= HALF_S, unit >= HALF_S ? unit - HALF_S : unit, k & 15)
-                                : (unsigned char)0;
-    }
-    // k = ((comp*8 + chunk)*30 + sector)*8 + t ; slot = chunk*8 + t
-    __half *o = reinterpret_cast<__half *>(buf + off_f16) + ((size_t)ch * n_pad + row) * K_F16;
-    for (int k = threadIdx.x; k < K_F16; k += blockDim.x) {
-      const int blk = k / (HALF_S * 8), rem = k - blk * (HALF_S * 8);
-      o[k] = slot_value(S, ch, blk >> 3, rem >> 3, (blk & 7) * 8 + (rem & 7), true);
-    }
-    if (threadIdx.x == 0) reinterpret_cast<float *>(buf + off_norm)[(size_t)ch * n_pad + row] = S.inv_norm[ch];
+  __shared__ RowImg S;
+  const int row = row0 + blockIdx.x, ch = blockIdx.y;
+  build_img(hist + (size_t)row * 2 * SC_SIZE, row < n, ch, true, HALF_S, S);
+  if (threadIdx.x == 0) {
+    if (S.nonbin) atomicOr(reinterpret_cast<int *>(buf) + ch, 1);
+    reinterpret_cast<float *>(buf + off_norm)[(size_t)ch * n_pad + row] = S.inv_norm;
+  }
+  // e2m1 row: units 0..29 E sectors, 30..59 O sectors, 60..63 zero padding of the 1024-byte row
+  uint4 *o4 = reinterpret_cast<uint4 *>(buf + off_f4 + ((size_t)ch * n_pad + row) * F4_ROW_BYTES);
+  for (int unit = threadIdx.x; unit < F4_ROW_BYTES / 16; unit += blockDim.x) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (unit < 2 * HALF_S) v = *reinterpret_cast<const uint4 *>(&S.f4[unit >= HALF_S][unit >= HALF_S ? unit - HALF_S : unit][0]);
+    o4[unit] = v;
+  }
+  // fp16 row: unit = (comp*8 + chunk)*30 + sector holds slots chunk*8 .. chunk*8 + 7 of that sector
+  uint4 *o = reinterpret_cast<uint4 *>(buf + off_f16 + ((size_t)ch * n_pad + row) * K_F16 * 2);
+  for (int unit = threadIdx.x; unit < K_F16 / 8; unit += blockDim.x) {
+    const int blk = unit / HALF_S, c = unit - blk * HALF_S;
+    o[unit] = *reinterpret_cast<const uint4 *>(&S.f16[blk >> 3][c][(blk & 7) * 8]);
   }
 }
 
 // Query operand: per (channel, base, query group of 4): [comp][chunk][unit 4u+b][16 B], unit u = sector u (0..59) of
 // the e / o sequence of the base vector of query b of the group (x: the query image, y: its sector reversal
-// y[c] = x[(60-c)%60]; e and o of y are the reversals of e and o of x).  One CTA prepares a query GROUP, so that the
-// interleaved units are written as one contiguous, fully coalesced stream of 16-byte stores.
+// y[c] = x[(60-c)%60]; e and o of y are the reversals of e and o of x).  One CTA prepares one channel of a query GROUP,
+// so that the interleaved units are written as one contiguous, fully coalesced stream of 16-byte stores.
 __global__ void __launch_bounds__(256)
 sc_tc_prep_query_kernel(const double *__restrict__ hist, int m, int m_pad, unsigned char *__restrict__ buf,
                         size_t off_f16, size_t off_f4, size_t off_norm, int group0) {
   extern __shared__ __align__(16) unsigned char prep_smem[];
-  RowPrep *S = reinterpret_cast<RowPrep *>(prep_smem);
-  const int group = group0 + blockIdx.x, ngroups = m_pad / QG;
+  RowImg *S = reinterpret_cast<RowImg *>(prep_smem);
+  const int group = group0 + blockIdx.x, ngroups = m_pad / QG, ch = blockIdx.y;
   for (int b = 0; b < QG; b++) {
     const int row = QG * group + b;
-    prep_row(hist + (size_t)row * 2 * SC_SIZE, row < m, S[b]);
-    if (threadIdx.x < 2 && S[b].nonbin[threadIdx.x]) atomicOr(reinterpret_cast<int *>(buf) + threadIdx.x, 1);
-    if (threadIdx.x < 2)
-      reinterpret_cast<float *>(buf + off_norm)[(size_t)threadIdx.x * m_pad + row] = S[b].inv_norm[threadIdx.x];
-  }
-  for (int ch = 0; ch < 2; ch++)
-    for (int base = 0; base < 2; base++) {
-      const size_t gb = ((size_t)ch * 2 + base) * ngroups + group;
-      uint4 *o = reinterpret_cast<uint4 *>(buf + off_f16 + gb * Q_F16_BYTES);
-      for (int e = threadIdx.x; e < NCOMP * F16_CHUNKS * Q_UNITS; e += blockDim.x) {
-        const int blk = e / Q_UNITS, w = e - blk * Q_UNITS;
-        const int b = w & 3, u = w >> 2;
-        const int c = base == 0 ? u : (SC_NUM_S - u) % SC_NUM_S;
-        __align__(16) __half v[8];
-#pragma unroll
-        for (int t = 0; t < 8; t++) v[t] = slot_value(S[b], ch, blk >> 3, c, (blk & 7) * 8 + t, false);
-        o[e] = *reinterpret_cast<const uint4 *>(v);
-      }
-      uint4 *o4 = reinterpret_cast<uint4 *>(buf + off_f4 + gb * Q_F4_BYTES);
-      for (int e = threadIdx.x; e < NCOMP * Q_UNITS; e += blockDim.x) {
-        const int comp = e / Q_UNITS, w = e - comp * Q_UNITS;
-        const int b = w & 3, u = w >> 2;
-        const int c = base == 0 ? u : (SC_NUM_S - u) % SC_NUM_S;
-        __align__(16) unsigned char v[16];
-#pragma unroll
-        for (int t = 0; t < 16; t++) v[t] = slot_nibbles(S[b], ch, comp, c, t);
-        o4[e] = *reinterpret_cast<const uint4 *>(v);
-      }
+    build_img(hist + (size_t)row * 2 * SC_SIZE, row < m, ch, false, SC_NUM_S, S[b]);
+    if (threadIdx.x == 0) {
+      if (S[b].nonbin) atomicOr(reinterpret_cast<int *>(buf) + ch, 1);
+      reinterpret_cast<float *>(buf + off_norm)[(size_t)ch * m_pad + row] = S[b].inv_norm;
     }
+  }
+  for (int base = 0; base < 2; base++) {
+    const size_t gb = ((size_t)ch * 2 + base) * ngroups + group;
+    uint4 *o = reinterpret_cast<uint4 *>(buf + off_f16 + gb * Q_F16_BYTES);
+    for (int e = threadIdx.x; e < NCOMP * F16_CHUNKS * Q_UNITS; e += blockDim.x) {
+      const int blk = e / Q_UNITS, w = e - blk * Q_UNITS;
+      const int b = w & 3, u = w >> 2;
+      const int c = base == 0 ? u : (u == 0 ? 0 : SC_NUM_S - u);
+      o[e] = *reinterpret_cast<const uint4 *>(&S[b].f16[blk >> 3][c][(blk & 7) * 8]);
+    }
+    uint4 *o4 = reinterpret_cast<uint4 *>(buf + off_f4 + gb * Q_F4_BYTES);
+    for (int e = threadIdx.x; e < NCOMP * Q_UNITS; e += blockDim.x) {
+      const int comp = e / Q_UNITS, w = e - comp * Q_UNITS;
+      const int b = w & 3, u = w >> 2;
+      const int c = base == 0 ? u : (u == 0 ? 0 : SC_NUM_S - u);
+      o4[e] = *reinterpret_cast<const uint4 *>(&S[b].f4[comp][c][0]);
+    }
+  }
 }
 
 struct TcParams {
@@ -611,8 +612,8 @@ cudaError_t launch_sc_tc_prep_db_rows(const double *hist, int n, int row0, int r
                                       int64_t *launches) {
   if (row1 <= row0) return cudaSuccess;
   DbLayout L(n);
-  sc_tc_prep_db_kernel<<<row1 - row0, 256, 0, st>>>(hist, n, L.n_pad, reinterpret_cast<unsigned char *>(db_buf),
-                                                    L.off_f16, L.off_f4, L.off_norm, row0);
+  sc_tc_prep_db_kernel<<<dim3(row1 - row0, 2), 128, 0, st>>>(hist, n, L.n_pad, reinterpret_cast<unsigned char *>(db_buf),
+                                                             L.off_f16, L.off_f4, L.off_norm, row0);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -622,10 +623,10 @@ cudaError_t launch_sc_tc_prep_query_rows(const double *hist, int m, int row0, in
   if (row1 <= row0) return cudaSuccess;
   QLayout L(m);
   if (row0 % QG) return cudaErrorInvalidValue;   // one CTA per query group
-  const int smem = QG * (int)sizeof(RowPrep);
+  const int smem = QG * (int)sizeof(RowImg);
   cudaError_t e = cudaFuncSetAttribute(sc_tc_prep_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  sc_tc_prep_query_kernel<<<(row1 - row0 + QG - 1) / QG, 256, smem, st>>>(
+  sc_tc_prep_query_kernel<<<dim3((row1 - row0 + QG - 1) / QG, 2), 256, smem, st>>>(
       hist, m, L.m_pad, reinterpret_cast<unsigned char *>(q_buf), L.off_f16, L.off_f4, L.off_norm, row0 / QG);
   if (launches) ++*launches;
   return cudaGetLastError();
