@@ -282,6 +282,23 @@ def run_ours(args):
         step(True)
     ms_e2e, wall_e2e, out2 = timed(True, args.steps)
 
+    # for reference (outside every timed region): what the host -> HBM copy of one step's points costs on its own
+    copy_ms = None
+    if rank == 0:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        scratch = [torch.empty_like(d_xyz), torch.empty_like(d_inten)]
+        torch.cuda.synchronize()
+        best = []
+        for _ in range(3):
+            ev0.record()
+            scratch[0].copy_(h_xyz, non_blocking=True)
+            scratch[1].copy_(h_inten, non_blocking=True)
+            ev1.record()
+            torch.cuda.synchronize()
+            best.append(ev0.elapsed_time(ev1))
+        copy_ms = min(best)
+        del scratch
+
     pairs_step = N_SCANS * n_global            # all ranks together
     idx = out[0].numpy()
     expect = (np.arange(N_SCANS) + N_SCANS // 2) % N_SCANS
@@ -303,7 +320,7 @@ def run_ours(args):
                        "planted_loop_top1_recovered": agree, "e2e_top1_identical": same_e2e},
             "e2e": {"value": pairs_step * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s",
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(N_SCANS * 12),
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "h2d_copy_alone_ms": copy_ms},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "sc_match_tc_kernel",
