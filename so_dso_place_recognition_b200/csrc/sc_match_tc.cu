@@ -332,17 +332,37 @@ __device__ __forceinline__ void issue_k_loop(TcBarriers *bars, uint32_t sA, uint
   }
 }
 
-// work item -> (unit id unique within the launch, channel, query group, DB tile)
-__device__ __forceinline__ void tc_decode(const TcParams &P, long long it, int &unit_id, int &ch, int &qg, int &tile) {
-  const int r = it >= P.w0;
-  const long long l = it - (r ? P.w0 : 0);
-  const int nt = P.n_tiles[r];
-  const int unit = (int)(l / nt);
-  tile = P.tile0[r] + (int)(l - (long long)unit * nt);
-  ch = unit & 1;
-  qg = P.qg0[r] + (unit >> 1);
-  unit_id = unit | (r << 28);
-}
+// Work items of a CTA pair in launch order: (unit id unique within the launch, channel, query group, DB tile).
+// One 64-bit division at the start (and at the rectangle switch), then counters.
+struct ItemIter {
+  int r, unit, tile_l, nt;
+  __device__ __forceinline__ void seek(const TcParams &P, long long it) {
+    r = it >= P.w0;
+    const long long l = it - (r ? P.w0 : 0);
+    nt = P.n_tiles[r];
+    unit = (int)(l / nt);
+    tile_l = (int)(l - (long long)unit * nt);
+  }
+  __device__ __forceinline__ void get(const TcParams &P, int &unit_id, int &ch, int &qg, int &tile) const {
+    tile = P.tile0[r] + tile_l;
+    ch = unit & 1;
+    qg = P.qg0[r] + (unit >> 1);
+    unit_id = unit | (r << 28);
+  }
+  // advance to item it_next = current + 1
+  __device__ __forceinline__ void next(const TcParams &P, long long it_next) {
+    if (r == 0 && it_next == P.w0) {
+      seek(P, it_next);
+    } else if (++tile_l == nt) {
+      tile_l = 0;
+      ++unit;
+    }
+  }
+  // is the current item the last one of its unit?  (more: item it + 1 exists)
+  __device__ __forceinline__ bool last_of_unit(const TcParams &P, long long it, bool more) const {
+    return !more || tile_l + 1 == nt || (r == 0 && it + 1 == P.w0);
+  }
+};
 
 // ---------------------------------------------------------------------------------------------
 // the kernel
@@ -414,9 +434,11 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
       const uint32_t leader_full0 = map_to_cta(smem_u32(&bars->full[0]), 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (long long it = it_begin; it < it_end; ++it) {
+      ItemIter iter;
+      iter.seek(P, it_begin);
+      for (long long it = it_begin; it < it_end; ++it, iter.next(P, it)) {
         int unit, ch, qg, tile;
-        tc_decode(P, it, unit, ch, qg, tile);
+        iter.get(P, unit, ch, qg, tile);
         const bool bin = binary[ch];
         const CUtensorMap *map = bin ? (ch == 0 ? &map_f4_0 : &map_f4_1) : (ch == 0 ? &map_f16_0 : &map_f16_1);
         const int num_kb = bin ? F4_KB : F16_KB;
@@ -448,9 +470,11 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
       uint32_t phase = 0;
       int prev_unit = -1;
       const int qgroups = P.m_pad / QG;
-      for (long long it = it_begin; it < it_end; ++it) {
+      ItemIter iter;
+      iter.seek(P, it_begin);
+      for (long long it = it_begin; it < it_end; ++it, iter.next(P, it)) {
         int unit, ch, qg, tile;
-        tc_decode(P, it, unit, ch, qg, tile);
+        iter.get(P, unit, ch, qg, tile);
         if (unit == prev_unit) continue;
         prev_unit = unit;
         const bool bin = binary[ch];
@@ -477,9 +501,11 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
       uint32_t phase = 0, b_phase = 0, t_phase = 0;
       int prev_unit = -1;
       const bool skip = (P.flags & 2) != 0;
-      for (long long it = it_begin; it < it_end; ++it) {
+      ItemIter iter;
+      iter.seek(P, it_begin);
+      for (long long it = it_begin; it < it_end; ++it, iter.next(P, it)) {
         int unit, ch, qg, tile;
-        tc_decode(P, it, unit, ch, qg, tile);
+        iter.get(P, unit, ch, qg, tile);
         if (unit != prev_unit) {
           prev_unit = unit;
           mbar_wait(smem_u32(&bars->b_full), b_phase, 4);
@@ -492,12 +518,7 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
           issue_k_loop<0>(bars, sA, sB, tmem_base, tmem_sf, stage, phase, skip);
         else
           issue_k_loop<2>(bars, sA, sB, tmem_base, tmem_sf, stage, phase, skip);
-        bool last_of_unit = it + 1 == it_end;
-        if (!last_of_unit) {
-          int u2, c2, g2, t2;
-          tc_decode(P, it + 1, u2, c2, g2, t2);
-          last_of_unit = u2 != unit;
-        }
+        const bool last_of_unit = iter.last_of_unit(P, it, it + 1 < it_end);
         if (elect_one()) {
           umma_commit_2sm(smem_u32(&bars->tmem_full));
           if (last_of_unit) umma_commit_2sm(smem_u32(&bars->b_empty));
@@ -513,9 +534,11 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
     const float *q_norm = reinterpret_cast<const float *>(P.q_buf + P.q_off_norm);
     const float *db_norm = reinterpret_cast<const float *>(P.db_buf + P.db_off_norm);
     uint32_t t_phase = 0;
-    for (long long it = it_begin; it < it_end; ++it) {
+    ItemIter iter;
+    iter.seek(P, it_begin);
+    for (long long it = it_begin; it < it_end; ++it, iter.next(P, it)) {
       int unit, ch, qg, tile;
-      tc_decode(P, it, unit, ch, qg, tile);
+      iter.get(P, unit, ch, qg, tile);
       const bool bin = binary[ch];
       mbar_wait(smem_u32(&bars->tmem_full), t_phase, 8);
       tc_fence_after();
