@@ -188,13 +188,23 @@ int sc_prepare(sodso_ctx *c, int algo, const double *hist_dev, int rows, Buf &op
   return SODSO_OK;
 }
 
+// A self-match (hist1 and hist2 are the same n rows) has a symmetric distance matrix: the tcgen05 matcher then computes
+// the lower block triangle only and stores every value at its transposed position as well.  SODSO_SC_SYMMETRY=0
+// switches this off (every pair computed, as for distinct operands).
+static bool sc_symmetry_enabled() {
+  const char *e = getenv("SODSO_SC_SYMMETRY");   // read per call: tests toggle it
+  return !(e && atoi(e) == 0);
+}
+
 int sc_match_core(sodso_ctx *c, int algo, const Buf &q_op, int m, const Buf &db_op, int n, float *dp,
-                  float *di, int ldd) {
+                  float *di, int ldd, bool self = false) {
   TimedRegion tr(c, algo == SODSO_ALGO_SIMT ? "sc_match_simt_kernel" : "sc_match_tc_kernel");
   if (algo == SODSO_ALGO_SIMT) {
     int ldq = (m + 31) & ~31, ldh = (n + 31) & ~31;
     SODSO_CUDA_CHECK(launch_sc_match_simt(q_op.as<float>(), m, ldq, db_op.as<float>(), n, ldh, dp, di,
                                           ldd, c->stream, &c->launches));
+  } else if (self && m == n && sc_symmetry_enabled()) {
+    SODSO_CUDA_CHECK(launch_sc_match_tc_self(q_op.p, db_op.p, n, 0, n, dp, di, ldd, c->num_sms, c->stream, &c->launches));
   } else {
     SODSO_CUDA_CHECK(launch_sc_match_tc(q_op.p, m, db_op.p, n, dp, di, ldd, c->num_sms, c->stream,
                                         &c->launches));
@@ -214,7 +224,7 @@ int match_to_device(sodso_ctx *c, int type, const double *hist1, int m, const do
   if (type == SODSO_TYPE_SC) {
     if ((rc = sc_prepare(c, c->algo, h2d, n, c->db_op, true))) return rc;
     if ((rc = sc_prepare(c, c->algo, h1d, m, c->q_op, false))) return rc;
-    return sc_match_core(c, c->algo, c->q_op, m, c->db_op, n, dp, di, n);
+    return sc_match_core(c, c->algo, c->q_op, m, c->db_op, n, dp, di, n, hist1 == hist2 && m == n);
   }
   if (c->algo == SODSO_ALGO_SIMT) {
     SODSO_CUDA_CHECK(c->m2dp_ws.reserve(m2dp_match_workspace_bytes(m, n)));
@@ -678,9 +688,14 @@ int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten,
     // processSC.m:22-33 for every (query, DB) pair that has become available: new queries x all DB rows so far,
     // old queries x new DB rows
     if (!streamed && e == cudaSuccess) c->ev_valid = cudaEventRecord(c->ev0, c->stream) == cudaSuccess;
-    if (e == cudaSuccess)   // one launch for the L-shaped region
-      e = launch_sc_match_tc_blocks(c->q_op.p, nscan, c->db_op.p, nscan, s0, s1, 0, s1, 0, s0, s0, s1, dp, di, nscan,
-                                    c->num_sms, c->stream, &c->launches);
+    if (e == cudaSuccess) {
+      if (sc_symmetry_enabled())   // self-match: the new queries against the DB rows up to their own block, transposes stored
+        e = launch_sc_match_tc_self(c->q_op.p, c->db_op.p, nscan, s0, s1, dp, di, nscan, c->num_sms, c->stream,
+                                    &c->launches);
+      else                         // one launch for the L-shaped region
+        e = launch_sc_match_tc_blocks(c->q_op.p, nscan, c->db_op.p, nscan, s0, s1, 0, s1, 0, s0, s0, s1, dp, di, nscan,
+                                      c->num_sms, c->stream, &c->launches);
+    }
     if (!streamed && c->ev_valid) c->ev_valid = cudaEventRecord(c->ev1, c->stream) == cudaSuccess;
     if (e != cudaSuccess) {
       set_error(std::string("scans_to_loops: ") + cudaGetErrorString(e));

@@ -272,7 +272,17 @@ struct TcParams {
   int n_units[2], n_tiles[2], qg0[2], tile0[2];
   long long w0, w_total;
   int flags;                    // debug: 1 skip epilogue loads, 2 skip MMAs, 4 force generic mode
+  // Self-match (queries == DB rows, m == n): d is symmetric, so only the (query group, DB tile) items with
+  // tile_start <= group_end are computed (rectangle 0 = queries [q0, q1), q0 a multiple of 256, tiles 0 .. diagonal) and
+  // every value whose transposed position belongs to an item that is not computed is stored there as well.
+  int tri, tri_nt0;             // tri_nt0: tiles of the first query block (q0 / 256 + 1)
 };
+constexpr int TRI_UNITS = 2 * TILE_M / QG;   // 128 units (2 channels x 64 query groups) share a tile count
+
+// items before query block lb of a triangular region
+__host__ __device__ __forceinline__ long long tri_prefix(int lb, int nt0) {
+  return (long long)TRI_UNITS * ((long long)lb * nt0 + (long long)lb * (lb - 1) / 2);
+}
 
 // One work item's K loop on the issuing thread, specialised per operand format so that the loop body is
 // straight-line: descriptors are advanced by integer adds on their 16-byte address field.
@@ -337,6 +347,17 @@ __device__ __forceinline__ void issue_k_loop(TcBarriers *bars, uint32_t sA, uint
 struct ItemIter {
   int r, unit, tile_l, nt;
   __device__ __forceinline__ void seek(const TcParams &P, long long it) {
+    if (P.tri) {
+      r = 0;
+      int lb = 0;
+      while (tri_prefix(lb + 1, P.tri_nt0) <= it) ++lb;
+      const long long rem = it - tri_prefix(lb, P.tri_nt0);
+      nt = P.tri_nt0 + lb;
+      const int u = (int)(rem / nt);
+      unit = lb * TRI_UNITS + u;
+      tile_l = (int)(rem - (long long)u * nt);
+      return;
+    }
     r = it >= P.w0;
     const long long l = it - (r ? P.w0 : 0);
     nt = P.n_tiles[r];
@@ -351,16 +372,17 @@ struct ItemIter {
   }
   // advance to item it_next = current + 1
   __device__ __forceinline__ void next(const TcParams &P, long long it_next) {
-    if (r == 0 && it_next == P.w0) {
+    if (!P.tri && r == 0 && it_next == P.w0) {
       seek(P, it_next);
     } else if (++tile_l == nt) {
       tile_l = 0;
       ++unit;
+      if (P.tri && (unit & (TRI_UNITS - 1)) == 0) ++nt;
     }
   }
   // is the current item the last one of its unit?  (more: item it + 1 exists)
   __device__ __forceinline__ bool last_of_unit(const TcParams &P, long long it, bool more) const {
-    return !more || tile_l + 1 == nt || (r == 0 && it + 1 == P.w0);
+    return !more || tile_l + 1 == nt || (!P.tri && r == 0 && it + 1 == P.w0);
   }
 };
 
@@ -581,13 +603,26 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
         for (int i = 0; i < 16; i++)
           best[i & 3] = fmaxf(best[i & 3], __uint_as_float(e[1][i]) + fabsf(__uint_as_float(o[1][i])));
         if (row < P.n && out) {
+          float d[QG];
 #pragma unroll
           for (int b = 0; b < QG; b++) {
             const int qi = qg * QG + b;
-            if (qi < P.m)
-              out[(size_t)qi * P.ldd + row] =
-                  bin ? (1.0f - 0.5f * best[b] * q_norm[(size_t)ch * P.m_pad + qi] * rd) * 0.5f
-                      : (1.0f - best[b] * ACC_SCALE) * 0.5f;
+            d[b] = bin ? (1.0f - 0.5f * best[b] * (qi < P.m ? q_norm[(size_t)ch * P.m_pad + qi] : 0.0f) * rd) * 0.5f
+                       : (1.0f - best[b] * ACC_SCALE) * 0.5f;
+            if (qi < P.m) out[(size_t)qi * P.ldd + row] = d[b];
+          }
+          // self-match: d(row, qi) = d(qi, row) when the item (query group of `row`, DB tile of qi) is not computed,
+          // i.e. when the tile of the queries starts after the group of `row` ends
+          const int q0 = qg * QG;
+          if (P.tri && (q0 / TILE_M) * TILE_M > (row | (QG - 1))) {
+            float *mo = out + (size_t)row * P.ldd + q0;
+            if (q0 + QG <= P.m && (P.ldd & 3) == 0) {
+              *reinterpret_cast<float4 *>(mo) = make_float4(d[0], d[1], d[2], d[3]);
+            } else {
+#pragma unroll
+              for (int b = 0; b < QG; b++)
+                if (q0 + b < P.m) mo[b] = d[b];
+            }
           }
         }
       } else {
@@ -677,11 +712,22 @@ cudaError_t launch_sc_match_tc_block(const void *q_buf, int m, int q0, int q1, c
   return launch_sc_match_tc_blocks(q_buf, m, db_buf, n, q0, q1, r0, r1, 0, 0, 0, 0, d_p, d_i, ldd, num_sms, st, launches);
 }
 
-// two rectangles [qa0, qa1) x [ra0, ra1) and [qb0, qb1) x [rb0, rb1) in one launch (either may be empty)
+// self-match of an n x n problem, queries [q0, q1) (q0 a multiple of 256) against the DB rows up to their own block:
+// the part of the lower block triangle that belongs to these queries; the transposed values are stored as well
+cudaError_t launch_sc_match_tc_self(const void *q_buf, const void *db_buf, int n, int q0, int q1, float *d_p, float *d_i,
+                                    int ldd, int num_sms, cudaStream_t st, int64_t *launches) {
+  if (q0 % TILE_M) return cudaErrorInvalidValue;
+  return launch_sc_match_tc_blocks(q_buf, n, db_buf, n, q0, q1, 0, n, -1, 0, 0, 0, d_p, d_i, ldd, num_sms, st, launches);
+}
+
+// two rectangles [qa0, qa1) x [ra0, ra1) and [qb0, qb1) x [rb0, rb1) in one launch (either may be empty);
+// qb0 < 0: rectangle A is the triangular region of a self-match (launch_sc_match_tc_self)
 cudaError_t launch_sc_match_tc_blocks(const void *q_buf, int m, const void *db_buf, int n, int qa0, int qa1, int ra0, int ra1,
                                       int qb0, int qb1, int rb0, int rb1, float *d_p, float *d_i, int ldd, int num_sms,
                                       cudaStream_t st, int64_t *launches) {
   if (m <= 0 || n <= 0) return cudaSuccess;
+  const bool tri = qb0 < 0;
+  if (tri) qb0 = 0;
   const int q0s[2] = {qa0, qb0}, q1s[2] = {qa1, qb1}, r0s[2] = {ra0, rb0}, r1s[2] = {ra1, rb1};
   long long wr[2];
   for (int r = 0; r < 2; r++) {
@@ -731,6 +777,13 @@ cudaError_t launch_sc_match_tc_blocks(const void *q_buf, int m, const void *db_b
   }
   P.w0 = wr[0];
   P.w_total = wr[0] + wr[1];
+  P.tri = tri ? 1 : 0;
+  P.tri_nt0 = qa0 / TILE_M + 1;
+  if (tri) {
+    const int units = P.n_units[0], lb_full = units / TRI_UNITS;
+    P.w0 = P.w_total = tri_prefix(lb_full, P.tri_nt0) + (long long)(units - lb_full * TRI_UNITS) * (P.tri_nt0 + lb_full);
+    P.tile0[0] = 0;
+  }
   P.flags = tc_flags();
   const long long W = P.w_total;
   int npairs = num_sms / 2;
