@@ -386,6 +386,40 @@ struct ItemIter {
   }
 };
 
+// Split of the item sequence over the CTA pairs by COST, not by count: an item of a generic channel (240 MMAs) takes
+// about 5.5 x as long as one of a binary channel (30 MMAs + the same hand-off), and the sequence alternates runs of up
+// to 20 items of either kind, so equal counts leave the slowest pair up to 0.3 ms behind.  Items of one query group g:
+// [channel 0: nt(g) tiles][channel 1: nt(g) tiles]; cost of a group = nt(g) (w0 + w1).  Returns the index of the item
+// at fraction num / den of the total cost.
+__device__ __forceinline__ long long item_at_cost(const TcParams &P, int w0, int w1, long long num, long long den) {
+  const long long tg_total = P.w_total / 2;                       // (group, tile) pairs of the launch
+  if (num >= den) return P.w_total;
+  const long long x = tg_total * (w0 + w1) * num / den;          // cost position (< 2^63 for any realistic launch)
+  // group containing cost x: tile-pair prefix T(g) <= x / (w0 + w1)
+  const long long tq = x / (w0 + w1);
+  long long t_before;   // T(g)
+  long long item_base;  // index of the first item of group g
+  int nt;
+  if (P.tri) {
+    int lb = 0;                                   // query block (64 groups share a tile count)
+    while (tri_prefix(lb + 1, P.tri_nt0) / 2 <= tq) ++lb;
+    nt = P.tri_nt0 + lb;
+    const long long k = (tq - tri_prefix(lb, P.tri_nt0) / 2) / nt;
+    t_before = tri_prefix(lb, P.tri_nt0) / 2 + k * nt;
+    item_base = 2 * t_before;
+  } else {
+    const long long tg0 = P.w0 / 2;
+    const int r = tq >= tg0;
+    nt = P.n_tiles[r];
+    const long long k = (tq - (r ? tg0 : 0)) / nt;
+    t_before = (r ? tg0 : 0) + k * nt;
+    item_base = 2 * t_before;
+  }
+  const long long rem = x - t_before * (w0 + w1);                 // cost inside the group, < nt (w0 + w1)
+  if (rem < (long long)nt * w0) return item_base + rem / w0;
+  return item_base + nt + (rem - (long long)nt * w0) / w1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
@@ -411,9 +445,10 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
   bool binary[2];
   for (int ch = 0; ch < 2; ch++) binary[ch] = !(P.flags & 4) && qf[ch] == 0 && df[ch] == 0;
 
-  // work items of this CTA pair: contiguous range in unit-major order
-  const long long W = P.w_total;
-  const long long it_begin = W * pair_id / npairs, it_end = W * (pair_id + 1) / npairs;
+  // work items of this CTA pair: contiguous range in unit-major order, equal shares of the estimated cost
+  constexpr int W_GENERIC = 11, W_BINARY = 2;   // measured: 30.8 k vs 5.6 k clocks per item incl. the hand-off
+  const int wc0 = binary[0] ? W_BINARY : W_GENERIC, wc1 = binary[1] ? W_BINARY : W_GENERIC;
+  const long long it_begin = item_at_cost(P, wc0, wc1, pair_id, npairs), it_end = item_at_cost(P, wc0, wc1, pair_id + 1, npairs);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; s++) {
