@@ -123,39 +123,53 @@ fuse_topk_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, i
   const long long qg = q_row0 + row;
   double last_s = 0.0;
   long long last_i = -1;  // nothing selected yet
-  // First selection: the two fp64 divisions per element are only needed to order the few entries that are within
-  // rounding distance of the row minimum.  A linear form a_p p + a_i q + c0 (two FMAs, |error| ~ 1e-13) gives the
-  // minimum to within `margin`; the exact expression of run_test.m:40-46 then decides among the entries below
-  // min + margin.  Rows with no finite unmasked entry, or with degenerate statistics, take the plain loop.
+  // The two fp64 divisions per element are only needed to order the few entries around the k smallest.  A linear
+  // form a_p p + a_i q + c0 (two FMAs, |error| ~ 1e-13) is selected k times (cheap passes, ordered by (value, index));
+  // every entry of the exact top-k then lies at or below the k-th selected value + margin, and the exact expression
+  // of run_test.m:40-46 is evaluated only for those.  Rows with fewer than k finite unmasked entries, or with
+  // degenerate statistics, take the plain loop (bound = +inf admits everything, masked entries included).
   const double a_p = p_weight / sd_p, a_i = 1.0 / sd_i, c0 = -(a_p * mu_p + a_i * mu_i);
   const bool lin_ok = isfinite(a_p) && isfinite(a_i) && isfinite(c0);
-  double bound = -INFINITY;   // candidates of the first selection: linear form <= bound
+  double bound = INFINITY;
   if (lin_ok) {
-    double mn = INFINITY;
-    for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
-      long long dist = qg - (db_row0 + j);
-      if (dist < 0) dist = -dist;
-      if (dist < (long long)mask_width) continue;
-      const double fl = fma(a_p, (double)p[j], fma(a_i, (double)q[j], c0));
-      mn = fmin(mn, fl);   // fmin ignores NaN
+    double sel_s = 0.0;
+    long long sel_i = -1;
+    bool enough = true;
+    for (int r = 0; r < k; r++) {
+      double bs = 0.0;
+      long long bi = -1;
+      for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
+        const long long jg = db_row0 + j;
+        long long dist = qg - jg;
+        if (dist < 0) dist = -dist;
+        if (dist < (long long)mask_width) continue;
+        const double fl = fma(a_p, (double)p[j], fma(a_i, (double)q[j], c0));
+        if (!isfinite(fl)) continue;
+        if (sel_i >= 0 && !cand_less(sel_s, sel_i, fl, jg)) continue;  // selected in an earlier pass
+        if (cand_less(fl, jg, bs, bi)) {
+          bs = fl;
+          bi = jg;
+        }
+      }
+      block_argmin(bs, bi, ss, si);
+      if (bi < 0) {
+        enough = false;
+        break;
+      }
+      sel_s = bs;
+      sel_i = bi;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    if ((threadIdx.x & 31) == 0) ss[threadIdx.x >> 5] = mn;
-    __syncthreads();
-    for (int w = 0; w < (int)(blockDim.x >> 5); w++) mn = fmin(mn, ss[w]);
-    __syncthreads();
-    if (isfinite(mn)) bound = mn + 1e-9 * (1.0 + fabs(mn));
+    if (enough) bound = sel_s + 1e-9 * (1.0 + fabs(sel_s));
   }
   for (int r = 0; r < k; r++) {
     double bs = 0.0;
     long long bi = -1;
-    const bool filtered = r == 0 && bound > -INFINITY;
+    const bool filtered = bound < INFINITY;
     for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
       const long long jg = db_row0 + j;
       if (filtered) {
-        // an unmasked entry above the bound cannot be the minimum; masked entries (+inf) lose against the finite
-        // minimum that is known to exist
+        // an unmasked entry above the bound cannot be among the k smallest; masked entries (+inf) lose against the
+        // k finite entries that are known to exist
         long long dist0 = qg - jg;
         if (dist0 < 0) dist0 = -dist0;
         if (dist0 < (long long)mask_width) continue;

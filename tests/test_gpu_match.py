@@ -142,3 +142,50 @@ def test_channel_modes_binary_and_generic(gpu_ctx, oracle, sigs):
     dp, di = api.processSC(one, one)
     rp, ri = oracle.sc_match_numpy(one, one)
     assert np.abs(dp - rp).max() < 1e-6 and np.abs(di - ri).max() < 1e-6
+
+
+def _topk_numpy(dp, di, q0, row0, mask, k):
+    n = dp.shape[1]
+    out = []
+    for i in range(dp.shape[0]):
+        with np.errstate(invalid="ignore", divide="ignore"):
+            mu_p, mu_i = np.mean(dp[i]), np.mean(di[i])
+            sd_p, sd_i = np.std(dp[i], ddof=1), np.std(di[i], ddof=1)
+            f = 2.0 * ((dp[i] - mu_p) / sd_p) + (di[i] - mu_i) / sd_i
+        jg = row0 + np.arange(n)
+        f[np.abs((q0 + i) - jg) < mask] = np.inf
+        order = [j for j in np.lexsort((jg, f)) if not np.isnan(f[j])][:k]
+        out.append((order, f))
+    return out
+
+
+@pytest.mark.parametrize("k", [1, 3, 8])
+@pytest.mark.parametrize("n_db", [384, 12])
+def test_topk_vs_numpy_on_device_distances(gpu_ctx, sigs, k, n_db):
+    """sodso_db_topk (run_test.m:38-57 generalised to the k best) against a numpy restatement on the SAME fp32
+    distances: indices identical incl. order, scores to 1e-9; with the mask, a NaN query row, global row offsets as a
+    shard would have them, and (12-row DB, mask 5) rows whose unmasked entries are fewer than k, where the masked
+    (+inf) entries are handed out in index order."""
+    h = sigs[:n_db]
+    mask = 20 if n_db > 100 else 5
+    row0 = 1000
+    q0 = row0 + (17 if n_db > 100 else 2)        # query i is global row q0 + i
+    q = sigs[:40].copy() if n_db > 100 else sigs[:8].copy()
+    q[5] = 0.0                                   # zero-norm query: NaN distances
+    db = api.SignatureDB("sc", h, global_row0=row0)
+    db.match(q)
+    st = db.partial_stats()
+    idx, score, dpa, dia = db.topk(st, n_db, q0, mask, 2.0, k)
+    dp, di = db.distances()
+    db.close()
+    dp, di = dp.astype(np.float64), di.astype(np.float64)
+    for i, (order, f) in enumerate(_topk_numpy(dp, di, q0, row0, mask, k)):
+        want = [row0 + j for j in order] + [-1] * (k - len(order))
+        assert list(idx[i]) == want, (i, idx[i], want)
+        for r, j in enumerate(order):
+            if np.isfinite(f[j]):
+                assert abs(score[i, r] - f[j]) < 1e-9 * (1 + abs(f[j]))
+            np.testing.assert_array_equal([dpa[i, r], dia[i, r]], [dp[i, j], di[i, j]])   # NaN == NaN here
+    # the zero-norm query has NaN everywhere; only masked entries (+inf by run_test.m:47-53) can be handed out
+    sel = idx[5][idx[5] >= 0]
+    assert (np.abs((q0 + 5) - sel) < mask).all()
