@@ -34,6 +34,11 @@
 //    go in as e2m1 under kind::mxf4 (32 slots per 16-byte unit; block scales all 1.0, parked in the TMEM columns the
 //    N = 240 accumulators leave free), TMEM accumulates exact integers, and the epilogue applies 1/(|q| |h|).
 //
+// Self-match.  When queries and DB are the same n signatures, d is symmetric (the variant set is closed under swapping
+// the two images), so only the (query group of 4, DB tile of 256) work items with tile_start <= group_end are run and
+// the epilogue also stores a value at its transposed position whenever the item owning that position is not run
+// (launch_sc_match_tc_self; TcParams::tri).  Work items are split over the CTA pairs by estimated cost.
+//
 // Roles per CTA (256 threads): warp 0 TMA producer (DB tiles), warp 1 MMA issuer (leader CTA; the
 // warp runs its loop uniformly, one elected lane issues; K loop specialised per operand format),
 // warp 2 TMEM allocator, warp 3 query-operand loader, warps 4-7 epilogue (tcgen05.ld of E and O -> max of E + |O|
