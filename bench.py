@@ -339,7 +339,7 @@ def run_ours(args):
                        if symmetric else "not applicable: the replicated queries are not the rank's DB shard"
                        if world > 1 else "off",
                        "every_pair_computed": general,
-                       "l2": "operands per step (DB 77 MB + queries 328 MB + distances 200 MB) exceed the 126 MB L2",
+                       "l2": "operands per step (DB 89 MB + queries 346 MB + distances 200 MB) exceed the 126 MB L2",
                        "planted_loop_top1_recovered": agree, "e2e_top1_identical": same_e2e},
             "e2e": {"value": pairs_step * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s",
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(N_SCANS * 12),
