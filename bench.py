@@ -215,9 +215,9 @@ def run_ours(args):
             if host_inputs:
                 idx, score = api.sc_scans_to_loops(h_xyz, h_inten, h_off, MASK_WIDTH, P_WEIGHT, ctx=ctx)
                 return torch.from_numpy(idx), torch.from_numpy(score)
-            idx, score = api.sc_scans_to_loops(d_xyz, d_inten, d_off, MASK_WIDTH, P_WEIGHT, ctx=ctx)
+            idx, score = api.sc_scans_to_loops(d_xyz, d_inten, d_off, MASK_WIDTH, P_WEIGHT, ctx=ctx, host_out=True)
             kern_ms.append(ctx.last_kernel_ms)
-            return idx.cpu(), score.cpu()
+            return torch.from_numpy(idx), torch.from_numpy(score)
         # ---- N > 1.  Queries: every rank bins 1/N of the replicated query scans, the signatures are all-gathered
         # over NVLink.  DB: the rank's shard is a resident sodso_db whose operand buffers are rewritten every step.
         qa, qb = rank * N_SCANS // world, (rank + 1) * N_SCANS // world

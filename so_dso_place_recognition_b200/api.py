@@ -427,10 +427,13 @@ def run_test_full(type, hist1, hist2, gt1, gt2, loop_diff, mask_width, p_weight=
     return float(auc.value), float(tr.value), lp_detected
 
 
-def sc_scans_to_loops(xyz, inten, scan_off, mask_width, p_weight=2.0, max_rho=45.0, want_hist=False, ctx=None):
+def sc_scans_to_loops(xyz, inten, scan_off, mask_width, p_weight=2.0, max_rho=45.0, want_hist=False, ctx=None,
+                      host_out=False):
     """test_sc.cpp:36-57 + run_test('sc', hist, hist, ...) (run_test.m:25-57, self-match as in test_kitti.m:28)
     in one call: scans in -> (diff_idx 0-based int32[n], diff_v[n] [, history_sc]).  Host (numpy / pinned torch)
-    point buffers are streamed to the GPU chunk by chunk, overlapped with binning and matching."""
+    point buffers are streamed to the GPU chunk by chunk, overlapped with binning and matching.
+    host_out: return diff_idx / diff_v as numpy arrays even for CUDA inputs (the library copies them out inside the
+    call, one synchronisation instead of one per `.cpu()`)."""
     if _is_torch(xyz) and not xyz.is_cuda:      # pinned host tensors: pass as host pointers
         dev_like = None
     else:
@@ -441,8 +444,9 @@ def sc_scans_to_loops(xyz, inten, scan_off, mask_width, p_weight=2.0, max_rho=45
     n = int(scan_off.shape[0]) - 1
     c = _ctx_for(*( [dev_like] if dev_like is not None else []), ctx=ctx)
     ref = dev_like if dev_like is not None else np.empty(0)
-    idx = _empty_like_kind(ref, (n,), np.int32, "int32")
-    score = _empty_like_kind(ref, (n,), np.float64, "float64")
+    out_ref = np.empty(0) if host_out else ref
+    idx = _empty_like_kind(out_ref, (n,), np.int32, "int32")
+    score = _empty_like_kind(out_ref, (n,), np.float64, "float64")
     hist = _empty_like_kind(ref, (n, 2 * SC_SIZE), np.float64, "float64") if want_hist else None
     N.check(N.lib().sodso_sc_scans_to_loops(c.handle, _ptr(xyz), _ptr(inten), _ptr(scan_off), n, float(max_rho),
                                             int(mask_width), float(p_weight), _ptr(hist), _ptr(idx), _ptr(score),

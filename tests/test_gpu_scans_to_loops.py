@@ -56,6 +56,9 @@ def test_streamed_equals_unstreamed(gpu_ctx, nscan):
     pin = lambda a: torch.from_numpy(a).pin_memory()
     idx_p, score_p = api.sc_scans_to_loops(pin(xyz), pin(inten), pin(off), 100)
     assert np.array_equal(idx_p, idx_s) and np.array_equal(score_p, score_s)
+    # device inputs, results copied out inside the call
+    idx_h, score_h = api.sc_scans_to_loops(d(xyz), d(inten), d(off), 100, host_out=True)
+    assert isinstance(idx_h, np.ndarray) and np.array_equal(idx_h, idx_s) and np.array_equal(score_h, score_s)
 
 
 def test_db_stream_match_equals_reload_match(gpu_ctx):
