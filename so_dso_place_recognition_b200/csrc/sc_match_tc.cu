@@ -656,7 +656,7 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
           const int q0 = qg * QG;
           if (P.tri && (q0 / TILE_M) * TILE_M > (row | (QG - 1))) {
             float *mo = out + (size_t)row * P.ldd + q0;
-            if (q0 + QG <= P.m && (P.ldd & 3) == 0) {
+            if (q0 + QG <= P.m && (reinterpret_cast<uintptr_t>(mo) & 15) == 0) {
               *reinterpret_cast<float4 *>(mo) = make_float4(d[0], d[1], d[2], d[3]);
             } else {
 #pragma unroll

@@ -60,3 +60,26 @@ def test_top1_identical_with_and_without_symmetry(gpu_ctx, monkeypatch):
     monkeypatch.delenv("SODSO_SC_SYMMETRY")
     assert np.array_equal(idx, idx0)
     np.testing.assert_allclose(score, score0, rtol=0, atol=1e-3)
+
+
+def test_self_match_into_misaligned_output(gpu_ctx, oracle):
+    """The transposed values are written with 16-byte stores only where the address allows it: an fp32 output matrix
+    that starts 4 bytes into an allocation (a caller's view) takes the scalar path."""
+    import ctypes as C
+
+    import torch
+
+    from so_dso_place_recognition_b200 import _native as N
+
+    n = 516
+    h = torch.from_numpy(_sigs(n, seed=21)).cuda()
+    buf_p = torch.zeros(n * n + 1, dtype=torch.float32, device="cuda")
+    buf_i = torch.zeros(n * n + 1, dtype=torch.float32, device="cuda")
+    dp, di = buf_p[1:], buf_i[1:]
+    assert dp.data_ptr() % 16 == 4
+    N.check(N.lib().sodso_sc_match_f32(gpu_ctx.handle, C.c_void_p(h.data_ptr()), n, C.c_void_p(h.data_ptr()), n,
+                                       C.c_void_p(dp.data_ptr()), C.c_void_p(di.data_ptr())))
+    torch.cuda.synchronize()
+    rp, ri = oracle.sc_match(h.cpu().numpy(), h.cpu().numpy(), nthreads=16)
+    np.testing.assert_allclose(dp.view(n, n).cpu().numpy(), rp, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(di.view(n, n).cpu().numpy(), ri, rtol=0, atol=1e-5)
