@@ -192,6 +192,11 @@ int sodso_pr_curve(const double *diff_v, const int32_t *diff_idx, const double *
  * SC.cpp:37 / M2DP.cpp:59 in fp64 decides).  Exposed so that tests can check the error bound the guard band rests on. */
 int sodso_debug_fast_turns(sodso_ctx *ctx, const float *num, const float *den, int64_t n, float *out);
 
+/* Test hook (host only, no GPU work): the number of (query group of 4, DB tile of 256, channel) work items the tcgen05
+ * matcher runs for queries [q0, q1) of an n x n SELF-match (q0 a multiple of 256) -- the lower block triangle
+ * tile_start <= group_end of processSC.m:22-33's all-pairs loop; -1 for bad arguments. */
+int64_t sodso_debug_sc_self_items(int64_t n, int64_t q0, int64_t q1);
+
 /* ---- resident, row-sharded signature database ------------------------ */
 /* A shard holds n_local consecutive DB signatures whose first row has global index
  * global_row0; the signatures stay resident in HBM in MMA operand format. */

@@ -66,6 +66,7 @@ _PROTOS = {
     "sodso_gt_loops": (_i, [_vp, _vp, _i, _vp, _i, _d, _i, _vp, _vp, C.POINTER(_i)]),
     "sodso_pr_curve": (_i, [_vp, _vp, _vp, _i, _vp, _i, _d, _i, C.POINTER(_d), C.POINTER(_d), C.POINTER(_i), _vp, _vp, _vp]),
     "sodso_debug_fast_turns": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "sodso_debug_sc_self_items": (_i64, [_i64, _i64, _i64]),
     "sodso_db_create": (_i, [_vp, _i, _vp, _i, _i64, C.POINTER(_vp)]),
     "sodso_db_destroy": (None, [_vp]),
     "sodso_db_reload": (_i, [_vp, _vp]),

@@ -876,6 +876,11 @@ int sodso_pr_curve(const double *diff_v, const int32_t *diff_idx, const double *
 }
 
 // test hook (see include/sodso_pr.h)
+int64_t sodso_debug_sc_self_items(int64_t n, int64_t q0, int64_t q1) {
+  if (n > INT32_MAX || q0 > INT32_MAX || q1 > INT32_MAX) return -1;
+  return (int64_t)sc_tc_self_items((int)n, (int)q0, (int)q1);
+}
+
 int sodso_debug_fast_turns(sodso_ctx *c, const float *num, const float *den, int64_t n, float *out) {
   CTX_CHECK(c);
   if (n < 0 || (n > 0 && (!num || !den || !out))) {

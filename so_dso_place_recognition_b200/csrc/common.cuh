@@ -105,6 +105,7 @@ int sc_tc_query_rows_padded(int m);
 cudaError_t launch_sc_match_tc_block(const void *q_buf, int m, int q0, int q1, const void *db_buf, int n,
                                      int r0, int r1, float *d_p, float *d_i, int ldd, int num_sms,
                                      cudaStream_t st, int64_t *launches);
+long long sc_tc_self_items(int n, int q0, int q1);
 cudaError_t launch_sc_match_tc_self(const void *q_buf, const void *db_buf, int n, int q0, int q1, float *d_p, float *d_i,
                                     int ldd, int num_sms, cudaStream_t st, int64_t *launches);
 cudaError_t launch_sc_match_tc_blocks(const void *q_buf, int m, const void *db_buf, int n, int qa0, int qa1,

@@ -284,6 +284,13 @@ struct TcParams {
 };
 constexpr int TRI_UNITS = 2 * TILE_M / QG;   // 128 units (2 channels x 64 query groups) share a tile count
 
+// items of a triangular region of `units` units (2 channels x query groups) whose first query block has nt0 tiles
+__host__ __device__ __forceinline__ long long tri_prefix(int lb, int nt0);
+__host__ __device__ __forceinline__ long long tri_total_items(int units, int nt0) {
+  const int lb_full = units / TRI_UNITS;
+  return tri_prefix(lb_full, nt0) + (long long)(units - lb_full * TRI_UNITS) * (nt0 + lb_full);
+}
+
 // items before query block lb of a triangular region
 __host__ __device__ __forceinline__ long long tri_prefix(int lb, int nt0) {
   return (long long)TRI_UNITS * ((long long)lb * nt0 + (long long)lb * (lb - 1) / 2);
@@ -752,6 +759,12 @@ cudaError_t launch_sc_match_tc_block(const void *q_buf, int m, int q0, int q1, c
   return launch_sc_match_tc_blocks(q_buf, m, db_buf, n, q0, q1, r0, r1, 0, 0, 0, 0, d_p, d_i, ldd, num_sms, st, launches);
 }
 
+// number of (query group, DB tile, channel) work items launch_sc_match_tc_self runs for queries [q0, q1); -1: bad arguments
+long long sc_tc_self_items(int n, int q0, int q1) {
+  if (n <= 0 || q0 < 0 || q1 > n || q1 <= q0 || q0 % TILE_M) return -1;
+  return tri_total_items(2 * ((q1 - q0 + QG - 1) / QG), q0 / TILE_M + 1);
+}
+
 // self-match of an n x n problem, queries [q0, q1) (q0 a multiple of 256) against the DB rows up to their own block:
 // the part of the lower block triangle that belongs to these queries; the transposed values are stored as well
 cudaError_t launch_sc_match_tc_self(const void *q_buf, const void *db_buf, int n, int q0, int q1, float *d_p, float *d_i,
@@ -820,8 +833,7 @@ cudaError_t launch_sc_match_tc_blocks(const void *q_buf, int m, const void *db_b
   P.tri = tri ? 1 : 0;
   P.tri_nt0 = qa0 / TILE_M + 1;
   if (tri) {
-    const int units = P.n_units[0], lb_full = units / TRI_UNITS;
-    P.w0 = P.w_total = tri_prefix(lb_full, P.tri_nt0) + (long long)(units - lb_full * TRI_UNITS) * (P.tri_nt0 + lb_full);
+    P.w0 = P.w_total = tri_total_items(P.n_units[0], P.tri_nt0);
     P.tile0[0] = 0;
   }
   P.flags = tc_flags();
