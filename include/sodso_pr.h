@@ -14,9 +14,12 @@
  *    buffers through its own pinned/HBM workspaces.  Nothing is ever freed for the caller.
  *  - return value: 0 = ok, negative = error (SODSO_E_*); sodso_last_error() gives the text.
  *  - there is NO CPU fallback: without a usable CUDA device every compute call fails.
- *  - calls on one context are stream-ordered on the context's stream and synchronous
- *    towards the host for host-pointer outputs; a context is not thread-safe, use one
- *    per thread / per GPU.
+ *  - calls on one context are stream-ordered on the context's stream and return after that
+ *    stream has been synchronised (inputs may be reused, outputs are complete, asynchronous
+ *    failures are reported by the call that caused them) -- except the *_sharded calls with
+ *    DEVICE output pointers, which only enqueue (see there).  A context is not thread-safe,
+ *    use one per thread / per GPU.
+ *  - test hooks and the fp32 cross-check kernels are declared in sodso_pr_debug.h, not here.
  */
 #ifndef SODSO_PR_H
 #define SODSO_PR_H
@@ -33,17 +36,13 @@ extern "C" {
 #define SODSO_E_CUDA (-2)    /* CUDA runtime / driver error */
 #define SODSO_E_NODEV (-3)   /* no usable sm_100 device */
 #define SODSO_E_STATE (-4)   /* call sequence error (e.g. topk before match) */
+#define SODSO_E_NCCL (-5)    /* NCCL error, or libnccl.so.2 could not be bound */
 
 #define SODSO_SC_SIZE 1200   /* SC.h:7-8   numS*numR = 60*20 */
 #define SODSO_M2DP_SIZE 192  /* M2DP.cpp:36 numS*numR + numP*numQ = 128 + 64 */
 
 #define SODSO_TYPE_SC 0      /* run_test.m:29 'sc'   */
 #define SODSO_TYPE_M2DP 1    /* run_test.m:27 'm2dp' */
-
-/* match algorithms (sodso_ctx_set_match_algo).  TC is the product path; SIMT is a plain
- * fp32 CUDA-core kernel kept as an on-GPU cross-check for the tensor-core path. */
-#define SODSO_ALGO_TC 0
-#define SODSO_ALGO_SIMT 1
 
 typedef struct sodso_ctx sodso_ctx;
 typedef struct sodso_db sodso_db;
@@ -56,7 +55,15 @@ void sodso_ctx_destroy(sodso_ctx *ctx);
 void *sodso_ctx_stream(sodso_ctx *ctx);
 /* Use an external stream (e.g. torch's current stream); NULL restores the own stream. */
 int sodso_ctx_set_stream(sodso_ctx *ctx, void *cuda_stream);
-int sodso_ctx_set_match_algo(sodso_ctx *ctx, int algo);
+/* Wait for everything enqueued on the context's stream (the *_sharded calls with DEVICE output pointers return
+ * without synchronising). */
+int sodso_ctx_sync(sodso_ctx *ctx);
+/* sodso_sc_scans_to_loops / sodso_db_stream_match / sodso_db_scans_query_sharded stream HOST point buffers in 512-scan
+ * chunks (copy of chunk k+1 overlapped with binning + matching of chunk k) when a call has at least min_scans scans
+ * (default 2048, minimum 512); below that one plain copy precedes the compute.  Use page-locked (cudaHostAlloc /
+ * cudaHostRegister) buffers: from pageable memory every chunk copy blocks the calling thread and runs at a fraction
+ * of the PCIe rate. */
+int sodso_ctx_set_stream_threshold(sodso_ctx *ctx, int min_scans);
 const char *sodso_last_error(void);
 const char *sodso_version(void);
 /* Number of kernels of this library launched on the context so far. */
@@ -187,22 +194,19 @@ int sodso_pr_curve(const double *diff_v, const int32_t *diff_idx, const double *
                    double loop_diff, int n_gt_loops, double *auc, double *top_recall, int *top_count,
                    int32_t *rank_out, double *precision_out, double *recall_out);
 
-/* Test hook, not part of the reference surface: the fp32 angle proposal atan2(num, den)/2pi + 1/2 that the generation
- * kernels use to PROPOSE a polar bin (accepted only outside an error-derived guard band around bin edges, otherwise
- * SC.cpp:37 / M2DP.cpp:59 in fp64 decides).  Exposed so that tests can check the error bound the guard band rests on. */
-int sodso_debug_fast_turns(sodso_ctx *ctx, const float *num, const float *den, int64_t n, float *out);
-
-/* Test hook (host only, no GPU work): the number of (query group of 4, DB tile of 256, channel) work items the tcgen05
- * matcher runs for queries [q0, q1) of an n x n SELF-match (q0 a multiple of 256) -- the lower block triangle
- * tile_start <= group_end of processSC.m:22-33's all-pairs loop; -1 for bad arguments. */
-int64_t sodso_debug_sc_self_items(int64_t n, int64_t q0, int64_t q1);
-
 /* ---- resident, row-sharded signature database ------------------------ */
 /* A shard holds n_local consecutive DB signatures whose first row has global index
- * global_row0; the signatures stay resident in HBM in MMA operand format. */
+ * global_row0; the signatures stay resident in HBM in MMA operand format.  n_local may be 0 (a shard that is
+ * filled by sodso_db_append). */
 int sodso_db_create(sodso_ctx *ctx, int type, const double *hist2, int n_local,
                     int64_t global_row0, sodso_db **out);
 void sodso_db_destroy(sodso_db *db);
+/* Incremental growth (streaming queries against a database that keeps growing, the on-line form of
+ * test_sc.cpp:52-54 appending one history row per scan): n_new further signatures behind the shard's last row (global
+ * indices global_row0 + n_local ...).  Only the new rows' operands are written; when the capacity runs out it doubles
+ * and the operand buffers are re-laid out on the device.  sodso_db_reserve sets the capacity up front. */
+int sodso_db_append(sodso_db *db, const double *hist_new, int n_new);
+int sodso_db_reserve(sodso_db *db, int capacity);
 /* Replace the shard's signatures by n_local new ones (same size, same global_row0): the operand buffers
  * are rewritten in place, nothing is reallocated. */
 int sodso_db_reload(sodso_db *db, const double *hist2);
@@ -215,9 +219,10 @@ int sodso_db_stream_match(sodso_db *db, const double *xyz, const float *inten, c
 int sodso_db_size(sodso_db *db);
 /* Distances of m queries against the shard (kept on the device inside the handle). */
 int sodso_db_match(sodso_db *db, const double *hist1, int m);
-/* Per-query partial row sums over this shard, m x 4 doubles:
- * [sum(d_p-c), sum((d_p-c)^2), sum(d_i-c), sum((d_i-c)^2)] with c = 0.25; NaN propagates.
- * Summed over shards (allreduce) they give the row mean / std of run_test.m:40. */
+/* Per-query partial row statistics over this shard, m x 6 doubles:
+ * [sum(d_p-c), sum((d_p-c)^2), count(d_p), sum(d_i-c), sum((d_i-c)^2), count(d_i)] with c = 0.25, over the non-NaN
+ * entries (MATLAB's normalize omits NaN: the NaN column of a zero-norm DB signature, processSC.m:15-20, does not
+ * poison the row).  Summed over shards (allreduce) they give the row mean / std of run_test.m:40. */
 int sodso_db_partial_stats(sodso_db *db, double *stats);
 /* Fuse with the GLOBAL stats, mask |q_global - j_global| < mask_width, emit the k best
  * (ascending score, lowest global index first on ties) of this shard:
@@ -238,6 +243,50 @@ int sodso_topk_merge_device(sodso_ctx *ctx, const int64_t *idx, const double *sc
                             double *out_score, double *out_d_p, double *out_d_i);
 /* Copy the last sodso_db_match result (fp32, m x n_local each; either may be NULL) out. */
 int sodso_db_get_distances(sodso_db *db, float *d_p, float *d_i);
+
+/* ---- multi-GPU: one rank per GPU, NCCL inside the library --------------------------------------
+ * The reference is single-process; this is the seam a sharded host (C++ or Python, one thread or process per GPU) binds.
+ * Rank 0 calls sodso_comm_unique_id and hands the SODSO_COMM_ID_BYTES bytes to every rank by any means (MPI, a file,
+ * torch.distributed); every rank then calls sodso_comm_init on its own context (ncclCommInitRank: collective, blocks
+ * until all ranks have joined).  libnccl.so.2 is bound at run time; a process that already has NCCL loaded (PyTorch)
+ * shares that copy.  All collectives run on the context's stream. */
+#define SODSO_COMM_ID_BYTES 128
+int sodso_comm_unique_id(void *id_out);
+int sodso_comm_init(sodso_ctx *ctx, const void *unique_id, int nranks, int rank);
+int sodso_comm_finalize(sodso_ctx *ctx);
+int sodso_comm_nranks(sodso_ctx *ctx);
+int sodso_comm_rank(sodso_ctx *ctx);
+int sodso_comm_nccl_version(void);   /* e.g. 22809; 0 if NCCL could not be bound */
+
+/* run_test.m:25-57 for m queries against a database whose rows are sharded over the ranks of the context's
+ * communicator.  COLLECTIVE: every rank calls it with the same queries and parameters and receives the same result,
+ * the k best candidates per query over the WHOLE database (ascending fused score, lowest global index first on ties --
+ * MATLAB's first minimum, run_test.m:57): idx m x k int64 global 0-based (-1 when fewer than k valid), score / d_p /
+ * d_i m x k doubles (d_p / d_i optional).  On the stream, without any host synchronisation in between:
+ * match -> partial row statistics -> ncclAllReduce -> fuse + mask + per-shard top-k -> ncclAllGather -> merge.
+ * DEVICE output pointers: the call returns as soon as the work is enqueued (sodso_ctx_sync, or stream order, before
+ * the results are read; several batches can be in flight).  HOST output pointers: copied out, one synchronisation.
+ * Without a communicator (or nranks == 1) the same path runs on the one shard, without collectives.
+ * q_global_row0: global index of query 0 for the temporal mask |q - j| < mask_width (run_test.m:47-53). */
+int sodso_db_query_sharded(sodso_db *db, const double *hist1, int m, int64_t q_global_row0, int mask_width,
+                           double p_weight, int k, int64_t *idx, double *score, double *d_p, double *d_i);
+/* The statistics / top-k / exchange / merge part alone, for the last match of the handle (sodso_db_match,
+ * sodso_db_stream_match). */
+int sodso_db_finish_sharded(sodso_db *db, int64_t q_global_row0, int mask_width, double p_weight, int k, int64_t *idx,
+                            double *score, double *d_p, double *d_i);
+/* One step of the sharded pipeline from POINTS (test_sc.cpp:36-57 + run_test.m:25-57), COLLECTIVE:
+ *  - queries: this rank bins scans [q_first, q_first + m_slice) of the m_total queries (q_xyz / q_inten / q_off describe
+ *    the slice only).  m_slice == m_total: every rank bins all queries, nothing is exchanged.  Otherwise the slices must
+ *    be the contiguous block partition of m_total over the ranks (rank r: base = m_total / R rows, the first
+ *    m_total % R ranks one more) and the signatures (19 KB per scan instead of 115 KB of points) are exchanged by NCCL;
+ *  - shard: db_xyz / db_inten / db_off non-NULL: the shard's n_local scans are binned and its operand is rewritten in
+ *    place, streamed chunk-wise from HOST buffers as in sodso_db_stream_match; NULL: the resident operand is used;
+ *  - then as sodso_db_query_sharded.  q_hist (optional, m_total x 2400): the query signatures. */
+int sodso_db_scans_query_sharded(sodso_db *db, const double *db_xyz, const float *db_inten, const int64_t *db_off,
+                                 const double *q_xyz, const float *q_inten, const int64_t *q_off, int m_total,
+                                 int q_first, int m_slice, double max_rho, int64_t q_global_row0, int mask_width,
+                                 double p_weight, int k, double *q_hist, int64_t *idx, double *score, double *d_p,
+                                 double *d_i);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,8 @@ import ctypes as C
 import os
 import subprocess
 
+import warnings
+
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -260,10 +262,13 @@ def sc_match_numpy(hist1, hist2):
 
 
 def fuse_top1_numpy(d_p, d_i, mask_width, p_weight=2.0):
-    def z(x):
-        return (x - x.mean(axis=1, keepdims=True)) / x.std(axis=1, ddof=1, keepdims=True)
+    def z(x):   # MATLAB normalize(x, 2): z-score per row, mean / std (N-1) with 'omitnan'
+        with np.errstate(invalid="ignore", divide="ignore"), warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            return (x - np.nanmean(x, axis=1, keepdims=True)) / np.nanstd(x, axis=1, ddof=1, keepdims=True)
 
     f = p_weight * z(d_p) + z(d_i)
+    f = np.where(np.isnan(f), np.inf, f)          # min skips NaN (run_test.m:57); an all-NaN row -> index 0
     m, n = f.shape
     ii = np.arange(m)[:, None]
     jj = np.arange(n)[None, :]

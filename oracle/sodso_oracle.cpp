@@ -493,8 +493,10 @@ void orc_m2dp_match(const double* hist1, int m, const double* hist2, int n, doub
   }
 }
 
-// run_test.m:38-57.  fused = p_weight*zscore_row(d_p) + zscore_row(d_i) (std with N-1,
-// over the UNMASKED row), then |i-j| < mask_width -> Inf, then first-index argmin.
+// run_test.m:38-57.  fused = p_weight*zscore_row(d_p) + zscore_row(d_i), then |i-j| < mask_width -> Inf, then
+// first-index argmin.  normalize(A, 2) (run_test.m:40) is MATLAB's z-score: mean and std (N-1) of each row over
+// the UNMASKED row, both computed with 'omitnan' -- NaN entries (the column of a zero-norm DB signature,
+// processSC.m:15-20) are left out of the statistics and stay NaN in the result, where min (run_test.m:57) skips them.
 // idx is 0-based (MATLAB's is 1-based).  fused_out optional (m x n, after masking).
 void orc_fuse_top1(const double* d_p, const double* d_i, int m, int n, int mask_width,
                    double p_weight, int* idx, double* score, double* fused_out) {
@@ -504,14 +506,16 @@ void orc_fuse_top1(const double* d_p, const double* d_i, int m, int n, int mask_
     double mu[2], sd[2];
     for (int c = 0; c < 2; c++) {
       double s = 0;
-      for (int j = 0; j < n; j++) s += chans[c][j];
-      mu[c] = s / n;
+      int cnt = 0;
+      for (int j = 0; j < n; j++)
+        if (chans[c][j] == chans[c][j]) { s += chans[c][j]; cnt++; }
+      mu[c] = s / cnt;
       double v = 0;
       for (int j = 0; j < n; j++) {
         double d = chans[c][j] - mu[c];
-        v += d * d;
+        if (d == d) v += d * d;
       }
-      sd[c] = std::sqrt(v / (n - 1));
+      sd[c] = std::sqrt(v / (cnt - 1));
     }
     for (int j = 0; j < n; j++)
       row[j] = p_weight * ((chans[0][j] - mu[0]) / sd[0]) + (chans[1][j] - mu[1]) / sd[1];

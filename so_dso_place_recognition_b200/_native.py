@@ -12,11 +12,14 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsodso_pr.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "sodso_pr.h")
+DEBUG_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "sodso_pr_debug.h")
 
 SODSO_TYPE_SC = 0
 SODSO_TYPE_M2DP = 1
-SODSO_ALGO_TC = 0
+SODSO_ALGO_TC = 0      # include/sodso_pr_debug.h
 SODSO_ALGO_SIMT = 1
+STATS_W = 6            # sodso_db_partial_stats row width
+COMM_ID_BYTES = 128
 SC_SIZE = 1200
 M2DP_SIZE = 192
 
@@ -32,7 +35,8 @@ _PROTOS = {
     "sodso_ctx_destroy": (None, [_vp]),
     "sodso_ctx_stream": (_vp, [_vp]),
     "sodso_ctx_set_stream": (_i, [_vp, _vp]),
-    "sodso_ctx_set_match_algo": (_i, [_vp, _i]),
+    "sodso_ctx_sync": (_i, [_vp]),
+    "sodso_ctx_set_stream_threshold": (_i, [_vp, _i]),
     "sodso_last_error": (C.c_char_p, []),
     "sodso_version": (C.c_char_p, []),
     "sodso_ctx_launch_count": (_i64, [_vp]),
@@ -65,10 +69,10 @@ _PROTOS = {
     "sodso_top1_single": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "sodso_gt_loops": (_i, [_vp, _vp, _i, _vp, _i, _d, _i, _vp, _vp, C.POINTER(_i)]),
     "sodso_pr_curve": (_i, [_vp, _vp, _vp, _i, _vp, _i, _d, _i, C.POINTER(_d), C.POINTER(_d), C.POINTER(_i), _vp, _vp, _vp]),
-    "sodso_debug_fast_turns": (_i, [_vp, _vp, _vp, _i64, _vp]),
-    "sodso_debug_sc_self_items": (_i64, [_i64, _i64, _i64]),
     "sodso_db_create": (_i, [_vp, _i, _vp, _i, _i64, C.POINTER(_vp)]),
     "sodso_db_destroy": (None, [_vp]),
+    "sodso_db_append": (_i, [_vp, _vp, _i]),
+    "sodso_db_reserve": (_i, [_vp, _i]),
     "sodso_db_reload": (_i, [_vp, _vp]),
     "sodso_db_stream_match": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _i]),
     "sodso_db_size": (_i, [_vp]),
@@ -78,11 +82,34 @@ _PROTOS = {
     "sodso_topk_merge": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sodso_topk_merge_device": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sodso_db_get_distances": (_i, [_vp, _vp, _vp]),
+    "sodso_comm_unique_id": (_i, [_vp]),
+    "sodso_comm_init": (_i, [_vp, _vp, _i, _i]),
+    "sodso_comm_finalize": (_i, [_vp]),
+    "sodso_comm_nranks": (_i, [_vp]),
+    "sodso_comm_rank": (_i, [_vp]),
+    "sodso_comm_nccl_version": (_i, []),
+    "sodso_db_query_sharded": (_i, [_vp, _vp, _i, _i64, _i, _d, _i, _vp, _vp, _vp, _vp]),
+    "sodso_db_finish_sharded": (_i, [_vp, _i64, _i, _d, _i, _vp, _vp, _vp, _vp]),
+    "sodso_db_scans_query_sharded": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _i64, _i, _d, _i, _vp, _vp,
+                                          _vp, _vp, _vp]),
+}
+
+# include/sodso_pr_debug.h: test hooks (cross-check kernels, kernel variant switches)
+_DEBUG_PROTOS = {
+    "sodso_debug_set_match_algo": (_i, [_vp, _i]),
+    "sodso_debug_set_sc_symmetry": (_i, [_vp, _i]),
+    "sodso_debug_set_kernel_flags": (_i, [_i, _i, _i]),
+    "sodso_debug_fast_turns": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "sodso_debug_sc_self_items": (_i64, [_i64, _i64, _i64]),
 }
 
 
 def exported_names():
     return sorted(_PROTOS)
+
+
+def debug_names():
+    return sorted(_DEBUG_PROTOS)
 
 
 def lib():
@@ -94,7 +121,7 @@ def lib():
                 f"{LIB_PATH} is missing: build it with `make -C so_dso_place_recognition_b200/csrc` "
                 "(or __graft_entry__.build()); there is no CPU fallback")
         L = C.CDLL(LIB_PATH)
-        for name, (res, args) in _PROTOS.items():
+        for name, (res, args) in {**_PROTOS, **_DEBUG_PROTOS}.items():
             f = getattr(L, name)
             f.restype = res
             f.argtypes = args

@@ -82,7 +82,41 @@ class Context:
         return self._h
 
     def set_match_algo(self, algo: int):
-        N.check(N.lib().sodso_ctx_set_match_algo(self._h, int(algo)))
+        """test hook (include/sodso_pr_debug.h): SODSO_ALGO_SIMT selects the fp32 cross-check kernels"""
+        N.check(N.lib().sodso_debug_set_match_algo(self._h, int(algo)))
+
+    def set_sc_symmetry(self, on: bool):
+        """test hook (include/sodso_pr_debug.h): off = a self-match computes every pair like distinct operands"""
+        N.check(N.lib().sodso_debug_set_sc_symmetry(self._h, 1 if on else 0))
+
+    def set_stream_threshold(self, min_scans: int):
+        N.check(N.lib().sodso_ctx_set_stream_threshold(self._h, int(min_scans)))
+
+    def sync(self):
+        N.check(N.lib().sodso_ctx_sync(self._h))
+
+    # ---- multi-GPU: NCCL communicator inside the library (include/sodso_pr.h, sodso_comm_*) ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(N.COMM_ID_BYTES)
+        N.check(N.lib().sodso_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes | None, nranks: int, rank: int):
+        """collective: every rank calls it with rank 0's id (sodso_comm_init -> ncclCommInitRank)"""
+        buf = C.create_string_buffer(unique_id, N.COMM_ID_BYTES) if unique_id else None
+        N.check(N.lib().sodso_comm_init(self._h, buf, int(nranks), int(rank)))
+
+    def comm_finalize(self):
+        N.check(N.lib().sodso_comm_finalize(self._h))
+
+    @property
+    def comm_nranks(self) -> int:
+        return int(N.lib().sodso_comm_nranks(self._h))
+
+    @property
+    def comm_rank(self) -> int:
+        return int(N.lib().sodso_comm_rank(self._h))
 
     def set_stream(self, cuda_stream_ptr):
         N.check(N.lib().sodso_ctx_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
@@ -463,6 +497,8 @@ class SignatureDB:
     def __init__(self, type, hist2, global_row0=0, ctx=None):
         self.type = {"sc": SODSO_TYPE_SC, "m2dp": SODSO_TYPE_M2DP}[type]
         rows = 1 if self.type == SODSO_TYPE_SC else 4
+        if hist2 is None:     # an empty shard, to be filled by append()
+            hist2 = np.empty((0, 2 * (SC_SIZE if self.type == SODSO_TYPE_SC else M2DP_SIZE)))
         hist2 = _prep(hist2, np.float64, "float64")
         self.n = hist2.shape[0] // rows
         self.row0 = int(global_row0)
@@ -482,6 +518,75 @@ class SignatureDB:
             self.close()
         except Exception:
             pass
+
+    def append(self, hist_new):
+        """sodso_db_append: further signatures behind the shard's last row (only their operand rows are written)"""
+        hist_new = _prep(hist_new, np.float64, "float64")
+        k = hist_new.shape[0] // self._rows
+        _ctx_for(hist_new, ctx=self.ctx)
+        N.check(N.lib().sodso_db_append(self._h, _ptr(hist_new), k))
+        self.n += k
+
+    def reserve(self, capacity: int):
+        N.check(N.lib().sodso_db_reserve(self._h, int(capacity)))
+
+    def query_sharded(self, hist1, q_global_row0=0, mask_width=100, p_weight=2.0, k=8, out=None):
+        """sodso_db_query_sharded (collective over the context's communicator): -> (idx int64 [m,k] global 0-based,
+        score, d_p, d_i).  numpy queries -> numpy results (one synchronisation); torch CUDA queries -> torch CUDA
+        results, only enqueued (ctx.sync() or stream order before reading).  out: preallocated result tuple."""
+        hist1 = _prep(hist1, np.float64, "float64")
+        _ctx_for(hist1, ctx=self.ctx)
+        self.m = hist1.shape[0] // self._rows
+        self._ref = hist1
+        if out is None:
+            out = (_empty_like_kind(hist1, (self.m, k), np.int64, "int64"),) + tuple(
+                _empty_like_kind(hist1, (self.m, k), np.float64, "float64") for _ in range(3))
+        idx, score, dp, di = out
+        N.check(N.lib().sodso_db_query_sharded(self._h, _ptr(hist1), self.m, int(q_global_row0), int(mask_width),
+                                               float(p_weight), int(k), _ptr(idx), _ptr(score), _ptr(dp), _ptr(di)))
+        return out
+
+    def finish_sharded(self, q_global_row0=0, mask_width=100, p_weight=2.0, k=8, like=None):
+        """sodso_db_finish_sharded for the last match / stream_match"""
+        ref = like if like is not None else np.empty(0)
+        idx = _empty_like_kind(ref, (self.m, k), np.int64, "int64")
+        score, dp, di = (_empty_like_kind(ref, (self.m, k), np.float64, "float64") for _ in range(3))
+        N.check(N.lib().sodso_db_finish_sharded(self._h, int(q_global_row0), int(mask_width), float(p_weight), int(k),
+                                                _ptr(idx), _ptr(score), _ptr(dp), _ptr(di)))
+        return idx, score, dp, di
+
+    def scans_query_sharded(self, q_xyz, q_inten, q_off, m_total, q_first=0, db_scans=None, q_global_row0=0,
+                            mask_width=100, p_weight=2.0, k=8, max_rho=45.0, want_hist=False, host_out=True):
+        """sodso_db_scans_query_sharded: one step of the sharded pipeline from points (collective).
+        q_*: this rank's slice [q_first, q_first + m_slice) of the m_total query scans (all of them: no exchange);
+        db_scans: None (resident operand) or (xyz, inten, off) of the shard's scans (rebuilt in place, streamed from
+        host buffers).  -> (idx, score, d_p, d_i [, q_hist])"""
+        q_xyz = _prep(q_xyz, np.float64, "float64")
+        q_inten = _prep(q_inten, np.float32, "float32")
+        q_off = _prep(q_off, np.int64, "int64")
+        m_slice = int(q_off.shape[0]) - 1
+        dev_like = q_xyz if (_is_torch(q_xyz) and q_xyz.is_cuda) else None
+        dx = di_ = do = None
+        if db_scans is not None:
+            dx, di_, do = (_prep(db_scans[0], np.float64, "float64"), _prep(db_scans[1], np.float32, "float32"),
+                           _prep(db_scans[2], np.int64, "int64"))
+            assert do.shape[0] - 1 == self.n
+            if dev_like is None and _is_torch(dx) and dx.is_cuda:
+                dev_like = dx
+        _ctx_for(*([dev_like] if dev_like is not None else []), ctx=self.ctx)
+        self.m = int(m_total)
+        ref = np.empty(0) if (host_out or dev_like is None) else dev_like
+        idx = _empty_like_kind(ref, (self.m, k), np.int64, "int64")
+        score, dp, di = (_empty_like_kind(ref, (self.m, k), np.float64, "float64") for _ in range(3))
+        hist = None
+        if want_hist:
+            hist = _empty_like_kind(dev_like if dev_like is not None else np.empty(0), (self.m, 2 * SC_SIZE), np.float64,
+                                    "float64")
+        N.check(N.lib().sodso_db_scans_query_sharded(
+            self._h, _ptr(dx), _ptr(di_), _ptr(do), _ptr(q_xyz), _ptr(q_inten), _ptr(q_off), self.m, int(q_first),
+            m_slice, float(max_rho), int(q_global_row0), int(mask_width), float(p_weight), int(k), _ptr(hist), _ptr(idx),
+            _ptr(score), _ptr(dp), _ptr(di)))
+        return (idx, score, dp, di, hist) if want_hist else (idx, score, dp, di)
 
     def reload(self, hist2):
         """new signatures for the same shard (same number of rows), operand buffers rewritten in place"""
@@ -513,7 +618,7 @@ class SignatureDB:
 
     def partial_stats(self, like=None):
         ref = like if like is not None else self._ref
-        st = _empty_like_kind(ref, (self.m, 4), np.float64, "float64")
+        st = _empty_like_kind(ref, (self.m, N.STATS_W), np.float64, "float64")
         N.check(N.lib().sodso_db_partial_stats(self._h, _ptr(st)))
         return st
 

@@ -7,78 +7,18 @@
 #include <string>
 #include <vector>
 
-#include "../../include/sodso_pr.h"
-#include "common.cuh"
+#include "capi_internal.cuh"
 
 namespace sodso {
 
 static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
-
-struct Buf {
-  void *p = nullptr;
-  size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-  template <class T>
-  T *as() const { return reinterpret_cast<T *>(p); }
-};
-
-static bool is_device_ptr(const void *p) {
-  if (!p) return false;
-  cudaPointerAttributes a;
-  cudaError_t e = cudaPointerGetAttributes(&a, p);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
-}
+const char *last_error_cstr() { return g_err.c_str(); }
+DebugFlags g_debug;
 
 }  // namespace sodso
 
 using namespace sodso;
-
-struct sodso_ctx {
-  int device = 0;
-  int num_sms = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  cudaStream_t copy_stream = nullptr;  // host -> HBM chunk copies of the streamed path
-  int algo = SODSO_ALGO_TC;
-  int64_t launches = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool ev_valid = false;
-  std::string kname;
-  // workspaces
-  Buf in_xyz, in_inten, in_off, out_hist, out_xyz, out_evec;
-  Buf h1, h2, q_op, db_op, dp32, di32, dp64, di64;
-  Buf stats, idx64, idx32, score, dpat, diat, gen_ws, m2dp_ws;
-};
-
-struct sodso_db {
-  sodso_ctx *ctx = nullptr;
-  int type = 0;
-  int n = 0;
-  int64_t row0 = 0;
-  Buf op;        // SC: MMA operand (TC) or normalised K-major fp32 (SIMT); M2DP: raw fp64 rows
-  int op_algo = 0;
-  Buf q_in, q_op, dp, di, stats, gstats, idx, score, dpat, diat, ws;
-  int m = 0;     // rows of the last match
-  bool matched = false;
-};
 
 struct sodso_staged {
   sodso_ctx *ctx = nullptr;
@@ -87,55 +27,7 @@ struct sodso_staged {
   Buf d_off, d_xyz, d_inten;
 };
 
-namespace {
-
-#define CTX_CHECK(ctx)                                   \
-  if (!(ctx)) {                                          \
-    set_error("null context");                           \
-    return SODSO_E_ARG;                                  \
-  }                                                      \
-  SODSO_CUDA_CHECK(cudaSetDevice((ctx)->device))
-
-// host-or-device input -> device pointer (copies through `ws` if host)
-template <class T>
-int stage_in(sodso_ctx *c, const T *src, size_t count, Buf &ws, const T **out) {
-  if (count == 0 || is_device_ptr(src)) {
-    *out = src;
-    return SODSO_OK;
-  }
-  SODSO_CUDA_CHECK(ws.reserve(count * sizeof(T)));
-  SODSO_CUDA_CHECK(cudaMemcpyAsync(ws.p, src, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
-  *out = ws.as<T>();
-  return SODSO_OK;
-}
-
-// host-or-device output -> device pointer to write to
-template <class T>
-int stage_out(sodso_ctx *c, T *dst, size_t count, Buf &ws, T **out) {
-  if (!dst) {
-    *out = nullptr;
-    return SODSO_OK;
-  }
-  if (is_device_ptr(dst)) {
-    *out = dst;
-    return SODSO_OK;
-  }
-  SODSO_CUDA_CHECK(ws.reserve(count * sizeof(T) + 16));
-  *out = ws.as<T>();
-  return SODSO_OK;
-}
-
-template <class T>
-int finish_out(sodso_ctx *c, T *dst, size_t count, const T *dev) {
-  if (!dst || dst == dev) return SODSO_OK;
-  SODSO_CUDA_CHECK(cudaMemcpyAsync(dst, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
-  return SODSO_OK;
-}
-
-int sync_ctx(sodso_ctx *c) {
-  SODSO_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  return SODSO_OK;
-}
+namespace sodso {
 
 struct TimedRegion {
   sodso_ctx *c;
@@ -189,25 +81,21 @@ int sc_prepare(sodso_ctx *c, int algo, const double *hist_dev, int rows, Buf &op
 }
 
 // A self-match (hist1 and hist2 are the same n rows) has a symmetric distance matrix: the tcgen05 matcher then computes
-// the lower block triangle only and stores every value at its transposed position as well.  SODSO_SC_SYMMETRY=0
-// switches this off (every pair computed, as for distinct operands).
-static bool sc_symmetry_enabled() {
-  const char *e = getenv("SODSO_SC_SYMMETRY");   // read per call: tests toggle it
-  return !(e && atoi(e) == 0);
-}
+// the lower block triangle only and stores every value at its transposed position as well.  The test hook
+// sodso_debug_set_sc_symmetry (include/sodso_pr_debug.h) switches this off (every pair computed, as for distinct operands).
 
 int sc_match_core(sodso_ctx *c, int algo, const Buf &q_op, int m, const Buf &db_op, int n, float *dp,
-                  float *di, int ldd, bool self = false) {
+                  float *di, int ldd, bool self = false, int n_layout = 0) {
   TimedRegion tr(c, algo == SODSO_ALGO_SIMT ? "sc_match_simt_kernel" : "sc_match_tc_kernel");
   if (algo == SODSO_ALGO_SIMT) {
     int ldq = (m + 31) & ~31, ldh = (n + 31) & ~31;
     SODSO_CUDA_CHECK(launch_sc_match_simt(q_op.as<float>(), m, ldq, db_op.as<float>(), n, ldh, dp, di,
                                           ldd, c->stream, &c->launches));
-  } else if (self && m == n && sc_symmetry_enabled()) {
+  } else if (self && m == n && c->sc_symmetry) {
     SODSO_CUDA_CHECK(launch_sc_match_tc_self(q_op.p, db_op.p, n, 0, n, dp, di, ldd, c->num_sms, c->stream, &c->launches));
   } else {
     SODSO_CUDA_CHECK(launch_sc_match_tc(q_op.p, m, db_op.p, n, dp, di, ldd, c->num_sms, c->stream,
-                                        &c->launches));
+                                        &c->launches, n_layout));
   }
   return SODSO_OK;
 }
@@ -299,7 +187,7 @@ int generate_common(sodso_ctx *c, const double *xyz, const float *inten, const i
   return SODSO_OK;
 }
 
-}  // namespace
+}  // namespace sodso
 
 extern "C" {
 
@@ -349,6 +237,7 @@ void sodso_ctx_destroy(sodso_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  comm_release(c);
   for (Buf *b : {&c->in_xyz, &c->in_inten, &c->in_off, &c->out_hist, &c->out_xyz, &c->out_evec, &c->h1,
                  &c->h2, &c->q_op, &c->db_op, &c->dp32, &c->di32, &c->dp64, &c->di64, &c->stats,
                  &c->idx64, &c->idx32, &c->score, &c->dpat, &c->diat, &c->gen_ws, &c->m2dp_ws})
@@ -368,12 +257,40 @@ int sodso_ctx_set_stream(sodso_ctx *c, void *s) {
   return SODSO_OK;
 }
 
-int sodso_ctx_set_match_algo(sodso_ctx *c, int algo) {
+int sodso_ctx_sync(sodso_ctx *c) {
+  CTX_CHECK(c);
+  return sync_ctx(c);
+}
+
+int sodso_ctx_set_stream_threshold(sodso_ctx *c, int min_scans) {
+  if (!c || min_scans < 0) {
+    set_error("bad stream threshold");
+    return SODSO_E_ARG;
+  }
+  c->stream_min_scans = std::max(min_scans, 512);
+  return SODSO_OK;
+}
+
+// ---- include/sodso_pr_debug.h: test hooks, not part of the reference surface ----
+int sodso_debug_set_match_algo(sodso_ctx *c, int algo) {
   if (!c || (algo != SODSO_ALGO_TC && algo != SODSO_ALGO_SIMT)) {
     set_error("bad algo");
     return SODSO_E_ARG;
   }
   c->algo = algo;
+  return SODSO_OK;
+}
+
+int sodso_debug_set_sc_symmetry(sodso_ctx *c, int on) {
+  if (!c) return SODSO_E_ARG;
+  c->sc_symmetry = on != 0;
+  return SODSO_OK;
+}
+
+int sodso_debug_set_kernel_flags(int tc_flags, int gen_flags, int gen_ctas) {
+  g_debug.tc_flags = tc_flags;
+  g_debug.gen_flags = gen_flags < 0 ? 2 : gen_flags;
+  g_debug.gen_ctas = gen_ctas;
   return SODSO_OK;
 }
 
@@ -546,7 +463,7 @@ int sodso_loop_top1(sodso_ctx *c, int type, const double *hist1, int m, const do
 static int fuse_top1_tail(sodso_ctx *c, int m, int n, int mask_width, double p_weight, int32_t *idx,
                           double *score, double *d_p_at, double *d_i_at) {
   int rc;
-  SODSO_CUDA_CHECK(c->stats.reserve((size_t)m * 4 * sizeof(double)));
+  SODSO_CUDA_CHECK(c->stats.reserve((size_t)m * STATS_W * sizeof(double)));
   SODSO_CUDA_CHECK(launch_row_stats(c->dp32.as<float>(), c->di32.as<float>(), m, n, n, c->stats.as<double>(),
                                     c->stream, &c->launches));
   SODSO_CUDA_CHECK(c->idx64.reserve((size_t)m * sizeof(int64_t)));
@@ -593,12 +510,8 @@ int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten,
   // scans are streamed in chunks (a multiple of the 256-row DB tile) when the points live in host memory
   // chunk boundaries (multiples of the 256-row DB tile): two 256-scan chunks first so that matching starts early --
   // the work that can be done grows with the square of what has arrived -- then 512-scan chunks
-  static const int CH = [] {
-    const char *e = getenv("SODSO_STREAM_CHUNK");
-    const int v = e ? atoi(e) : 512;
-    return v >= 256 && v % 256 == 0 ? v : 512;
-  }();
-  const bool streamed = host_pts && host_int && host_off && nscan >= 2048;
+  const int CH = 512;
+  const bool streamed = host_pts && host_int && host_off && nscan >= c->stream_min_scans;
   std::vector<int> bounds{0};
   if (streamed) {
     for (int b = 256; b < nscan; b += b < 512 ? 256 : CH) bounds.push_back(b);
@@ -635,29 +548,42 @@ int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten,
   SODSO_CUDA_CHECK(launch_sc_tc_clear_flags(c->q_op.p, c->stream));
   float *dp = c->dp32.as<float>(), *di = c->di32.as<float>();
 
-  std::vector<cudaEvent_t> evs;
+  // events of the chunk copies: destroyed on every exit path
+  struct Events {
+    std::vector<cudaEvent_t> v;
+    ~Events() {
+      for (cudaEvent_t e : v)
+        if (e) cudaEventDestroy(e);
+    }
+  } evs;
+  auto enqueue_copy = [&](int k) -> cudaError_t {   // chunk k of the host buffers -> HBM, on the copy stream
+    const int s0 = bounds[k], s1 = bounds[k + 1];
+    const int64_t p0 = off[s0], p1 = off[s1];
+    cudaError_t e = cudaSuccess;
+    if (p1 > p0) {
+      e = cudaMemcpyAsync(c->in_xyz.as<double>() + 3 * p0, xyz + 3 * p0, (size_t)(p1 - p0) * 3 * sizeof(double),
+                          cudaMemcpyHostToDevice, c->copy_stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(c->in_inten.as<float>() + p0, inten + p0, (size_t)(p1 - p0) * sizeof(float),
+                            cudaMemcpyHostToDevice, c->copy_stream);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&evs.v[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(evs.v[k], c->copy_stream);
+    return e;
+  };
   if (streamed) {
     if (!c->copy_stream) SODSO_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    evs.resize(nchunk, nullptr);
+    evs.v.assign(nchunk, nullptr);
     // the staging buffers may still be read by earlier work on the compute stream
     cudaEvent_t e0;
     SODSO_CUDA_CHECK(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
-    SODSO_CUDA_CHECK(cudaEventRecord(e0, c->stream));
-    SODSO_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, e0, 0));
+    cudaError_t e = cudaEventRecord(e0, c->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, e0, 0);
     cudaEventDestroy(e0);
-    for (int k = 0; k < nchunk; k++) {
-      const int s0 = bounds[k], s1 = bounds[k + 1];
-      const int64_t p0 = off[s0], p1 = off[s1];
-      if (p1 > p0) {
-        SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_xyz.as<double>() + 3 * p0, xyz + 3 * p0,
-                                         (size_t)(p1 - p0) * 3 * sizeof(double), cudaMemcpyHostToDevice,
-                                         c->copy_stream));
-        SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_inten.as<float>() + p0, inten + p0, (size_t)(p1 - p0) * sizeof(float),
-                                         cudaMemcpyHostToDevice, c->copy_stream));
-      }
-      SODSO_CUDA_CHECK(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
-      SODSO_CUDA_CHECK(cudaEventRecord(evs[k], c->copy_stream));
-    }
+    SODSO_CUDA_CHECK(e);
+    // copies are enqueued one chunk ahead of the compute below: with pageable host memory cudaMemcpyAsync returns only
+    // once the chunk has been staged, and the previous chunk's kernels are already in the queue by then
+    SODSO_CUDA_CHECK(enqueue_copy(0));
   } else {
     if (host_pts)
       SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_xyz.p, xyz, (size_t)total * 3 * sizeof(double), cudaMemcpyHostToDevice,
@@ -675,7 +601,8 @@ int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten,
     const int s0 = bounds[k], s1 = bounds[k + 1];
     const bool last = k == nchunk - 1;
     cudaError_t e = cudaSuccess;
-    if (streamed) e = cudaStreamWaitEvent(c->stream, evs[k], 0);
+    if (streamed && !last) e = enqueue_copy(k + 1);
+    if (streamed && e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, evs.v[k], 0);
     // test_sc.cpp:40-57 for the scans of this chunk
     if (e == cudaSuccess)
       e = launch_sc_generate(xd, id, od + s0, s1 - s0, max_rho, hd + (size_t)s0 * 2 * SC_SIZE, c->num_sms, c->stream,
@@ -689,7 +616,7 @@ int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten,
     // old queries x new DB rows
     if (!streamed && e == cudaSuccess) c->ev_valid = cudaEventRecord(c->ev0, c->stream) == cudaSuccess;
     if (e == cudaSuccess) {
-      if (sc_symmetry_enabled())   // self-match: the new queries against the DB rows up to their own block, transposes stored
+      if (c->sc_symmetry)   // self-match: the new queries against the DB rows up to their own block, transposes stored
         e = launch_sc_match_tc_self(c->q_op.p, c->db_op.p, nscan, s0, s1, dp, di, nscan, c->num_sms, c->stream,
                                     &c->launches);
       else                         // one launch for the L-shaped region
@@ -702,10 +629,9 @@ int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten,
       rc = SODSO_E_CUDA;
     }
   }
-  for (cudaEvent_t ev : evs)
-    if (ev) cudaEventDestroy(ev);
   if (rc) {
     cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     return rc;
   }
   if (hist && hist != hd && (rc = finish_out(c, hist, hcnt, hd))) return rc;
@@ -1062,10 +988,42 @@ int sodso_staged_copy(sodso_staged *S, int32_t *ids, int64_t *scan_off, double *
 }
 
 // ---- resident row-sharded database ---------------------------------------------------------
+// (re)builds the operand of rows [row0, row0 + rows) of a shard laid out for db->cap rows from `rows` signatures on
+// the device; row0 == 0 also clears the binary-channel flags
+static int db_write_rows(sodso_db *db, const double *hist_dev, int row0, int rows, bool pad_tail) {
+  sodso_ctx *c = db->ctx;
+  const size_t w = db->type == SODSO_TYPE_SC ? 2 * SC_SIZE : 2 * M2DP_SIG;
+  if (db->type == SODSO_TYPE_M2DP) {
+    SODSO_CUDA_CHECK(cudaMemcpyAsync(db->op.as<double>() + (size_t)4 * row0 * w, hist_dev, (size_t)4 * rows * w * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, c->stream));
+    return SODSO_OK;
+  }
+  if (db->op_algo == SODSO_ALGO_SIMT) {   // cross-check kernels: whole-operand rebuild only
+    if (row0 != 0) {
+      set_error("the fp32 cross-check database cannot grow");
+      return SODSO_E_STATE;
+    }
+    return sc_prepare(c, db->op_algo, hist_dev, rows, db->op, true);
+  }
+  if (row0 == 0) SODSO_CUDA_CHECK(launch_sc_tc_clear_flags(db->op.p, c->stream));
+  const int n_valid = row0 + rows;
+  const int row1 = pad_tail ? sc_tc_db_rows_padded(db->cap) : n_valid;
+  // the kernel indexes hist by absolute row: hand it the virtual base of row 0 (only rows >= row0 are read)
+  SODSO_CUDA_CHECK(launch_sc_tc_prep_db_rows(hist_dev - (size_t)row0 * w, n_valid, row0, row1, db->op.p, c->stream,
+                                             &c->launches, db->cap));
+  return SODSO_OK;
+}
+
+static size_t db_op_bytes(const sodso_db *db, int cap) {
+  if (db->type == SODSO_TYPE_M2DP) return (size_t)4 * cap * 2 * M2DP_SIG * sizeof(double);
+  if (db->op_algo == SODSO_ALGO_SIMT) return (size_t)2 * SC_SIZE * ((cap + 31) & ~31) * sizeof(float);
+  return sc_tc_db_bytes(cap);
+}
+
 int sodso_db_create(sodso_ctx *c, int type, const double *hist2, int n_local, int64_t global_row0,
                     sodso_db **out) {
   CTX_CHECK(c);
-  if (!out || (type != SODSO_TYPE_SC && type != SODSO_TYPE_M2DP) || n_local <= 0 || !hist2) {
+  if (!out || (type != SODSO_TYPE_SC && type != SODSO_TYPE_M2DP) || n_local < 0 || (n_local > 0 && !hist2)) {
     set_error("bad db_create arguments");
     return SODSO_E_ARG;
   }
@@ -1074,25 +1032,21 @@ int sodso_db_create(sodso_ctx *c, int type, const double *hist2, int n_local, in
   db->ctx = c;
   db->type = type;
   db->n = n_local;
+  db->cap = std::max(n_local, 1);
   db->row0 = global_row0;
   db->op_algo = c->algo;
   const size_t w = type == SODSO_TYPE_SC ? 2 * SC_SIZE : 2 * M2DP_SIG;
   const size_t rows = type == SODSO_TYPE_SC ? n_local : 4 * (size_t)n_local;
-  const double *hd;
-  int rc = stage_in(c, hist2, rows * w, c->h2, &hd);
-  if (!rc) {
-    if (type == SODSO_TYPE_SC)
-      rc = sc_prepare(c, db->op_algo, hd, n_local, db->op, true);
-    else {
-      cudaError_t e = db->op.reserve(rows * w * sizeof(double));
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(db->op.p, hd, rows * w * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
-      if (e != cudaSuccess) {
-        set_error(std::string("db_create: ") + cudaGetErrorString(e));
-        rc = SODSO_E_CUDA;
-      }
-    }
+  const double *hd = nullptr;
+  int rc = SODSO_OK;
+  cudaError_t e = db->op.reserve(db_op_bytes(db, db->cap));
+  if (e == cudaSuccess) e = cudaMemsetAsync(db->op.p, 0, db->op.cap, c->stream);
+  if (e != cudaSuccess) {
+    set_error(std::string("db_create: ") + cudaGetErrorString(e));
+    rc = SODSO_E_CUDA;
   }
+  if (!rc && n_local > 0) rc = stage_in(c, hist2, rows * w, c->h2, &hd);
+  if (!rc && n_local > 0) rc = db_write_rows(db, hd, 0, n_local, true);
   if (!rc) rc = sync_ctx(c);
   if (rc) {
     sodso_db_destroy(db);
@@ -1100,6 +1054,67 @@ int sodso_db_create(sodso_ctx *c, int type, const double *hist2, int n_local, in
   }
   *out = db;
   return SODSO_OK;
+}
+
+// capacity: the operand buffers are laid out for `cap` rows; growing re-lays them out on the device (no host traffic)
+int sodso_db_reserve(sodso_db *db, int capacity) {
+  if (!db || capacity < 0) {
+    set_error("bad db_reserve arguments");
+    return SODSO_E_ARG;
+  }
+  sodso_ctx *c = db->ctx;
+  CTX_CHECK(c);
+  if (capacity <= db->cap) return SODSO_OK;
+  if (db->type == SODSO_TYPE_SC && db->op_algo == SODSO_ALGO_SIMT) {
+    set_error("the fp32 cross-check database cannot grow");
+    return SODSO_E_STATE;
+  }
+  Buf nb;
+  SODSO_CUDA_CHECK(nb.reserve(db_op_bytes(db, capacity)));
+  cudaError_t e = cudaMemsetAsync(nb.p, 0, nb.cap, c->stream);
+  if (e == cudaSuccess) {
+    if (db->type == SODSO_TYPE_M2DP)
+      e = cudaMemcpyAsync(nb.p, db->op.p, (size_t)4 * db->n * 2 * M2DP_SIG * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+    else
+      e = sc_tc_db_relayout(db->op.p, db->cap, nb.p, capacity, c->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    nb.release();
+    set_error(std::string("db_reserve: ") + cudaGetErrorString(e));
+    return SODSO_E_CUDA;
+  }
+  db->op.release();
+  db->op = nb;
+  db->cap = capacity;
+  db->matched = false;
+  return SODSO_OK;
+}
+
+// n_new further signatures behind the shard's last row (global indices global_row0 + n ...): only their operand rows
+// are written; capacity doubles when it runs out
+int sodso_db_append(sodso_db *db, const double *hist_new, int n_new) {
+  if (!db || n_new < 0 || (n_new > 0 && !hist_new)) {
+    set_error("bad db_append arguments");
+    return SODSO_E_ARG;
+  }
+  sodso_ctx *c = db->ctx;
+  CTX_CHECK(c);
+  if (n_new == 0) return SODSO_OK;
+  if ((int64_t)db->n + n_new > INT32_MAX / 4) {
+    set_error("db_append: too many rows");
+    return SODSO_E_ARG;
+  }
+  int rc;
+  if (db->n + n_new > db->cap && (rc = sodso_db_reserve(db, std::max(db->n + n_new, 2 * db->cap)))) return rc;
+  const size_t w = db->type == SODSO_TYPE_SC ? 2 * SC_SIZE : 2 * M2DP_SIG;
+  const size_t rows = db->type == SODSO_TYPE_SC ? n_new : 4 * (size_t)n_new;
+  const double *hd;
+  if ((rc = stage_in(c, hist_new, rows * w, c->h2, &hd))) return rc;
+  if ((rc = db_write_rows(db, hd, db->n, n_new, false))) return rc;
+  db->n += n_new;
+  db->matched = false;
+  return sync_ctx(c);
 }
 
 int sodso_db_reload(sodso_db *db, const double *hist2) {
@@ -1115,29 +1130,18 @@ int sodso_db_reload(sodso_db *db, const double *hist2) {
   const double *hd;
   int rc;
   if ((rc = stage_in(c, hist2, rows * w, c->h2, &hd))) return rc;
-  if (db->type == SODSO_TYPE_SC) {
-    if ((rc = sc_prepare(c, db->op_algo, hd, db->n, db->op, true))) return rc;
-  } else {
-    SODSO_CUDA_CHECK(cudaMemcpyAsync(db->op.p, hd, rows * w * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-  }
+  if ((rc = db_write_rows(db, hd, 0, db->n, true))) return rc;
   return sync_ctx(c);
 }
 
 // reload + match in one streamed pass: the shard's scans arrive as HOST point buffers, are copied in 512-scan chunks
 // on the copy stream, binned and written into the operand buffers in place, and every chunk is matched against the m
 // queries as soon as it has landed.  Afterwards the handle is in the state sodso_db_reload + sodso_db_match leave it in.
-int sodso_db_stream_match(sodso_db *db, const double *xyz, const float *inten, const int64_t *off, double max_rho,
-                          const double *hist1, int m) {
-  if (!db || !xyz || !inten || !off || !hist1 || m <= 0) {
-    set_error("bad db_stream_match arguments");
-    return SODSO_E_ARG;
-  }
+// The query operand (db->q_op, m rows) must already be enqueued on the context's stream; nothing is synchronised.
+}  // extern "C"
+namespace sodso {
+int db_stream_match_async(sodso_db *db, const double *xyz, const float *inten, const int64_t *off, double max_rho, int m) {
   sodso_ctx *c = db->ctx;
-  CTX_CHECK(c);
-  if (db->type != SODSO_TYPE_SC || db->op_algo != SODSO_ALGO_TC) {
-    set_error("db_stream_match: Scan Context shards with the tensor-core matcher only");
-    return SODSO_E_STATE;
-  }
   const int n = db->n;
   int rc;
   int64_t total = 0;
@@ -1145,12 +1149,8 @@ int sodso_db_stream_match(sodso_db *db, const double *xyz, const float *inten, c
   db->matched = false;
   const bool host_pts = !is_device_ptr(xyz) && !is_device_ptr(inten) && !is_device_ptr(off);
   const int CH = 512;
-  const bool streamed = host_pts && n >= 4 * CH;
+  const bool streamed = host_pts && n >= std::max(c->stream_min_scans, 2 * CH);
   const int nchunk = streamed ? (n + CH - 1) / CH : 1;
-  // queries: operand first (it gates every block)
-  const double *hq;
-  if ((rc = stage_in(c, hist1, (size_t)m * 2 * SC_SIZE, db->q_in, &hq))) return rc;
-  if ((rc = sc_prepare(c, db->op_algo, hq, m, db->q_op, false))) return rc;
   const double *xd = xyz;
   const float *id = inten;
   const int64_t *od;
@@ -1166,65 +1166,97 @@ int sodso_db_stream_match(sodso_db *db, const double *xyz, const float *inten, c
   const size_t cnt = (size_t)m * n;
   SODSO_CUDA_CHECK(db->dp.reserve(cnt * 4));
   SODSO_CUDA_CHECK(db->di.reserve(cnt * 4));
-  SODSO_CUDA_CHECK(db->op.reserve(sc_tc_db_bytes(n)));
   SODSO_CUDA_CHECK(launch_sc_tc_clear_flags(db->op.p, c->stream));
-  std::vector<cudaEvent_t> evs;
+  // events of the chunk copies: destroyed on every exit path
+  struct Events {
+    std::vector<cudaEvent_t> v;
+    ~Events() {
+      for (cudaEvent_t e : v)
+        if (e) cudaEventDestroy(e);
+    }
+  } evs;
+  auto enqueue_copy = [&](int k) -> cudaError_t {   // chunk k of the host buffers -> HBM, on the copy stream
+    const int s0 = k * CH, s1 = std::min(n, s0 + CH);
+    const int64_t p0 = off[s0], p1 = off[s1];
+    cudaError_t e = cudaSuccess;
+    if (p1 > p0) {
+      e = cudaMemcpyAsync(c->in_xyz.as<double>() + 3 * p0, xyz + 3 * p0, (size_t)(p1 - p0) * 3 * sizeof(double),
+                          cudaMemcpyHostToDevice, c->copy_stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(c->in_inten.as<float>() + p0, inten + p0, (size_t)(p1 - p0) * sizeof(float),
+                            cudaMemcpyHostToDevice, c->copy_stream);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&evs.v[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(evs.v[k], c->copy_stream);
+    return e;
+  };
   if (streamed) {
     if (!c->copy_stream) SODSO_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     cudaEvent_t e0;
     SODSO_CUDA_CHECK(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
-    SODSO_CUDA_CHECK(cudaEventRecord(e0, c->stream));
-    SODSO_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, e0, 0));
+    cudaError_t e = cudaEventRecord(e0, c->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, e0, 0);
     cudaEventDestroy(e0);
-    evs.resize(nchunk, nullptr);
-    for (int k = 0; k < nchunk; k++) {
-      const int s0 = k * CH, s1 = std::min(n, s0 + CH);
-      const int64_t p0 = off[s0], p1 = off[s1];
-      if (p1 > p0) {
-        SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_xyz.as<double>() + 3 * p0, xyz + 3 * p0,
-                                         (size_t)(p1 - p0) * 3 * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
-        SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_inten.as<float>() + p0, inten + p0, (size_t)(p1 - p0) * sizeof(float),
-                                         cudaMemcpyHostToDevice, c->copy_stream));
-      }
-      SODSO_CUDA_CHECK(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
-      SODSO_CUDA_CHECK(cudaEventRecord(evs[k], c->copy_stream));
-    }
+    SODSO_CUDA_CHECK(e);
+    evs.v.assign(nchunk, nullptr);
+    // copies run one chunk ahead of the compute that is enqueued below (with pageable host memory cudaMemcpyAsync
+    // returns only once the chunk has been staged: the compute of the previous chunk is already in the queue then)
+    SODSO_CUDA_CHECK(enqueue_copy(0));
   } else if (host_pts) {
     SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_xyz.p, xyz, (size_t)total * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_inten.p, inten, (size_t)total * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   }
-  const int n_pad = sc_tc_db_rows_padded(n);
+  const int n_pad = sc_tc_db_rows_padded(db->cap);
   c->kname = "sc_match_tc_kernel";
   c->ev_valid = false;
-  rc = SODSO_OK;
-  for (int k = 0; k < nchunk && rc == SODSO_OK; k++) {
+  for (int k = 0; k < nchunk; k++) {
     const int s0 = streamed ? k * CH : 0, s1 = streamed ? std::min(n, s0 + CH) : n;
     const bool last = k == nchunk - 1;
     cudaError_t e = cudaSuccess;
-    if (streamed) e = cudaStreamWaitEvent(c->stream, evs[k], 0);
+    if (streamed && !last) e = enqueue_copy(k + 1);
+    if (streamed && e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, evs.v[k], 0);
     if (e == cudaSuccess)
       e = launch_sc_generate(xd, id, od + s0, s1 - s0, max_rho, hd + (size_t)s0 * 2 * SC_SIZE, c->num_sms, c->stream,
                              &c->launches);
     if (e == cudaSuccess)
-      e = launch_sc_tc_prep_db_rows(hd, n, s0, last ? n_pad : s1, db->op.p, c->stream, &c->launches);
+      e = launch_sc_tc_prep_db_rows(hd, n, s0, last ? n_pad : s1, db->op.p, c->stream, &c->launches, db->cap);
     if (!streamed && e == cudaSuccess) c->ev_valid = cudaEventRecord(c->ev0, c->stream) == cudaSuccess;
     if (e == cudaSuccess)
-      e = launch_sc_match_tc_block(db->q_op.p, m, 0, m, db->op.p, n, s0, s1, db->dp.as<float>(), db->di.as<float>(), n,
-                                   c->num_sms, c->stream, &c->launches);
+      e = launch_sc_match_tc_blocks(db->q_op.p, m, db->op.p, n, 0, m, s0, s1, 0, 0, 0, 0, db->dp.as<float>(),
+                                    db->di.as<float>(), n, c->num_sms, c->stream, &c->launches, db->cap);
     if (!streamed && c->ev_valid) c->ev_valid = cudaEventRecord(c->ev1, c->stream) == cudaSuccess;
     if (e != cudaSuccess) {
       set_error(std::string("db_stream_match: ") + cudaGetErrorString(e));
-      rc = SODSO_E_CUDA;
+      cudaStreamSynchronize(c->stream);
+      if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+      return SODSO_E_CUDA;
     }
-  }
-  for (cudaEvent_t ev : evs)
-    if (ev) cudaEventDestroy(ev);
-  if (rc) {
-    cudaStreamSynchronize(c->stream);
-    return rc;
   }
   db->m = m;
   db->matched = true;
+  return SODSO_OK;
+}
+}  // namespace sodso
+extern "C" {
+
+int sodso_db_stream_match(sodso_db *db, const double *xyz, const float *inten, const int64_t *off, double max_rho,
+                          const double *hist1, int m) {
+  if (!db || !xyz || !inten || !off || !hist1 || m <= 0) {
+    set_error("bad db_stream_match arguments");
+    return SODSO_E_ARG;
+  }
+  sodso_ctx *c = db->ctx;
+  CTX_CHECK(c);
+  if (db->type != SODSO_TYPE_SC || db->op_algo != SODSO_ALGO_TC || db->n <= 0) {
+    set_error("db_stream_match: non-empty Scan Context shards with the tensor-core matcher only");
+    return SODSO_E_STATE;
+  }
+  int rc;
+  // queries: operand first (it gates every block)
+  const double *hq;
+  if ((rc = stage_in(c, hist1, (size_t)m * 2 * SC_SIZE, db->q_in, &hq))) return rc;
+  if ((rc = sc_prepare(c, db->op_algo, hq, m, db->q_op, false))) return rc;
+  if ((rc = db_stream_match_async(db, xyz, inten, off, max_rho, m))) return rc;
   return sync_ctx(c);
 }
 
@@ -1233,25 +1265,38 @@ void sodso_db_destroy(sodso_db *db) {
   cudaSetDevice(db->ctx->device);
   cudaStreamSynchronize(db->ctx->stream);
   for (Buf *b : {&db->op, &db->q_in, &db->q_op, &db->dp, &db->di, &db->stats, &db->gstats, &db->idx,
-                 &db->score, &db->dpat, &db->diat, &db->ws})
+                 &db->score, &db->dpat, &db->diat, &db->ws, &db->q_hist, &db->pack, &db->gather, &db->q_xyz, &db->q_inten, &db->q_off})
     b->release();
   delete db;
 }
 
 int sodso_db_size(sodso_db *db) { return db ? db->n : 0; }
 
-int sodso_db_match(sodso_db *db, const double *hist1, int m) {
-  if (!db) {
-    set_error("null db");
-    return SODSO_E_ARG;
-  }
+}  // extern "C"
+namespace sodso {
+int db_match_prepared_async(sodso_db *db, int m) {
   sodso_ctx *c = db->ctx;
-  CTX_CHECK(c);
-  if (m <= 0 || !hist1) {
-    set_error("bad db_match arguments");
-    return SODSO_E_ARG;
-  }
   db->matched = false;
+  const size_t cnt = (size_t)m * db->n;
+  int rc;
+  SODSO_CUDA_CHECK(db->dp.reserve(cnt * 4));
+  SODSO_CUDA_CHECK(db->di.reserve(cnt * 4));
+  if ((rc = sc_match_core(c, db->op_algo, db->q_op, m, db->op, db->n, db->dp.as<float>(), db->di.as<float>(), db->n,
+                          false, db->cap)))
+    return rc;
+  db->m = m;
+  db->matched = true;
+  return SODSO_OK;
+}
+
+// distances of m queries against the shard, everything enqueued on the context's stream, nothing synchronised
+int db_match_async(sodso_db *db, const double *hist1, int m) {
+  sodso_ctx *c = db->ctx;
+  db->matched = false;
+  if (db->n <= 0) {
+    set_error("the database is empty");
+    return SODSO_E_STATE;
+  }
   const size_t w = db->type == SODSO_TYPE_SC ? 2 * SC_SIZE : 2 * M2DP_SIG;
   const size_t rows = db->type == SODSO_TYPE_SC ? m : 4 * (size_t)m;
   const double *hd;
@@ -1262,9 +1307,7 @@ int sodso_db_match(sodso_db *db, const double *hist1, int m) {
   SODSO_CUDA_CHECK(db->di.reserve(cnt * 4));
   if (db->type == SODSO_TYPE_SC) {
     if ((rc = sc_prepare(c, db->op_algo, hd, m, db->q_op, false))) return rc;
-    if ((rc = sc_match_core(c, db->op_algo, db->q_op, m, db->op, db->n, db->dp.as<float>(), db->di.as<float>(),
-                            db->n)))
-      return rc;
+    return db_match_prepared_async(db, m);
   } else {
     if (db->op_algo == SODSO_ALGO_SIMT) {
       SODSO_CUDA_CHECK(db->ws.reserve(m2dp_match_workspace_bytes(m, db->n)));
@@ -1282,6 +1325,26 @@ int sodso_db_match(sodso_db *db, const double *hist1, int m) {
   db->matched = true;
   return SODSO_OK;
 }
+}  // namespace sodso
+extern "C" {
+
+int sodso_db_match(sodso_db *db, const double *hist1, int m) {
+  if (!db) {
+    set_error("null db");
+    return SODSO_E_ARG;
+  }
+  sodso_ctx *c = db->ctx;
+  CTX_CHECK(c);
+  if (m <= 0 || !hist1) {
+    set_error("bad db_match arguments");
+    return SODSO_E_ARG;
+  }
+  int rc;
+  if ((rc = db_match_async(db, hist1, m))) return rc;
+  // hist1 may be pageable / pinned host memory or a device tensor the caller reuses: the call returns once the library
+  // has finished reading it (and asynchronous kernel failures surface here, not in a later unrelated call)
+  return sync_ctx(c);
+}
 
 int sodso_db_partial_stats(sodso_db *db, double *stats) {
   if (!db || !stats) {
@@ -1296,7 +1359,7 @@ int sodso_db_partial_stats(sodso_db *db, double *stats) {
   }
   double *sd;
   int rc;
-  const size_t cnt = (size_t)db->m * 4;
+  const size_t cnt = (size_t)db->m * STATS_W;
   if ((rc = stage_out(c, stats, cnt, db->stats, &sd))) return rc;
   SODSO_CUDA_CHECK(launch_row_stats(db->dp.as<float>(), db->di.as<float>(), db->m, db->n, db->n, sd, c->stream,
                                     &c->launches));
@@ -1320,7 +1383,7 @@ int sodso_db_topk(sodso_db *db, const double *global_stats, int64_t n_global, in
   const double *gs;
   int rc;
   const size_t cnt = (size_t)db->m * k;
-  if ((rc = stage_in(c, global_stats, (size_t)db->m * 4, db->gstats, &gs))) return rc;
+  if ((rc = stage_in(c, global_stats, (size_t)db->m * STATS_W, db->gstats, &gs))) return rc;
   int64_t *id;
   double *sd, *pa, *ia;
   if ((rc = stage_out(c, idx, cnt, db->idx, &id))) return rc;

@@ -20,6 +20,7 @@ constexpr int M2DP_SR = M2DP_NUM_S * M2DP_NUM_R;  // 128
 constexpr int M2DP_SIG = M2DP_PQ + M2DP_SR;       // 192
 
 constexpr double STAT_SHIFT = 0.25;  // centre of the [0, 0.5] distance range, see sodso_db_partial_stats
+constexpr int STATS_W = 6;           // per query row: [sum, sum of squares, count] of the non-NaN entries, per channel
 
 #ifdef __CUDACC__
 // atan2(num, den) / 2pi + 1/2 in [0, 1] ("turns"), fp32, |error| < 2e-7 turns for finite inputs that are
@@ -46,6 +47,14 @@ __device__ __forceinline__ float fast_turns(float num, float den) {
 #endif
 
 void set_error(const std::string &msg);
+
+// kernel debug switches of tools/ (sodso_debug_set_kernel_flags, include/sodso_pr_debug.h); never read from the environment
+struct DebugFlags {
+  int tc_flags = 0;    // sc_match_tc_kernel: 1 skip epilogue loads, 2 skip MMAs, 4 force generic mode
+  int gen_flags = 2;   // sc_generate_kernel variant bits
+  int gen_ctas = 0;    // CTAs per SM of sc_generate_kernel (0 = default)
+};
+extern DebugFlags g_debug;
 
 struct KernelTimer;  // capi.cu
 
@@ -97,10 +106,11 @@ cudaError_t launch_sc_tc_prep_query(const double *hist, int m, void *q_buf, cuda
 // streamed / blocked variants: operands are filled row range by row range and matched block by block
 cudaError_t launch_sc_tc_clear_flags(void *buf, cudaStream_t st);
 cudaError_t launch_sc_tc_prep_db_rows(const double *hist, int n, int row0, int row1, void *db_buf,
-                                      cudaStream_t st, int64_t *launches);
+                                      cudaStream_t st, int64_t *launches, int n_layout = 0);
 cudaError_t launch_sc_tc_prep_query_rows(const double *hist, int m, int row0, int row1, void *q_buf,
                                          cudaStream_t st, int64_t *launches);
 int sc_tc_db_rows_padded(int n);
+cudaError_t sc_tc_db_relayout(const void *old_buf, int old_cap, void *new_buf, int new_cap, cudaStream_t st);
 int sc_tc_query_rows_padded(int m);
 cudaError_t launch_sc_match_tc_block(const void *q_buf, int m, int q0, int q1, const void *db_buf, int n,
                                      int r0, int r1, float *d_p, float *d_i, int ldd, int num_sms,
@@ -110,10 +120,11 @@ cudaError_t launch_sc_match_tc_self(const void *q_buf, const void *db_buf, int n
                                     int ldd, int num_sms, cudaStream_t st, int64_t *launches);
 cudaError_t launch_sc_match_tc_blocks(const void *q_buf, int m, const void *db_buf, int n, int qa0, int qa1,
                                       int ra0, int ra1, int qb0, int qb1, int rb0, int rb1, float *d_p,
-                                      float *d_i, int ldd, int num_sms, cudaStream_t st, int64_t *launches);
+                                      float *d_i, int ldd, int num_sms, cudaStream_t st, int64_t *launches,
+                                      int n_layout = 0);
 // d_p / d_i: fp32 m x ldd.  Returns cudaErrorNotSupported if tensor maps cannot be encoded.
 cudaError_t launch_sc_match_tc(const void *q_buf, int m, const void *db_buf, int n, float *d_p,
-                               float *d_i, int ldd, int num_sms, cudaStream_t st, int64_t *launches);
+                               float *d_i, int ldd, int num_sms, cudaStream_t st, int64_t *launches, int n_layout = 0);
 
 // stage_points.cu : pts_preprocess on the GPU
 struct StagePlan {                  // host bookkeeping of the sequential pose walk (pts_preprocess.h:187-216)
@@ -173,7 +184,7 @@ cudaError_t launch_fuse_top1_f64(const double *d_p, const double *d_i, int m, in
                                  int64_t *launches);
 cudaError_t launch_topk_merge(const int64_t *idx, const double *score, const double *d_p, const double *d_i,
                               int nshards, int m, int k, int64_t *out_idx, double *out_score, double *out_d_p,
-                              double *out_d_i, cudaStream_t st, int64_t *launches);
+                              double *out_d_i, cudaStream_t st, int64_t *launches, size_t shard_stride = 0);
 cudaError_t launch_gt_loops(const double *gt1, int m, const double *gt2, int n, int mask_width,
                             int32_t *nearest, double *dist2, cudaStream_t st, int64_t *launches);
 cudaError_t launch_f32_to_f64(const float *src, int rows, int cols, int ld, double *dst,

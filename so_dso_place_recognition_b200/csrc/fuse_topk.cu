@@ -87,23 +87,32 @@ __device__ __forceinline__ void block_argmin(double &s, long long &i, double *ss
   __syncthreads();
 }
 
-// stats[row] = [sum(dp-c), sum((dp-c)^2), sum(di-c), sum((di-c)^2)], c = STAT_SHIFT
+// stats[row] = [sum(dp-c), sum((dp-c)^2), count(dp), sum(di-c), sum((di-c)^2), count(di)], c = STAT_SHIFT, over the
+// non-NaN entries only: MATLAB's normalize (run_test.m:40) computes its mean and std with 'omitnan', so the NaN column
+// of one zero-norm DB signature (processSC.m:15-20) stays NaN and every other candidate is still ranked.
 __global__ void __launch_bounds__(FUSE_THREADS)
 row_stats_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, int n, int ldd,
                  double *__restrict__ stats) {
-  __shared__ double scratch[4 * 32];
+  __shared__ double scratch[STATS_W * 32];
   const int row = blockIdx.x;
   const float *p = d_p + (size_t)row * ldd, *q = d_i + (size_t)row * ldd;
-  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  double v[STATS_W] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
-    double a = (double)p[j] - STAT_SHIFT, b = (double)q[j] - STAT_SHIFT;
-    v[0] += a;
-    v[1] += a * a;
-    v[2] += b;
-    v[3] += b * b;
+    const float pf = p[j], qf = q[j];
+    const double a = (double)pf - STAT_SHIFT, b = (double)qf - STAT_SHIFT;
+    if (pf == pf) {
+      v[0] += a;
+      v[1] += a * a;
+      v[2] += 1.0;
+    }
+    if (qf == qf) {
+      v[3] += b;
+      v[4] += b * b;
+      v[5] += 1.0;
+    }
   }
-  block_sum_d<4>(v, scratch);
-  if (threadIdx.x < 4) stats[(size_t)row * 4 + threadIdx.x] = v[threadIdx.x];
+  block_sum_d<STATS_W>(v, scratch);
+  if (threadIdx.x < STATS_W) stats[(size_t)row * STATS_W + threadIdx.x] = v[threadIdx.x];
 }
 
 __global__ void __launch_bounds__(FUSE_THREADS)
@@ -115,11 +124,11 @@ fuse_topk_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, i
   __shared__ long long si[32];
   const int row = blockIdx.x;
   const float *p = d_p + (size_t)row * ldd, *q = d_i + (size_t)row * ldd;
-  const double *st = gstats + (size_t)row * 4;
-  const double N = (double)n_global;
-  const double mu_p = STAT_SHIFT + st[0] / N, mu_i = STAT_SHIFT + st[2] / N;
-  const double sd_p = sqrt((st[1] - st[0] * st[0] / N) / (N - 1.0));
-  const double sd_i = sqrt((st[3] - st[2] * st[2] / N) / (N - 1.0));
+  const double *st = gstats + (size_t)row * STATS_W;
+  const double Np = st[2], Ni = st[5];   // non-NaN entries of the whole (global) row, per channel
+  const double mu_p = STAT_SHIFT + st[0] / Np, mu_i = STAT_SHIFT + st[3] / Ni;
+  const double sd_p = sqrt((st[1] - st[0] * st[0] / Np) / (Np - 1.0));
+  const double sd_i = sqrt((st[4] - st[3] * st[3] / Ni) / (Ni - 1.0));
   const long long qg = q_row0 + row;
   double last_s = 0.0;
   long long last_i = -1;  // nothing selected yet
@@ -210,31 +219,38 @@ fuse_topk_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, i
   }
 }
 
-// run_test.m:38-57 on caller-supplied fp64 matrices, two-pass statistics like MATLAB normalize.
+// run_test.m:38-57 on caller-supplied fp64 matrices, two-pass statistics over the non-NaN entries like MATLAB normalize.
 __global__ void __launch_bounds__(FUSE_THREADS)
 fuse_top1_f64_kernel(const double *__restrict__ d_p, const double *__restrict__ d_i, int n,
                      int mask_width, double p_weight, int32_t *__restrict__ idx,
                      double *__restrict__ score) {
-  __shared__ double scratch[2 * 32];
+  __shared__ double scratch[4 * 32];
   __shared__ double ss[32];
   __shared__ long long si[32];
   const int row = blockIdx.x;
   const double *p = d_p + (size_t)row * n, *q = d_i + (size_t)row * n;
-  double s[2] = {0.0, 0.0};
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
   for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
-    s[0] += p[j];
-    s[1] += q[j];
+    const double a = p[j], b = q[j];
+    if (a == a) {
+      s[0] += a;
+      s[2] += 1.0;
+    }
+    if (b == b) {
+      s[1] += b;
+      s[3] += 1.0;
+    }
   }
-  block_sum_d<2>(s, scratch);
-  const double mu_p = s[0] / n, mu_i = s[1] / n;
+  block_sum_d<4>(s, scratch);
+  const double mu_p = s[0] / s[2], mu_i = s[1] / s[3];
   double v[2] = {0.0, 0.0};
   for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
-    double a = p[j] - mu_p, b = q[j] - mu_i;
-    v[0] += a * a;
-    v[1] += b * b;
+    const double a = p[j] - mu_p, b = q[j] - mu_i;
+    if (a == a) v[0] += a * a;
+    if (b == b) v[1] += b * b;
   }
   block_sum_d<2>(v, scratch);
-  const double sd_p = sqrt(v[0] / (n - 1)), sd_i = sqrt(v[1] / (n - 1));
+  const double sd_p = sqrt(v[0] / (s[2] - 1.0)), sd_i = sqrt(v[1] / (s[3] - 1.0));
   double bs = 0.0;
   long long bi = -1;
   for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
@@ -332,8 +348,9 @@ gt_loops_kernel(const double *__restrict__ gt1, const double *__restrict__ gt2, 
 // thread per query walks the R list heads k times.  idx < 0 marks an exhausted list.
 __global__ void topk_merge_kernel(const int64_t *__restrict__ idx, const double *__restrict__ score,
                                   const double *__restrict__ d_p, const double *__restrict__ d_i, int nshards, int m,
-                                  int k, int64_t *__restrict__ out_idx, double *__restrict__ out_score,
-                                  double *__restrict__ out_d_p, double *__restrict__ out_d_i) {
+                                  int k, size_t shard_stride, int64_t *__restrict__ out_idx,
+                                  double *__restrict__ out_score, double *__restrict__ out_d_p,
+                                  double *__restrict__ out_d_i) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= m) return;
   int pos[16];   // list heads (at most 16 shards)
@@ -343,7 +360,7 @@ __global__ void topk_merge_kernel(const int64_t *__restrict__ idx, const double 
     size_t bo = 0;
     for (int s = 0; s < nshards; s++) {
       if (pos[s] >= k) continue;
-      const size_t o = ((size_t)s * m + q) * k + pos[s];
+      const size_t o = (size_t)s * shard_stride + (size_t)q * k + pos[s];
       if (idx[o] < 0) continue;
       if (best < 0 || score[o] < score[bo] || (score[o] == score[bo] && idx[o] < idx[bo])) {
         best = s;
@@ -366,13 +383,16 @@ __global__ void topk_merge_kernel(const int64_t *__restrict__ idx, const double 
   }
 }
 
+// shard_stride: elements between the lists of consecutive shards in each of the four arrays (0 = m * k, i.e. four
+// separate R x m x k arrays; the packed all-gather buffer of sharded.cu uses 4 * m * k)
 cudaError_t launch_topk_merge(const int64_t *idx, const double *score, const double *d_p, const double *d_i,
                               int nshards, int m, int k, int64_t *out_idx, double *out_score, double *out_d_p,
-                              double *out_d_i, cudaStream_t st, int64_t *launches) {
+                              double *out_d_i, cudaStream_t st, int64_t *launches, size_t shard_stride) {
   if (m <= 0) return cudaSuccess;
   if (nshards > 16) return cudaErrorInvalidValue;
-  topk_merge_kernel<<<(m + 127) / 128, 128, 0, st>>>(idx, score, d_p, d_i, nshards, m, k, out_idx, out_score, out_d_p,
-                                                     out_d_i);
+  if (shard_stride == 0) shard_stride = (size_t)m * k;
+  topk_merge_kernel<<<(m + 127) / 128, 128, 0, st>>>(idx, score, d_p, d_i, nshards, m, k, shard_stride, out_idx, out_score,
+                                                     out_d_p, out_d_i);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

@@ -313,9 +313,7 @@ cudaError_t launch_sc_generate(const double *xyz, const float *inten, const int6
   if (e != cudaSuccess) return e;
   const double S_res_inv = SC_NUM_S / (2.0 * 3.14159265358979323846);  // SC.cpp:6
   const double R_res_inv = SC_NUM_R / max_rho;                          // SC.cpp:7
-  int per_sm = GEN_CTAS_PER_SM, flags = 2;
-  if (const char *e = getenv("SODSO_GEN_CTAS")) per_sm = atoi(e);
-  if (const char *e = getenv("SODSO_GEN_FLAGS")) flags = atoi(e);
+  const int per_sm = g_debug.gen_ctas > 0 ? g_debug.gen_ctas : GEN_CTAS_PER_SM, flags = g_debug.gen_flags;
   int grid = nscan < per_sm * num_sms ? nscan : per_sm * num_sms;
   sc_generate_kernel<<<grid, GEN_THREADS, sizeof(ScSmem), st>>>(xyz, inten, off, nscan, S_res_inv,
                                                                 R_res_inv, hist, flags);

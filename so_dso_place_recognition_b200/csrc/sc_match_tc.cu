@@ -694,11 +694,8 @@ sc_match_tc_kernel(const __grid_constant__ CUtensorMap map_f16_0, const __grid_c
 // ---------------------------------------------------------------------------------------------
 }  // namespace
 
-// debug flags (SODSO_TC_FLAGS): 1 skip epilogue loads, 2 skip MMAs, 4 force generic mode
-static int tc_flags() {
-  const char *e = getenv("SODSO_TC_FLAGS");
-  return e ? atoi(e) : 0;
-}
+// debug flags (sodso_debug_set_kernel_flags): 1 skip epilogue loads, 2 skip MMAs, 4 force generic mode
+static int tc_flags() { return g_debug.tc_flags; }
 
 size_t sc_tc_db_bytes(int n) { return DbLayout(n).total; }
 size_t sc_tc_query_bytes(int m) { return QLayout(m).total; }
@@ -713,10 +710,11 @@ cudaError_t launch_sc_tc_prep_db(const double *hist, int n, void *db_buf, cudaSt
 cudaError_t launch_sc_tc_clear_flags(void *buf, cudaStream_t st) { return cudaMemsetAsync(buf, 0, HEADER_BYTES, st); }
 
 // rows [row0, row1) of an n-row operand (row1 may run into the zero padding up to n_pad)
+// n_layout > 0: the operand buffer is laid out for n_layout >= n rows (a database with spare capacity, sodso_db_append)
 cudaError_t launch_sc_tc_prep_db_rows(const double *hist, int n, int row0, int row1, void *db_buf, cudaStream_t st,
-                                      int64_t *launches) {
+                                      int64_t *launches, int n_layout) {
   if (row1 <= row0) return cudaSuccess;
-  DbLayout L(n);
+  DbLayout L(n_layout > 0 ? n_layout : n);
   sc_tc_prep_db_kernel<<<dim3(row1 - row0, 2), 128, 0, st>>>(hist, n, L.n_pad, reinterpret_cast<unsigned char *>(db_buf),
                                                              L.off_f16, L.off_f4, L.off_norm, row0);
   if (launches) ++*launches;
@@ -738,6 +736,22 @@ cudaError_t launch_sc_tc_prep_query_rows(const double *hist, int m, int row0, in
 }
 
 int sc_tc_db_rows_padded(int n) { return DbLayout(n).n_pad; }
+
+// moves the rows of a DB operand laid out for old_cap rows into a (zeroed) buffer laid out for new_cap >= old_cap rows
+cudaError_t sc_tc_db_relayout(const void *old_buf, int old_cap, void *new_buf, int new_cap, cudaStream_t st) {
+  const DbLayout A(old_cap), B(new_cap);
+  const unsigned char *a = reinterpret_cast<const unsigned char *>(old_buf);
+  unsigned char *b = reinterpret_cast<unsigned char *>(new_buf);
+  cudaError_t e = cudaMemcpyAsync(b, a, HEADER_BYTES, cudaMemcpyDeviceToDevice, st);
+  const size_t row_bytes[3] = {(size_t)K_F16 * 2, (size_t)F4_ROW_BYTES, sizeof(float)};
+  const size_t offa[3] = {A.off_f16, A.off_f4, A.off_norm}, offb[3] = {B.off_f16, B.off_f4, B.off_norm};
+  for (int part = 0; part < 3 && e == cudaSuccess; part++)
+    for (int ch = 0; ch < 2 && e == cudaSuccess; ch++)
+      e = cudaMemcpyAsync(b + offb[part] + (size_t)ch * B.n_pad * row_bytes[part],
+                          a + offa[part] + (size_t)ch * A.n_pad * row_bytes[part], (size_t)A.n_pad * row_bytes[part],
+                          cudaMemcpyDeviceToDevice, st);
+  return e;
+}
 int sc_tc_query_rows_padded(int m) { return QLayout(m).m_pad; }
 
 cudaError_t launch_sc_tc_prep_query(const double *hist, int m, void *q_buf, cudaStream_t st, int64_t *launches) {
@@ -748,8 +762,8 @@ cudaError_t launch_sc_tc_prep_query(const double *hist, int m, void *q_buf, cuda
 }
 
 cudaError_t launch_sc_match_tc(const void *q_buf, int m, const void *db_buf, int n, float *d_p, float *d_i, int ldd,
-                               int num_sms, cudaStream_t st, int64_t *launches) {
-  return launch_sc_match_tc_block(q_buf, m, 0, m, db_buf, n, 0, n, d_p, d_i, ldd, num_sms, st, launches);
+                               int num_sms, cudaStream_t st, int64_t *launches, int n_layout) {
+  return launch_sc_match_tc_blocks(q_buf, m, db_buf, n, 0, m, 0, n, 0, 0, 0, 0, d_p, d_i, ldd, num_sms, st, launches, n_layout);
 }
 
 // queries [q0, q1) x DB rows [r0, r1) of the m x n problem; q0 must be a multiple of 4 and r0 of 256
@@ -777,7 +791,7 @@ cudaError_t launch_sc_match_tc_self(const void *q_buf, const void *db_buf, int n
 // qb0 < 0: rectangle A is the triangular region of a self-match (launch_sc_match_tc_self)
 cudaError_t launch_sc_match_tc_blocks(const void *q_buf, int m, const void *db_buf, int n, int qa0, int qa1, int ra0, int ra1,
                                       int qb0, int qb1, int rb0, int rb1, float *d_p, float *d_i, int ldd, int num_sms,
-                                      cudaStream_t st, int64_t *launches) {
+                                      cudaStream_t st, int64_t *launches, int n_layout) {
   if (m <= 0 || n <= 0) return cudaSuccess;
   const bool tri = qb0 < 0;
   if (tri) qb0 = 0;
@@ -791,7 +805,7 @@ cudaError_t launch_sc_match_tc_blocks(const void *q_buf, int m, const void *db_b
   if (wr[0] + wr[1] == 0) return cudaSuccess;
   PFN_encodeTiled enc = get_encode();
   if (!enc) return cudaErrorNotSupported;
-  DbLayout DL(n);
+  DbLayout DL(n_layout > 0 ? n_layout : n);   // rows >= n are never stored (P.n), whatever the padding holds
   QLayout QL(m);
   const unsigned char *dbb = reinterpret_cast<const unsigned char *>(db_buf);
   CUtensorMap maps[4];

@@ -8,19 +8,52 @@ import pytest
 from so_dso_place_recognition_b200 import _native as N
 
 
-def _declared():
-    txt = open(N.HEADER_PATH).read()
+def _declared(path=None):
+    txt = open(path or N.HEADER_PATH).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(sodso_[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_header_symbols_exported():
     names = _declared()
-    assert len(names) >= 25
+    assert len(names) >= 40
     L = ctypes.CDLL(N.LIB_PATH)
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/sodso_pr.h but not exported"
     assert set(names) == set(N.exported_names()), "python prototypes out of sync with the header"
+
+
+def test_debug_header_is_separate():
+    """test hooks and the cross-check switches live in sodso_pr_debug.h, not in the reference-facing header"""
+    pub, dbg = _declared(), _declared(N.DEBUG_HEADER_PATH)
+    assert not [n for n in pub if "debug" in n]
+    assert "SODSO_ALGO_SIMT" not in open(N.HEADER_PATH).read()
+    assert dbg and all(n.startswith("sodso_debug_") for n in dbg)
+    L = ctypes.CDLL(N.LIB_PATH)
+    for n in dbg:
+        assert hasattr(L, n), f"{n} declared in include/sodso_pr_debug.h but not exported"
+    assert set(dbg) == set(N.debug_names())
+
+
+def test_library_reads_nothing_from_the_environment():
+    """behaviour switches are context state behind sodso_pr_debug.h, never environment variables (the static CUDA
+    runtime linked into the .so does call getenv itself, so the sources are what is checked)"""
+    import glob
+    import os
+
+    src = os.path.join(os.path.dirname(N.LIB_PATH), "..", "csrc")
+    files = glob.glob(os.path.join(src, "*.cu")) + glob.glob(os.path.join(src, "*.cuh"))
+    assert len(files) > 10
+    for f in files:
+        assert "getenv" not in open(f).read(), f
+
+
+def test_comm_entry_points_without_gpu():
+    """communicator plumbing that needs no device: rank bookkeeping defaults and argument checks"""
+    L = N.lib()
+    assert L.sodso_comm_nranks(None) == 1 and L.sodso_comm_rank(None) == 0
+    assert L.sodso_comm_unique_id(None) == -1          # SODSO_E_ARG
+    assert L.sodso_comm_init(None, None, 2, 0) != 0
 
 
 def test_sizes_and_version():

@@ -149,8 +149,8 @@ def _topk_numpy(dp, di, q0, row0, mask, k):
     out = []
     for i in range(dp.shape[0]):
         with np.errstate(invalid="ignore", divide="ignore"):
-            mu_p, mu_i = np.mean(dp[i]), np.mean(di[i])
-            sd_p, sd_i = np.std(dp[i], ddof=1), np.std(di[i], ddof=1)
+            mu_p, mu_i = np.nanmean(dp[i]), np.nanmean(di[i])       # MATLAB normalize omits NaN (run_test.m:40)
+            sd_p, sd_i = np.nanstd(dp[i], ddof=1), np.nanstd(di[i], ddof=1)
             f = 2.0 * ((dp[i] - mu_p) / sd_p) + (di[i] - mu_i) / sd_i
         jg = row0 + np.arange(n)
         f[np.abs((q0 + i) - jg) < mask] = np.inf
@@ -189,3 +189,30 @@ def test_topk_vs_numpy_on_device_distances(gpu_ctx, sigs, k, n_db):
     # the zero-norm query has NaN everywhere; only masked entries (+inf by run_test.m:47-53) can be handed out
     sel = idx[5][idx[5] >= 0]
     assert (np.abs((q0 + 5) - sel) < mask).all()
+
+
+def test_zero_norm_db_row_does_not_poison_fusion(gpu_ctx, oracle, sigs):
+    """One degenerate (all-zero, e.g. empty scan) DB signature gives a NaN column (processSC.m:15-20).  MATLAB's
+    normalize (run_test.m:40) omits NaN from the row statistics, so every other candidate is still ranked: same top-1
+    as the oracle, never the NaN column, and -- on the fused kernels and on sodso_fuse_top1 -- finite scores."""
+    h = sigs[:300].copy()
+    h[123] = 0.0
+    q = sigs[300:340]
+    idx, score = api.run_test("sc", q, h, 0)
+    rp, ri = oracle.sc_match_numpy(q, h)
+    assert np.isnan(rp[:, 123]).all()
+    ridx, rscore = oracle.fuse_top1(rp, ri, 0)
+    np.testing.assert_array_equal(idx, ridx)
+    assert np.isfinite(score).all() and not (idx == 123).any()
+    np.testing.assert_allclose(score, rscore, rtol=0, atol=2e-3)     # fp32 distances vs fp64: scores, not decisions
+    dp, di = api.processSC(q, h)
+    fidx, fscore = api.fuse_top1(dp, di, 0)
+    np.testing.assert_array_equal(fidx, oracle.fuse_top1(dp, di, 0)[0])
+    assert np.isfinite(fscore).all()
+    # the same through the resident-database entry points (partial statistics carry the non-NaN counts)
+    db = api.SignatureDB("sc", h)
+    kidx, kscore, _, _ = db.query_sharded(q, 0, 0, 2.0, 2)
+    st_m = db.partial_stats()
+    db.close()
+    np.testing.assert_array_equal(kidx[:, 0], ridx)
+    assert (st_m[:, 2] == 299).all() and (st_m[:, 5] == 299).all()    # the NaN column is not counted

@@ -1,7 +1,7 @@
 """Self-match symmetry of the tcgen05 Scan Context matcher (so_dso_place_recognition_b200/csrc/sc_match_tc.cu,
 `launch_sc_match_tc_self`): when hist1 and hist2 are the same n rows the library computes the lower block triangle of
 (query group, DB tile) items and stores each value at its transposed position too.  Checked against the oracle
-(processSC.m:1-45), against the full computation (SODSO_SC_SYMMETRY=0) and for exact symmetry of the mirrored part."""
+(processSC.m:1-45), against the full computation (test hook sodso_debug_set_sc_symmetry) and for exact symmetry of the mirrored part."""
 import numpy as np
 import pytest
 
@@ -24,12 +24,14 @@ def test_self_match_vs_oracle(gpu_ctx, oracle, n):
     np.testing.assert_allclose(di, ri, rtol=0, atol=1e-5)
 
 
-def test_self_match_equals_full_computation(gpu_ctx, monkeypatch):
+def test_self_match_equals_full_computation(gpu_ctx):
     h = _sigs(1301, seed=7)
     dp, di = api.processSC(h, h)
-    monkeypatch.setenv("SODSO_SC_SYMMETRY", "0")
-    fp, fi = api.processSC(h, h)
-    monkeypatch.delenv("SODSO_SC_SYMMETRY")
+    gpu_ctx.set_sc_symmetry(False)
+    try:
+        fp, fi = api.processSC(h, h)
+    finally:
+        gpu_ctx.set_sc_symmetry(True)
     # the directly computed part is bit-identical, the mirrored part differs by fp32 summation order only
     np.testing.assert_allclose(dp, fp, rtol=0, atol=2e-6)
     np.testing.assert_allclose(di, fi, rtol=0, atol=2e-6)
@@ -52,12 +54,14 @@ def test_same_values_different_buffers_take_the_general_path(gpu_ctx, oracle):
     np.testing.assert_allclose(di, ri, rtol=0, atol=1e-5)
 
 
-def test_top1_identical_with_and_without_symmetry(gpu_ctx, monkeypatch):
+def test_top1_identical_with_and_without_symmetry(gpu_ctx):
     h = _sigs(2000, seed=11)
     idx, score = api.run_test("sc", h, h, 100)
-    monkeypatch.setenv("SODSO_SC_SYMMETRY", "0")
-    idx0, score0 = api.run_test("sc", h, h, 100)
-    monkeypatch.delenv("SODSO_SC_SYMMETRY")
+    gpu_ctx.set_sc_symmetry(False)
+    try:
+        idx0, score0 = api.run_test("sc", h, h, 100)
+    finally:
+        gpu_ctx.set_sc_symmetry(True)
     assert np.array_equal(idx, idx0)
     np.testing.assert_allclose(score, score0, rtol=0, atol=1e-3)
 

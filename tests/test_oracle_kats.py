@@ -174,3 +174,32 @@ def test_planted_loops_are_recovered(oracle):
     idx, score = oracle.fuse_top1(dp, di, 3)
     expect = (np.arange(n) + n // 2) % n
     assert (idx == expect).mean() >= 0.9
+
+
+def test_fuse_omits_nan_entries_from_row_statistics(oracle):
+    """run_test.m:40: MATLAB's normalize computes mean / std with 'omitnan'.  One zero-norm DB signature (e.g. an empty
+    scan, processSC.m:15-20) gives a NaN column; every other candidate must still be ranked exactly as if that column
+    were not there, and the NaN column is never chosen."""
+    rng = np.random.default_rng(21)
+    m, n, bad = 40, 90, 33
+    dp, di = rng.random((m, n)) * 0.5, rng.random((m, n)) * 0.5
+    dpn, din = dp.copy(), di.copy()
+    dpn[:, bad] = np.nan
+    din[:, bad] = np.nan
+    idx, sc = oracle.fuse_top1(dpn, din, 5)
+    keep = np.arange(n) != bad
+    # without the column: same statistics; the mask must use the ORIGINAL column numbers -> emulate with +inf rows
+    ridx, rsc, fused = oracle.fuse_top1(dp[:, keep], di[:, keep], 0, want_fused=True)
+    cols = np.arange(n)[keep]
+    fused = np.where(np.abs(np.arange(m)[:, None] - cols[None, :]) < 5, np.inf, fused)
+    want = cols[np.argmin(fused, axis=1)]
+    assert np.array_equal(idx, want) and not (idx == bad).any()
+    np.testing.assert_allclose(sc, fused.min(axis=1), rtol=1e-12)
+    # numpy twin used by the bench's CPU arm agrees
+    nidx, _ = oracle.fuse_top1_numpy(dpn, din, 5)
+    assert np.array_equal(nidx, want)
+    # one channel NaN only: that channel's entry is NaN -> the fused entry is NaN -> skipped
+    dpo = dp.copy()
+    dpo[3, 7] = np.nan
+    idx2, _ = oracle.fuse_top1(dpo, di, 0)
+    assert idx2[3] != 7 or np.argmin(np.delete(dp[3], 7)) != 7

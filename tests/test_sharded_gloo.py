@@ -25,16 +25,19 @@ class OracleShard:
         self.dp, self.di = self.O.sc_match_numpy(hist_q, self.h)
 
     def partial_stats(self):
+        # [sum, sum of squares, count] of the non-NaN entries per channel (MATLAB normalize omits NaN)
         a, b = self.dp - STAT_SHIFT, self.di - STAT_SHIFT
-        return np.stack([a.sum(1), (a * a).sum(1), b.sum(1), (b * b).sum(1)], axis=1)
+        return np.stack([np.nansum(a, 1), np.nansum(a * a, 1), (~np.isnan(a)).sum(1).astype(np.float64),
+                         np.nansum(b, 1), np.nansum(b * b, 1), (~np.isnan(b)).sum(1).astype(np.float64)], axis=1)
 
-    def topk(self, gs, n_global, q_row0, mask_width, p_weight, k):
+    def topk(self, gs, q_row0, mask_width, p_weight, k):
         gs = np.asarray(gs)
-        N = float(n_global)
-        mu_p, mu_i = STAT_SHIFT + gs[:, 0] / N, STAT_SHIFT + gs[:, 2] / N
-        sd_p = np.sqrt((gs[:, 1] - gs[:, 0] ** 2 / N) / (N - 1))
-        sd_i = np.sqrt((gs[:, 3] - gs[:, 2] ** 2 / N) / (N - 1))
+        Np, Ni = gs[:, 2], gs[:, 5]
+        mu_p, mu_i = STAT_SHIFT + gs[:, 0] / Np, STAT_SHIFT + gs[:, 3] / Ni
+        sd_p = np.sqrt((gs[:, 1] - gs[:, 0] ** 2 / Np) / (Np - 1))
+        sd_i = np.sqrt((gs[:, 4] - gs[:, 3] ** 2 / Ni) / (Ni - 1))
         f = p_weight * ((self.dp - mu_p[:, None]) / sd_p[:, None]) + (self.di - mu_i[:, None]) / sd_i[:, None]
+        f = np.where(np.isnan(f), np.inf, f)
         m, n = f.shape
         jg = self.row0 + np.arange(n)
         qg = q_row0 + np.arange(m)
@@ -53,7 +56,7 @@ def _worker(rank, world, port, hist, mask, k, out):
     n = hist.shape[0]
     row0, n_local = sharded.shard_rows(n, world, rank)
     shard = OracleShard(O, hist[row0:row0 + n_local], row0)
-    idx, score, dp, di = sharded.sharded_query(shard, hist, n, 0, mask, 2.0, k)
+    idx, score, dp, di = sharded.protocol_reference(shard, hist, 0, mask, 2.0, k)
     if rank == 0:
         out["idx"], out["score"], out["dp"], out["di"] = idx, score, dp, di
     dist.barrier()
