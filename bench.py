@@ -5,18 +5,24 @@
   python bench.py --gpus N --steps K --warmup W          (torchrun for N > 1)
   python bench.py --impl reference ...                   (the CPU restatement on the host cores)
 
-Workload (BASELINE.json configs[2], `config.workload`): a 5 000-scan synthetic set (4 096 points per
-scan, planted loops), Scan Context signatures, all-pairs match over the 120 shift/reversal variants,
-two-channel z-score fusion, temporal mask 100, top-1 loop candidate.  One step = one pass of that
-hot path: sc_generate of the rank's scans -> match of all queries against the rank's DB shard ->
-row statistics -> (N > 1: all-reduce of the statistics, all-gather of the per-shard top-k) ->
-top-1.  For N > 1 the DB is row-sharded, 5 000 scans per GPU (weak scaling), the 5 000 queries
-are replicated.
+Workload (BASELINE.json configs[2], `config.workload`): a 5 000-scan synthetic set (4 096 points per scan, planted
+loops), Scan Context signatures, all-pairs match over the 120 shift / reversal variants, two-channel z-score fusion,
+temporal mask 100, top-1 loop candidate.  One step = one pass of that hot path through ONE C-ABI call,
+sodso_db_scans_query_sharded: bin the rank's 5 000 DB scans and the 5 000 queries, match every (query, DB row) pair
+of the rank's shard, row statistics, (N > 1: NCCL all-reduce of the statistics and all-gather of the per-shard
+candidates, inside the library, on its stream), top-1.  The DB is row-sharded, 5 000 scans per GPU (weak scaling);
+the 5 000 queries are the scans of shard 0.  The SAME entry point and the same general (every pair computed) match
+kernel run at every N, so the 1 -> N curve compares like with like; the N = 1 line additionally reports, as the
+named sub-record `self_match`, the single-GPU self-match API (sodso_sc_scans_to_loops) that exploits
+d(i, j) = d(j, i) and computes the lower block triangle only.
 
-`value` is measured with the points resident in HBM; `e2e` with the points in pinned host memory,
-copied in every step (by the library, in 512-scan chunks on a copy stream, overlapped with the
-block-wise match of the chunks that have arrived) and the top-1 result copied out every step.
-Both go through ONE C-ABI call per step, sodso_sc_scans_to_loops.
+`value` is measured with the points resident in HBM; `e2e` with the points in pinned host memory, copied in every
+step (by the library, in 512-scan chunks on a copy stream, overlapped with binning and block-wise matching of the
+chunks that have arrived) and the result copied out every step.
+
+`--gpus N` also runs BASELINE configs[3] in the same process group, outside the headline timed region: a resident
+6 250 x N-row database, 1 000 queries streamed in batches of 128, top-8 -- reported as `config4`, with the sharded
+result compared to ONE GPU holding the whole database (`sharded_topk_identical_to_single_gpu`).
 """
 from __future__ import annotations
 
@@ -28,6 +34,11 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv:
+    # torch.distributed.run exports OMP_NUM_THREADS=1 for nproc > 1: the CPU arm must keep all host cores
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -37,10 +48,11 @@ N_SCANS = 5000
 N_PTS = 4096
 MASK_WIDTH = 100          # test_kitti.m:19
 P_WEIGHT = 2.0            # run_test.m:39
-TOPK = 8
 FLOP_PER_PAIR = 576000    # 2 channels x 120 variants x 1200 x 2
 EXEC_FLOP_PER_PAIR = 2 * (120 * 1920 + 120 * 960 // 4)   # what sc_match_tc_kernel issues, in bf16-rate equivalents
-SC_BYTES_PER_SCAN = 133888
+SC_BYTES_PER_SCAN = 133888                                # 4096 x 28 B in + 2 x 1200 x 8 B out
+C4_ROWS_PER_GPU, C4_QUERIES, C4_BATCH, C4_K = 6250, 1000, 128, 8    # BASELINE configs[3]
+GOLDEN = os.path.join(ROOT, "tests", "golden", "config2_oracle_decision.npz")
 
 
 def load_peaks():
@@ -101,6 +113,15 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the oracle restatement timed the way the reference times itself
 # ---------------------------------------------------------------------------------------------------
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        return max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
+    except Exception:
+        return None
+
+
 def cpu_sample(nq: int, hist_db: np.ndarray, xyz, inten, off, threads: int):
     """One bounded sample of the hot path on the host: SC generation of nq scans (test_sc.cpp:40-57),
     match of those nq queries against the whole DB (processSC.m:22-33, one BLAS dgemm per query like
@@ -123,6 +144,12 @@ def run_reference(args):
     from so_dso_place_recognition_b200 import synth
 
     threads = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=threads, user_api="blas")
+    except Exception:
+        pass
     nq = args.ref_queries
     xyz, inten, off = synth.make_scan_set(N_SCANS, N_PTS, planted_loops=True)
     hist = O.sc_generate(xyz, inten, off, nthreads=threads)     # DB signatures (untimed set-up)
@@ -131,6 +158,7 @@ def run_reference(args):
     t = [cpu_sample(nq, hist, xyz, inten, off, threads) for _ in range(args.steps)]
     dt = float(np.sum(t))
     value = nq * N_SCANS * args.steps / dt
+    bt = blas_threads()
     line = {
         "impl": "reference", "metric": "query x DB pair-distances/s (Scan Context generate+match+fuse)",
         "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -139,9 +167,10 @@ def run_reference(args):
         "config": {"workload": "5k-scan DB all-pairs ScanContext match, 4096 pts/scan (BASELINE configs[2])",
                    "n_db": N_SCANS, "pts_per_scan": N_PTS, "mask_width": MASK_WIDTH,
                    "sample": f"{nq} queries x {N_SCANS} DB per step"},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "blas_threads": bt, "kind": "port",
                          "sample": f"{nq} queries (generated + matched + fused) x {N_SCANS} DB per step, "
-                                   f"numpy/OpenBLAS dgemm per query as MATLAB does, {threads} threads"},
+                                   f"numpy/OpenBLAS dgemm per query as MATLAB does, {bt} BLAS threads, "
+                                   f"{threads} OpenMP threads for generation"},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -165,82 +194,53 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)       # control plane: barriers, max-over-ranks, set-up gathers
     ctx = api.default_context(local_rank)
+    sharded.init_comm(ctx)                                    # data plane: the library's own NCCL communicator
     peaks = load_peaks()
+    lib_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
-    # ---- synthetic scans: queries = set 0 (planted loops inside it); rank r's DB shard = set r
+    # ---- synthetic scans: shard r = scan set r; the queries are the scans of shard 0 (planted loops inside it)
     n_local = N_SCANS
+    n_global = n_local * world
     xyz_q, inten_q, off_q = synth.make_scan_set(N_SCANS, N_PTS, planted_loops=True, first=0)
     if rank == 0:
         xyz_d, inten_d, off_d = xyz_q, inten_q, off_q
     else:
         xyz_d, inten_d, off_d = synth.make_scan_set(N_SCANS, N_PTS, planted_loops=False, first=1_000_000 * rank)
-    n_global = n_local * world
-    row0 = rank * n_local
-
     pin = lambda a: torch.from_numpy(a).pin_memory()
     h_xyz, h_inten, h_off = pin(xyz_d), pin(inten_d), pin(off_d)
     d_xyz, d_inten, d_off = h_xyz.to(dev), h_inten.to(dev), h_off.to(dev)
+    qa, qn = sharded.shard_rows(N_SCANS, world, rank)          # this rank's slice of the query scans (e2e leg, N > 1)
     if rank == 0:
-        hq_xyz, hq_inten, dq_xyz, dq_inten = h_xyz, h_inten, d_xyz, d_inten
+        dq = (d_xyz, d_inten, d_off)
     else:
-        hq_xyz, hq_inten = pin(xyz_q), pin(inten_q)
-        dq_xyz, dq_inten = hq_xyz.to(dev), hq_inten.to(dev)
-    h2d_bytes = (h_xyz.numel() * 8 + h_inten.numel() * 4 + h_off.numel() * 8)
-    if world > 1:   # + this rank's 1/N slice of the replicated query scans
-        h2d_bytes += (hq_xyz.numel() * 8 + hq_inten.numel() * 4) // world
-
-    kern_ms = []
-    db_kernel_ms = [0.0]
-    _orig_match = api.SignatureDB.match
-
-    def _timed_match(self, h):
-        _orig_match(self, h)
-        db_kernel_ms[0] = ctx.last_kernel_ms
-
-    api.SignatureDB.match = _timed_match
-    shard_db = [None]
+        dq = tuple(torch.from_numpy(a).to(dev) for a in (xyz_q, inten_q, off_q))
+    pa, pb = int(off_q[qa]), int(off_q[qa + qn])
+    hq_slice = (pin(xyz_q[pa:pb]), pin(inten_q[pa:pb]), pin(np.ascontiguousarray(off_q[qa:qa + qn + 1] - off_q[qa])))
+    h2d_bytes = h_xyz.numel() * 8 + h_inten.numel() * 4 + h_off.numel() * 8
     if world > 1:
-        shard_db[0] = api.SignatureDB("sc", api.sc_generate(d_xyz, d_inten, d_off, ctx=ctx), global_row0=row0, ctx=ctx)
-        qa, qb = rank * N_SCANS // world, (rank + 1) * N_SCANS // world
-        hq_off_slices = {rank: pin(np.ascontiguousarray(off_q[qa:qb + 1] - off_q[qa]))}
-        dq_off_slice = hq_off_slices[rank].to(dev)
+        h2d_bytes += hq_slice[0].numel() * 8 + hq_slice[1].numel() * 4 + hq_slice[2].numel() * 8
+    d2h_bytes = N_SCANS * 4 * 8                                  # idx, score, d_p, d_i of the top-1
+
+    shard_db = api.SignatureDB("sc", api.sc_generate(d_xyz, d_inten, d_off, ctx=ctx), global_row0=rank * n_local, ctx=ctx)
+    kern_ms = []
 
     def step(host_inputs: bool):
-        """one pass of the hot path; returns (idx, score) of the top-1 on the host"""
-        if world == 1:
-            # one C-ABI call: scans in -> loop candidates out (test_sc.cpp:36-57 + run_test.m:25-57, self-match).
-            # HOST point buffers are streamed in chunks by the library, overlapped with binning and matching.
-            if host_inputs:
-                idx, score = api.sc_scans_to_loops(h_xyz, h_inten, h_off, MASK_WIDTH, P_WEIGHT, ctx=ctx)
-                return torch.from_numpy(idx), torch.from_numpy(score)
-            idx, score = api.sc_scans_to_loops(d_xyz, d_inten, d_off, MASK_WIDTH, P_WEIGHT, ctx=ctx, host_out=True)
+        """one pass of the hot path = one C-ABI call; returns the top-1 (idx, score) on the host"""
+        if world == 1 or (rank == 0 and not host_inputs):
+            # the queries are this rank's own scans: same buffers, copied and binned once
+            src = (h_xyz, h_inten, h_off) if host_inputs else (d_xyz, d_inten, d_off)
+            r = shard_db.scans_query_sharded(*src, N_SCANS, 0, "same", 0, MASK_WIDTH, P_WEIGHT, 1)
+        elif host_inputs:
+            # every rank copies in its shard + its 1/N slice of the query scans; the slices are binned where they
+            # land and exchanged as signatures over NVLink (NCCL, inside the library)
+            r = shard_db.scans_query_sharded(*hq_slice, N_SCANS, qa, (h_xyz, h_inten, h_off), 0, MASK_WIDTH, P_WEIGHT, 1)
+        else:
+            r = shard_db.scans_query_sharded(*dq, N_SCANS, 0, (d_xyz, d_inten, d_off), 0, MASK_WIDTH, P_WEIGHT, 1)
+        if not host_inputs:
             kern_ms.append(ctx.last_kernel_ms)
-            return torch.from_numpy(idx), torch.from_numpy(score)
-        # ---- N > 1.  Queries: every rank bins 1/N of the replicated query scans, the signatures are all-gathered
-        # over NVLink.  DB: the rank's shard is a resident sodso_db whose operand buffers are rewritten every step.
-        qa, qb = rank * N_SCANS // world, (rank + 1) * N_SCANS // world
-        pa, pb = int(off_q[qa]), int(off_q[qb])
-        hist_slice = torch.empty((qb - qa, 2400), dtype=torch.float64, device=dev)
-        if host_inputs:
-            api.N.check(api.N.lib().sodso_sc_generate(ctx.handle, hq_xyz[pa:pb].data_ptr(), hq_inten[pa:pb].data_ptr(),
-                                                      hq_off_slices[rank].data_ptr(), qb - qa, 45.0, hist_slice.data_ptr()))
-        else:
-            hist_slice = api.sc_generate(dq_xyz[pa:pb], dq_inten[pa:pb], dq_off_slice, ctx=ctx)
-        hist_q = sharded.gather_query_signatures(hist_slice)
-        if host_inputs:
-            # HOST point buffers of the shard: streamed in chunks, binned and matched as they land
-            shard_db[0].stream_match(h_xyz, h_inten, h_off, hist_q)
-        else:
-            hist_db = api.sc_generate(d_xyz, d_inten, d_off, ctx=ctx)
-            shard_db[0].reload(hist_db)
-            shard_db[0].match(hist_q)
-        # stats all-reduce + per-shard top-k all-gather + merge (so_dso_place_recognition_b200/sharded.py)
-        mi, ms, mp, md = sharded.sharded_query(shard_db[0], hist_q, n_global, 0, MASK_WIDTH, P_WEIGHT, TOPK, device=dev,
-                                               already_matched=True)
-        kern_ms.append(db_kernel_ms[0])
-        return torch.from_numpy(mi[:, 0]), torch.from_numpy(ms[:, 0])
+        return r[0][:, 0], r[1][:, 0]
 
     def sync_all():
         torch.cuda.synchronize()
@@ -248,21 +248,18 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(host_inputs: bool, steps: int):
+    def timed(fn, steps: int):
+        """K calls bracketed by barrier + synchronize on both sides, CUDA events on the library stream, max over ranks"""
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        st = torch.cuda.ExternalStream(ctx.stream or 0, device=dev) if ctx.stream else torch.cuda.current_stream()
         t0 = time.perf_counter()
-        e0.record(st)
+        e0.record(lib_stream)
         for _ in range(steps):
-            out = step(host_inputs)
-        e1.record(st)
+            out = fn()
+        e1.record(lib_stream)
         sync_all()
         wall = time.perf_counter() - t0
-        ms = max(e0.elapsed_time(e1), 0.0)
-        # the API is host-synchronous per call; events on the library stream bracket the same work
-        ms = max(ms, 0.0)
-        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
+        t = torch.tensor([e0.elapsed_time(e1), wall * 1e3], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1]), out
@@ -274,56 +271,90 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ms_dev, wall_dev, out = timed(False, args.steps)
+    ms_dev, wall_dev, out = timed(lambda: step(False), args.steps)
     launches = ctx.launch_count - l0
     clk = clocks.stop() if rank == 0 else None
     k_ms = float(np.mean(kern_ms))
     for _ in range(2):
         step(True)
-    ms_e2e, wall_e2e, out2 = timed(True, args.steps)
+    ms_e2e, wall_e2e, out2 = timed(lambda: step(True), args.steps)
 
-    # for reference (outside every timed region): what the host -> HBM copy of one step's points costs on its own
-    copy_ms = None
-    if rank == 0:
+    # for reference (outside every timed region): what the host -> HBM copy of one step's points costs on its own,
+    # on this rank alone and with all ranks copying at the same time (the host memory system is shared)
+    def copy_alone():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         scratch = [torch.empty_like(d_xyz), torch.empty_like(d_inten)]
-        torch.cuda.synchronize()
         best = []
         for _ in range(3):
+            sync_all()
             ev0.record()
             scratch[0].copy_(h_xyz, non_blocking=True)
             scratch[1].copy_(h_inten, non_blocking=True)
             ev1.record()
             torch.cuda.synchronize()
             best.append(ev0.elapsed_time(ev1))
-        copy_ms = min(best)
-        del scratch
+        t = torch.tensor([min(best)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
 
-    pairs_step = N_SCANS * n_global            # all ranks together
-    # fraction of the (query group, DB tile) items the match kernel executes: at N = 1 the step is a self-match and only
-    # the lower block triangle is computed, the transposed values are stored (sc_match_tc.cu, launch_sc_match_tc_self)
-    symmetric = world == 1 and os.environ.get("SODSO_SC_SYMMETRY", "1") != "0"
-    if symmetric:
-        groups, tiles = (N_SCANS + 3) // 4, (N_SCANS + 255) // 256
-        exec_frac = sum(min((4 * g + 3) // 256 + 1, tiles) for g in range(groups)) / (groups * tiles)
-    else:
-        exec_frac = 1.0
-    idx = out[0].numpy()
+    copy_ms = copy_alone()
+
+    idx = out[0]
     expect = (np.arange(N_SCANS) + N_SCANS // 2) % N_SCANS
     agree = float((idx == expect).mean())
-    same_e2e = bool(np.array_equal(idx, out2[0].numpy()))
-    # like-for-like reference for the N > 1 lines (whose operands are distinct, so every pair is computed): the same N = 1
-    # step with the self-match symmetry switched off, a few steps, outside the reported numbers
-    general = None
-    if symmetric:
-        os.environ["SODSO_SC_SYMMETRY"] = "0"
-        step(False)
-        ms_gen, _, out3 = timed(False, 3)
-        del os.environ["SODSO_SC_SYMMETRY"]
-        general = {"value": pairs_step * 3 / (ms_gen * 1e-3), "ms_per_step": ms_gen / 3,
-                   "top1_identical": bool(np.array_equal(idx, out3[0].numpy()))}
+    same_e2e = bool(np.array_equal(idx, out2[0]))
+    oracle_check = None
+    if world == 1 and os.path.exists(GOLDEN):
+        g = np.load(GOLDEN)
+        oracle_check = {"top1_identical_to_oracle": bool(np.array_equal(idx, g["sc_idx"])),
+                        "max_abs_score_diff": float(np.max(np.abs(out[1] - g["sc_score"]))),
+                        "oracle": "tests/golden/config2_oracle_decision.npz (CPU restatement, all 25e6 pairs)"}
 
+    # ---- generation kernel on its own (BASELINE configs[1] and the 5 000-scan set), device-resident
+    gen = None
     if rank == 0:
+        gen = {}
+        for tag, ns in (("configs1_1000_scans", 1000), ("5000_scans", N_SCANS)):
+            o = d_off[:ns + 1]
+            tms = []
+            for _ in range(7):
+                api.sc_generate(d_xyz[:ns * N_PTS], d_inten[:ns * N_PTS], o, ctx=ctx)
+                tms.append(ctx.last_kernel_ms)
+            t_ms = float(np.median(tms[2:]))
+            gen[tag] = {"kernel_ms": t_ms, "achieved": ns * SC_BYTES_PER_SCAN / (t_ms * 1e-3) / 1e9, "unit": "GB/s",
+                        "frac": ns * SC_BYTES_PER_SCAN / (t_ms * 1e-3) / 1e9 / peaks["hbm"], "scans_per_s": ns / (t_ms * 1e-3)}
+
+    # ---- N = 1: the single-GPU self-match API (symmetry exploited), as a named sub-record
+    self_match = None
+    if world == 1:
+        def sm(host):
+            a = (h_xyz, h_inten, h_off) if host else (d_xyz, d_inten, d_off)
+            return api.sc_scans_to_loops(*a, MASK_WIDTH, P_WEIGHT, ctx=ctx, host_out=True)
+        for _ in range(3):
+            sm(False)
+        ms_s, _, o_s = timed(lambda: sm(False), args.steps)
+        ks = ctx.last_kernel_ms
+        sm(True)
+        ms_se, _, o_se = timed(lambda: sm(True), args.steps)
+        groups, tiles = (N_SCANS + 3) // 4, (N_SCANS + 255) // 256
+        exec_frac = sum(min((4 * g + 3) // 256 + 1, tiles) for g in range(groups)) / (groups * tiles)
+        pairs = N_SCANS * N_SCANS
+        self_match = {"api": "sodso_sc_scans_to_loops", "value": pairs * args.steps / (ms_s * 1e-3), "unit": "pairs/s",
+                      "ms_per_step": ms_s / args.steps, "e2e_value": pairs * args.steps / (ms_se * 1e-3),
+                      "e2e_ms_per_step": ms_se / args.steps, "match_kernel_ms": ks,
+                      "executed_pair_fraction": exec_frac,
+                      "frac_executed": exec_frac * pairs * EXEC_FLOP_PER_PAIR / (ks * 1e-3) / 1e12 / peaks["tf"],
+                      "top1_identical_to_general_path": bool(np.array_equal(o_s[0], idx)),
+                      "e2e_top1_identical": bool(np.array_equal(o_se[0], idx))}
+
+    # ---- BASELINE configs[3]: resident sharded DB, streaming query batches, top-8
+    config4 = run_config4(ctx, dev, world, rank, local_rank)
+
+    pairs_step = N_SCANS * n_global            # all ranks together
+    if rank == 0:
+        achieved = N_SCANS * n_local * FLOP_PER_PAIR / (k_ms * 1e-3) / 1e12
+        executed = N_SCANS * n_local * EXEC_FLOP_PER_PAIR / (k_ms * 1e-3) / 1e12
         line = {
             "metric": "query x DB pair-distances/s (Scan Context generate+match+fuse)",
             "value": pairs_step * args.steps / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": world,
@@ -332,45 +363,186 @@ def run_ours(args):
             "dtype": "match: fp16 3-term split (structure) + e2m1 exact counts (binary intensity), fp32 accumulate in TMEM; generation: f64", "data": "synthetic",
             "config": {"workload": "5k-scan DB all-pairs ScanContext match, 4096 pts/scan (BASELINE configs[2])",
                        "n_queries": N_SCANS, "n_db_per_gpu": n_local, "n_db_total": n_global, "pts_per_scan": N_PTS,
-                       "variants_per_pair": 120, "mask_width": MASK_WIDTH, "topk": 1 if world == 1 else TOPK,
-                       "sharding": "DB rows" if world > 1 else "none",
-                       "self_match_symmetry": ("used: queries and DB are the same scans, d(i,j) = d(j,i); "
-                                               f"{exec_frac:.3f} of the pair tiles are computed, the rest mirrored")
-                       if symmetric else "not applicable: the replicated queries are not the rank's DB shard"
-                       if world > 1 else "off",
-                       "every_pair_computed": general,
+                       "variants_per_pair": 120, "mask_width": MASK_WIDTH, "topk": 1,
+                       "sharding": "DB rows, 5000 per GPU; queries = the scans of shard 0",
+                       "path": "sodso_db_scans_query_sharded at every N: every (query, DB row) pair is computed "
+                               "(general match kernel); collectives = NCCL inside the library, on its stream",
                        "l2": "operands per step (DB 89 MB + queries 346 MB + distances 200 MB) exceed the 126 MB L2",
-                       "planted_loop_top1_recovered": agree, "e2e_top1_identical": same_e2e},
+                       "planted_loop_top1_recovered": agree, "e2e_top1_identical": same_e2e,
+                       "oracle_check": oracle_check},
             "e2e": {"value": pairs_step * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s",
-                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(N_SCANS * 12),
-                    "ms_per_step": ms_e2e / args.steps, "h2d_copy_alone_ms": copy_ms},
+                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                    "ms_per_step": ms_e2e / args.steps, "h2d_copy_alone_ms_all_ranks_concurrent": copy_ms},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "sc_match_tc_kernel",
-                         "achieved": N_SCANS * n_local * FLOP_PER_PAIR / (k_ms * 1e-3) / 1e12,
-                         "peak": peaks["tf"], "unit": "TFLOP/s",
-                         "frac": N_SCANS * n_local * FLOP_PER_PAIR / (k_ms * 1e-3) / 1e12 / peaks["tf"],
+                         "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": achieved / peaks["tf"],
                          "traffic": load_traffic(), "peak_source": peaks["src"] + " bf16 burst",
                          "peak_sustained": peaks["tf_sus"],
-                         "frac_of_sustained": (N_SCANS * n_local * FLOP_PER_PAIR / (k_ms * 1e-3) / 1e12 / peaks["tf_sus"])
-                         if peaks["tf_sus"] else None,
-                         "kernel_ms": k_ms,
-                         "executed_tflops_bf16_equiv": exec_frac * N_SCANS * n_local * EXEC_FLOP_PER_PAIR / (k_ms * 1e-3) / 1e12,
-                         "frac_executed": exec_frac * N_SCANS * n_local * EXEC_FLOP_PER_PAIR / (k_ms * 1e-3) / 1e12 / peaks["tf"],
-                         "executed_pair_fraction": exec_frac,
+                         "frac_of_sustained": achieved / peaks["tf_sus"] if peaks["tf_sus"] else None,
+                         "kernel_ms": k_ms, "pairs_per_launch": N_SCANS * n_local,
+                         "executed_tflops_bf16_equiv": executed, "frac_executed": executed / peaks["tf"],
                          "note": "achieved/frac use the ALGORITHMIC 576 kFLOP/pair of the direct method (2 channels x 120 variants x "
                                  "1200 MACs, SURVEY 8d).  The kernel gets the same 120 variants from two half-size contractions "
                                  "(E = corr[s]+corr[s+30], O = corr[s]-corr[s+30], max = max(E+|O|)/2), so frac can exceed 1.  "
-                                 "Executed tensor work per pair in bf16-rate equivalents: structure 3-term fp16 split 120 x 1920 "
-                                 "MACs + intensity e2m1 (kind::mxf4, 4x rate) 120 x 960 / 4 MACs = 518 kFLOP, times the fraction "
-                                 "of pair tiles executed (self-match symmetry at N = 1) -> frac_executed; "
-                                 "MMA N = 240 = 2 bases x 30 shifts x 4 interleaved queries"},
+                                 "frac_executed counts the tensor work actually issued per pair in bf16-rate equivalents: structure "
+                                 "3-term fp16 split 120 x 1920 MACs + intensity e2m1 (kind::mxf4, 4x rate) 120 x 960 / 4 MACs = "
+                                 "518 kFLOP; MMA N = 240 = 2 bases x 30 shifts x 4 interleaved queries"},
+            "roofline_generate": {"bound": "hbm", "kernel": "sc_generate_kernel", "peak": peaks["hbm"],
+                                  "bytes_per_scan": SC_BYTES_PER_SCAN, **(gen or {})},
+            "self_match": self_match,
+            "config4": config4,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line))
+    shard_db.close()
+    ctx.comm_finalize()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def run_config4(ctx, dev, world, rank, local_rank):
+    """BASELINE configs[3]: a resident database of 6 250 x N Scan Context signatures row-sharded over the N GPUs,
+    1 000 queries (revisits of database places) streamed in batches of 128, top-8 per query through
+    sodso_db_query_sharded.  Returns the record rank 0 prints (None on other ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    from so_dso_place_recognition_b200 import api, synth
+
+    nl, m, B, k = C4_ROWS_PER_GPU, C4_QUERIES, C4_BATCH, C4_K
+    n = nl * world
+    base = 2_000_000
+    xyz, inten, off = synth.make_scan_set(nl, N_PTS, planted_loops=False, first=base + rank * nl)
+    to = lambda a: torch.from_numpy(a).to(dev)
+    hist_db = api.sc_generate(to(xyz), to(inten), to(off), ctx=ctx)            # this rank's shard, (nl x 2400) in HBM
+    del xyz, inten
+    # queries: revisits (yaw rotation, jitter, 10 % resampled points) of database places spread over all shards
+    src = (np.arange(m, dtype=np.int64) * n) // m + 7
+    qx = np.empty((m * N_PTS, 3))
+    qi = np.empty(m * N_PTS, dtype=np.float32)
+    for j in range(m):
+        p, it = synth.make_scan(base + int(src[j]), N_PTS)
+        p, it = synth.revisit(p, it, base + 9_000_000 + j)
+        qx[j * N_PTS:(j + 1) * N_PTS], qi[j * N_PTS:(j + 1) * N_PTS] = p, it
+    qoff = np.arange(m + 1, dtype=np.int64) * N_PTS
+    hq = api.sc_generate(to(qx), to(qi), to(qoff), ctx=ctx)                    # (m x 2400) in HBM, replicated
+    db = api.SignatureDB("sc", hist_db, global_row0=rank * nl, ctx=ctx)
+    batches = [(b, min(b + B, m)) for b in range(0, m, B)]
+    q_row0 = n                                                                 # the queries are newer than every DB row
+    lib_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def maxr(v):
+        t = torch.tensor(v, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    # (1) latency mode: one call per batch, results copied to the host (one synchronisation per batch)
+    def latency_pass():
+        res = []
+        for a, b in batches:
+            hb = hq[a:b]
+            o = (np.empty((b - a, k), dtype=np.int64),) + tuple(np.empty((b - a, k)) for _ in range(3))
+            res.append(db.query_sharded(hb, q_row0 + a, MASK_WIDTH, P_WEIGHT, k, out=o))
+        return res
+
+    # (2) throughput mode: device outputs, all batches enqueued back to back, one synchronisation at the end
+    outs = [(torch.empty((b - a, k), dtype=torch.int64, device=dev),) +
+            tuple(torch.empty((b - a, k), dtype=torch.float64, device=dev) for _ in range(3)) for a, b in batches]
+
+    def pipelined_pass():
+        for (a, b), o in zip(batches, outs):
+            db.query_sharded(hq[a:b], q_row0 + a, MASK_WIDTH, P_WEIGHT, k, out=o)
+        ctx.sync()
+
+    for _ in range(3):
+        res = latency_pass()
+        pipelined_pass()
+    reps = 5
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        res = latency_pass()
+    sync_all()
+    lat_ms = (time.perf_counter() - t0) * 1e3 / reps
+    kern_ms = ctx.last_kernel_ms                                    # match kernel of the last (ragged) batch
+    sync_all()
+    e0.record(lib_stream)
+    for _ in range(reps):
+        pipelined_pass()
+    e1.record(lib_stream)
+    sync_all()
+    pipe_ms = e0.elapsed_time(e1) / reps
+    lat_ms, pipe_ms = maxr([lat_ms, pipe_ms])
+    # match kernel of one full batch on its own
+    db.match(hq[:B])
+    kern_full_ms = ctx.last_kernel_ms
+    # the local part of a batch (match + statistics + top-k, no collectives, no merge): the same entry point on a
+    # context without a communicator
+    ctx1 = api.Context(local_rank)
+    db1 = api.SignatureDB("sc", hist_db, global_row0=rank * nl, ctx=ctx1)
+    o1 = (torch.empty((B, k), dtype=torch.int64, device=dev),) + tuple(torch.empty((B, k), dtype=torch.float64, device=dev)
+                                                                      for _ in range(3))
+    s1 = torch.cuda.ExternalStream(ctx1.stream, device=dev)
+    for _ in range(3):
+        db1.query_sharded(hq[:B], q_row0, MASK_WIDTH, P_WEIGHT, k, out=o1)
+    ctx1.sync()
+    sync_all()
+    e0.record(s1)
+    for _ in range(8 * reps):
+        db1.query_sharded(hq[:B], q_row0, MASK_WIDTH, P_WEIGHT, k, out=o1)
+    e1.record(s1)
+    ctx1.sync()
+    local_ms = maxr([e0.elapsed_time(e1) / (8 * reps)])[0]
+    db1.close()
+
+    idx = np.concatenate([r[0] for r in res])
+    score = np.concatenate([r[1] for r in res])
+    pipe_idx = torch.cat([o[0] for o in outs]).cpu().numpy()
+    # ---- identity check: rank 0 holds ALL signatures and answers the same queries alone (no communicator)
+    if world > 1:
+        parts = [torch.empty_like(hist_db) for _ in range(world)]
+        dist.all_gather(parts, hist_db)
+        hist_all = torch.cat(parts) if rank == 0 else None
+        del parts
+    else:
+        hist_all = hist_db
+    rec = None
+    if rank == 0:
+        dbf = api.SignatureDB("sc", hist_all, global_row0=0, ctx=ctx1)
+        ref = [dbf.query_sharded(hq[a:b].cpu().numpy(), q_row0 + a, MASK_WIDTH, P_WEIGHT, k) for a, b in batches]
+        dbf.close()
+        ridx = np.concatenate([r[0] for r in ref])
+        rscore = np.concatenate([r[1] for r in ref])
+        nb = len(batches)
+        rec = {"workload": f"{n}-row Scan Context DB row-sharded over {world} GPU(s) ({nl} rows per GPU, resident), "
+                           f"{m} queries streamed in batches of {B}, top-{k} (BASELINE configs[3])",
+               "n_db_total": n, "queries": m, "batch": B, "k": k,
+               "pairs_s": m * n / (pipe_ms * 1e-3), "ms_per_batch": pipe_ms / nb,
+               "pairs_s_one_call_per_batch_host_results": m * n / (lat_ms * 1e-3), "ms_per_batch_latency_mode": lat_ms / nb,
+               "match_kernel_ms_per_full_batch": kern_full_ms, "local_part_ms_per_full_batch": local_ms,
+               "collective_ms": max(pipe_ms / nb - local_ms * (m / B) / nb, 0.0),
+               "sharded_topk_identical_to_single_gpu": bool(np.array_equal(idx, ridx)),
+               "pipelined_identical_to_per_batch": bool(np.array_equal(idx, pipe_idx)),
+               "max_abs_score_diff_vs_single_gpu": float(np.nanmax(np.abs(score - rscore))),
+               "revisit_is_top1": float((ridx[:, 0] == src).mean()),
+               "note": "pairs_s / ms_per_batch: device-resident query signatures, device outputs, all batches enqueued, one "
+                       "synchronisation (CUDA events on the library stream, max over ranks); *_latency_mode: one call per "
+                       "batch with the k-lists copied to the host (wall clock, max over ranks); collective_ms = "
+                       "ms_per_batch - the same batch on a context without a communicator (match + statistics + top-k)"}
+    db.close()
+    ctx1.close()
+    return rec
 
 
 def load_traffic():
@@ -396,9 +568,10 @@ def cpu_baseline(args):
     while t < 10.0 and reps < 20:
         t += cpu_sample(nq, hist, xyz, inten, off, threads)
         reps += 1
-    return {"value": nq * N_SCANS * reps / t, "unit": "pairs/s", "cores": threads, "kind": "port",
+    bt = blas_threads()
+    return {"value": nq * N_SCANS * reps / t, "unit": "pairs/s", "cores": threads, "blas_threads": bt, "kind": "port",
             "sample": f"{reps} x ({nq} queries generated+matched+fused against the {N_SCANS}-scan DB), "
-                      f"oracle restatement, numpy/OpenBLAS dgemm per query as MATLAB does, {threads} threads"}
+                      f"oracle restatement, numpy/OpenBLAS dgemm per query as MATLAB does, {bt} BLAS threads"}
 
 
 def main():

@@ -281,6 +281,11 @@ int sodso_db_finish_sharded(sodso_db *db, int64_t q_global_row0, int mask_width,
  *    m_total % R ranks one more) and the signatures (19 KB per scan instead of 115 KB of points) are exchanged by NCCL;
  *  - shard: db_xyz / db_inten / db_off non-NULL: the shard's n_local scans are binned and its operand is rewritten in
  *    place, streamed chunk-wise from HOST buffers as in sodso_db_stream_match; NULL: the resident operand is used;
+ *    If the query pointers ARE the shard pointers (q_xyz == db_xyz, q_inten == db_inten, q_off == db_off, m_slice ==
+ *    m_total == n_local: on this rank the queries are the shard's own scans, the KITTI self-match of test_kitti.m:28)
+ *    the scans are copied and binned once and matched block-wise while they stream in.  Unlike
+ *    sodso_sc_scans_to_loops the sharded entry points compute every pair (the mirrored half of a self-match triangle
+ *    does not exist for the other ranks' shards);
  *  - then as sodso_db_query_sharded.  q_hist (optional, m_total x 2400): the query signatures. */
 int sodso_db_scans_query_sharded(sodso_db *db, const double *db_xyz, const float *db_inten, const int64_t *db_off,
                                  const double *q_xyz, const float *q_inten, const int64_t *q_off, int m_total,

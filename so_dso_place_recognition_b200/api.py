@@ -559,15 +559,19 @@ class SignatureDB:
                             mask_width=100, p_weight=2.0, k=8, max_rho=45.0, want_hist=False, host_out=True):
         """sodso_db_scans_query_sharded: one step of the sharded pipeline from points (collective).
         q_*: this rank's slice [q_first, q_first + m_slice) of the m_total query scans (all of them: no exchange);
-        db_scans: None (resident operand) or (xyz, inten, off) of the shard's scans (rebuilt in place, streamed from
-        host buffers).  -> (idx, score, d_p, d_i [, q_hist])"""
+        db_scans: None (resident operand), (xyz, inten, off) of the shard's scans (rebuilt in place, streamed from
+        host buffers), or "same": the shard's scans ARE the query scans (same buffers: copied and binned once).
+        -> (idx, score, d_p, d_i [, q_hist])"""
         q_xyz = _prep(q_xyz, np.float64, "float64")
         q_inten = _prep(q_inten, np.float32, "float32")
         q_off = _prep(q_off, np.int64, "int64")
         m_slice = int(q_off.shape[0]) - 1
         dev_like = q_xyz if (_is_torch(q_xyz) and q_xyz.is_cuda) else None
         dx = di_ = do = None
-        if db_scans is not None:
+        if isinstance(db_scans, str):
+            assert db_scans == "same" and m_slice == int(m_total) == self.n
+            dx, di_, do = q_xyz, q_inten, q_off
+        elif db_scans is not None:
             dx, di_, do = (_prep(db_scans[0], np.float64, "float64"), _prep(db_scans[1], np.float32, "float32"),
                            _prep(db_scans[2], np.int64, "int64"))
             assert do.shape[0] - 1 == self.n

@@ -1140,7 +1140,12 @@ int sodso_db_reload(sodso_db *db, const double *hist2) {
 // The query operand (db->q_op, m rows) must already be enqueued on the context's stream; nothing is synchronised.
 }  // extern "C"
 namespace sodso {
-int db_stream_match_async(sodso_db *db, const double *xyz, const float *inten, const int64_t *off, double max_rho, int m) {
+int db_stream_match_async(sodso_db *db, const double *xyz, const float *inten, const int64_t *off, double max_rho, int m,
+                          bool self, double *hist_dev) {
+  // self: the m == n queries ARE the shard's scans (same buffers): they are binned once, both operands are filled
+  // chunk by chunk and every chunk is matched as an L-shaped region (new queries x all DB rows so far, old queries x
+  // new DB rows).  Every pair is computed: the sharded entry points never use the self-match triangle, whose mirrored
+  // half does not exist for the other ranks' shards.
   sodso_ctx *c = db->ctx;
   const int n = db->n;
   int rc;
@@ -1150,7 +1155,13 @@ int db_stream_match_async(sodso_db *db, const double *xyz, const float *inten, c
   const bool host_pts = !is_device_ptr(xyz) && !is_device_ptr(inten) && !is_device_ptr(off);
   const int CH = 512;
   const bool streamed = host_pts && n >= std::max(c->stream_min_scans, 2 * CH);
-  const int nchunk = streamed ? (n + CH - 1) / CH : 1;
+  // chunk boundaries (multiples of the 256-row DB tile).  self: two 256-scan chunks first, the work that can be done
+  // grows with the square of what has arrived
+  std::vector<int> bounds{0};
+  if (streamed)
+    for (int b = self ? 256 : CH; b < n; b += (self && b < 512) ? 256 : CH) bounds.push_back(b);
+  bounds.push_back(n);
+  const int nchunk = (int)bounds.size() - 1;
   const double *xd = xyz;
   const float *id = inten;
   const int64_t *od;
@@ -1161,12 +1172,19 @@ int db_stream_match_async(sodso_db *db, const double *xyz, const float *inten, c
     id = c->in_inten.as<float>();
   }
   if ((rc = stage_in(c, off, (size_t)n + 1, c->in_off, &od))) return rc;
-  SODSO_CUDA_CHECK(c->out_hist.reserve((size_t)n * 2 * SC_SIZE * sizeof(double)));
-  double *hd = c->out_hist.as<double>();
+  double *hd = hist_dev;
+  if (!hd) {
+    SODSO_CUDA_CHECK(c->out_hist.reserve((size_t)n * 2 * SC_SIZE * sizeof(double)));
+    hd = c->out_hist.as<double>();
+  }
   const size_t cnt = (size_t)m * n;
   SODSO_CUDA_CHECK(db->dp.reserve(cnt * 4));
   SODSO_CUDA_CHECK(db->di.reserve(cnt * 4));
   SODSO_CUDA_CHECK(launch_sc_tc_clear_flags(db->op.p, c->stream));
+  if (self) {
+    SODSO_CUDA_CHECK(db->q_op.reserve(sc_tc_query_bytes(m)));
+    SODSO_CUDA_CHECK(launch_sc_tc_clear_flags(db->q_op.p, c->stream));
+  }
   // events of the chunk copies: destroyed on every exit path
   struct Events {
     std::vector<cudaEvent_t> v;
@@ -1176,7 +1194,7 @@ int db_stream_match_async(sodso_db *db, const double *xyz, const float *inten, c
     }
   } evs;
   auto enqueue_copy = [&](int k) -> cudaError_t {   // chunk k of the host buffers -> HBM, on the copy stream
-    const int s0 = k * CH, s1 = std::min(n, s0 + CH);
+    const int s0 = bounds[k], s1 = bounds[k + 1];
     const int64_t p0 = off[s0], p1 = off[s1];
     cudaError_t e = cudaSuccess;
     if (p1 > p0) {
@@ -1206,11 +1224,11 @@ int db_stream_match_async(sodso_db *db, const double *xyz, const float *inten, c
     SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_xyz.p, xyz, (size_t)total * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     SODSO_CUDA_CHECK(cudaMemcpyAsync(c->in_inten.p, inten, (size_t)total * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   }
-  const int n_pad = sc_tc_db_rows_padded(db->cap);
+  const int n_pad = sc_tc_db_rows_padded(db->cap), m_pad = sc_tc_query_rows_padded(m);
   c->kname = "sc_match_tc_kernel";
   c->ev_valid = false;
   for (int k = 0; k < nchunk; k++) {
-    const int s0 = streamed ? k * CH : 0, s1 = streamed ? std::min(n, s0 + CH) : n;
+    const int s0 = bounds[k], s1 = bounds[k + 1];
     const bool last = k == nchunk - 1;
     cudaError_t e = cudaSuccess;
     if (streamed && !last) e = enqueue_copy(k + 1);
@@ -1220,10 +1238,17 @@ int db_stream_match_async(sodso_db *db, const double *xyz, const float *inten, c
                              &c->launches);
     if (e == cudaSuccess)
       e = launch_sc_tc_prep_db_rows(hd, n, s0, last ? n_pad : s1, db->op.p, c->stream, &c->launches, db->cap);
+    if (self && e == cudaSuccess)
+      e = launch_sc_tc_prep_query_rows(hd, m, s0, last ? m_pad : s1, db->q_op.p, c->stream, &c->launches);
     if (!streamed && e == cudaSuccess) c->ev_valid = cudaEventRecord(c->ev0, c->stream) == cudaSuccess;
-    if (e == cudaSuccess)
-      e = launch_sc_match_tc_blocks(db->q_op.p, m, db->op.p, n, 0, m, s0, s1, 0, 0, 0, 0, db->dp.as<float>(),
-                                    db->di.as<float>(), n, c->num_sms, c->stream, &c->launches, db->cap);
+    if (e == cudaSuccess) {
+      if (self)
+        e = launch_sc_match_tc_blocks(db->q_op.p, m, db->op.p, n, s0, s1, 0, s1, 0, s0, s0, s1, db->dp.as<float>(),
+                                      db->di.as<float>(), n, c->num_sms, c->stream, &c->launches, db->cap);
+      else
+        e = launch_sc_match_tc_blocks(db->q_op.p, m, db->op.p, n, 0, m, s0, s1, 0, 0, 0, 0, db->dp.as<float>(),
+                                      db->di.as<float>(), n, c->num_sms, c->stream, &c->launches, db->cap);
+    }
     if (!streamed && c->ev_valid) c->ev_valid = cudaEventRecord(c->ev1, c->stream) == cudaSuccess;
     if (e != cudaSuccess) {
       set_error(std::string("db_stream_match: ") + cudaGetErrorString(e));
@@ -1256,7 +1281,7 @@ int sodso_db_stream_match(sodso_db *db, const double *xyz, const float *inten, c
   const double *hq;
   if ((rc = stage_in(c, hist1, (size_t)m * 2 * SC_SIZE, db->q_in, &hq))) return rc;
   if ((rc = sc_prepare(c, db->op_algo, hq, m, db->q_op, false))) return rc;
-  if ((rc = db_stream_match_async(db, xyz, inten, off, max_rho, m))) return rc;
+  if ((rc = db_stream_match_async(db, xyz, inten, off, max_rho, m, false, nullptr))) return rc;
   return sync_ctx(c);
 }
 

@@ -139,7 +139,8 @@ int check_offsets_host(const int64_t *off, int nscan, int64_t *total);
 int sc_prepare(sodso_ctx *c, int algo, const double *hist_dev, int rows, Buf &op, bool is_db);
 int db_match_async(sodso_db *db, const double *hist1, int m);   // sodso_db_match without the final synchronisation
 int db_match_prepared_async(sodso_db *db, int m);               // Scan Context: db->q_op already holds the m queries
-int db_stream_match_async(sodso_db *db, const double *xyz, const float *inten, const int64_t *off, double max_rho, int m);
+int db_stream_match_async(sodso_db *db, const double *xyz, const float *inten, const int64_t *off, double max_rho, int m,
+                          bool self, double *hist_dev);
 // sharded.cu
 void comm_release(sodso_ctx *c);
 

@@ -293,6 +293,10 @@ int sodso_db_scans_query_sharded(sodso_db *db, const double *db_xyz, const float
     }
   }
   int rc;
+  // the queries are the shard's own scans (same buffers, a self-match on this rank): they are binned once, while the
+  // shard streams in.  Every pair is still computed -- see db_stream_match_async.
+  const bool self = db_xyz && q_xyz == db_xyz && q_inten == db_inten && q_off == db_off && m_slice == m_total &&
+                    m_total == db->n;
   // ---- query signatures: this rank's slice is binned here (test_sc.cpp:40-57); slices travel as signatures
   // (19 KB per scan instead of 115 KB of points) over NVLink
   double *qh;
@@ -303,35 +307,39 @@ int sodso_db_scans_query_sharded(sodso_db *db, const double *db_xyz, const float
     SODSO_CUDA_CHECK(db->q_hist.reserve(qcnt * sizeof(double)));
     qh = db->q_hist.as<double>();
   }
-  if (m_slice > 0) {
-    int64_t total = 0;
-    if ((rc = check_offsets_host(q_off, m_slice, &total))) return rc;
-    const double *xd;
-    const float *id;
-    const int64_t *od;
-    if ((rc = stage_in(c, q_xyz, (size_t)total * 3, db->q_xyz, &xd))) return rc;
-    if ((rc = stage_in(c, q_inten, (size_t)total, db->q_inten, &id))) return rc;
-    if ((rc = stage_in(c, q_off, (size_t)m_slice + 1, db->q_off, &od))) return rc;
-    SODSO_CUDA_CHECK(launch_sc_generate(xd, id, od, m_slice, max_rho, qh + (size_t)q_first * 2 * SC_SIZE, c->num_sms,
-                                        c->stream, &c->launches));
-  }
-  if (gather) {
-    SODSO_NCCL_CHECK(nccl().GroupStart());
-    for (int r = 0; r < R; r++) {
-      int first, count;
-      block_partition(m_total, R, r, &first, &count);
-      if (count == 0) continue;
-      double *p = qh + (size_t)first * 2 * SC_SIZE;
-      SODSO_NCCL_CHECK(nccl().Broadcast(p, p, (size_t)count * 2 * SC_SIZE, ncclDouble, r, c->comm->comm, c->stream));
-    }
-    SODSO_NCCL_CHECK(nccl().GroupEnd());
-  }
-  if ((rc = sc_prepare(c, db->op_algo, qh, m_total, db->q_op, false))) return rc;
-  // ---- the shard: new scans (binned, operand rewritten in place, matched chunk by chunk) or the resident operand
-  if (db_xyz) {
-    if ((rc = db_stream_match_async(db, db_xyz, db_inten, db_off, max_rho, m_total))) return rc;
+  if (self) {
+    if ((rc = db_stream_match_async(db, db_xyz, db_inten, db_off, max_rho, m_total, true, qh))) return rc;
   } else {
-    if ((rc = db_match_prepared_async(db, m_total))) return rc;
+    if (m_slice > 0) {
+      int64_t total = 0;
+      if ((rc = check_offsets_host(q_off, m_slice, &total))) return rc;
+      const double *xd;
+      const float *id;
+      const int64_t *od;
+      if ((rc = stage_in(c, q_xyz, (size_t)total * 3, db->q_xyz, &xd))) return rc;
+      if ((rc = stage_in(c, q_inten, (size_t)total, db->q_inten, &id))) return rc;
+      if ((rc = stage_in(c, q_off, (size_t)m_slice + 1, db->q_off, &od))) return rc;
+      SODSO_CUDA_CHECK(launch_sc_generate(xd, id, od, m_slice, max_rho, qh + (size_t)q_first * 2 * SC_SIZE, c->num_sms,
+                                          c->stream, &c->launches));
+    }
+    if (gather) {
+      SODSO_NCCL_CHECK(nccl().GroupStart());
+      for (int r = 0; r < R; r++) {
+        int first, count;
+        block_partition(m_total, R, r, &first, &count);
+        if (count == 0) continue;
+        double *p = qh + (size_t)first * 2 * SC_SIZE;
+        SODSO_NCCL_CHECK(nccl().Broadcast(p, p, (size_t)count * 2 * SC_SIZE, ncclDouble, r, c->comm->comm, c->stream));
+      }
+      SODSO_NCCL_CHECK(nccl().GroupEnd());
+    }
+    if ((rc = sc_prepare(c, db->op_algo, qh, m_total, db->q_op, false))) return rc;
+    // ---- the shard: new scans (binned, operand rewritten in place, matched chunk by chunk) or the resident operand
+    if (db_xyz) {
+      if ((rc = db_stream_match_async(db, db_xyz, db_inten, db_off, max_rho, m_total, false, nullptr))) return rc;
+    } else {
+      if ((rc = db_match_prepared_async(db, m_total))) return rc;
+    }
   }
   const bool host_qh = q_hist && q_hist != qh;
   if (host_qh && (rc = finish_out(c, q_hist, qcnt, qh))) return rc;

@@ -136,3 +136,32 @@ def test_place_recognition_end_to_end(gpu_ctx, oracle, tmp_path):
         dp, di = (oracle.sc_match_numpy if kind == "sc" else oracle.m2dp_match)(ref, ref)
         ridx, rscore = oracle.fuse_top1(dp, di, 20)
         np.testing.assert_array_equal(idx, ridx)
+
+
+def test_sharded_cpp_host(gpu_ctx, tmp_path):
+    """match_signatures_sharded: the C++ host of the row-sharded path (one thread per GPU, sodso_comm_init +
+    sodso_db_query_sharded), on 1 GPU and -- when the box has them -- 2 GPUs, against the Python binding on one GPU."""
+    import torch
+
+    from so_dso_place_recognition_b200 import api, synth
+
+    subprocess.check_call(["make", "-C", HOST, "-s"])
+    exe = os.path.join(BIN, "match_signatures_sharded")
+    xyz, inten, off = synth.make_scan_set(600, 512, planted_loops=True, first=77)
+    hist = api.sc_generate(xyz, inten, off)
+    hfile = str(tmp_path / "history_sc.bin")
+    api.save_history(hfile, hist)
+    qfile = str(tmp_path / "queries.bin")
+    api.save_history(qfile, hist[300:420])
+    db = api.SignatureDB("sc", hist)
+    idx, score, dp, di = db.query_sharded(hist[300:420], 300, 20, 2.0, 4)
+    db.close()
+    for gpus in ([1, 2] if torch.cuda.device_count() >= 2 else [1]):
+        out = str(tmp_path / f"topk_{gpus}.txt")
+        subprocess.check_call([exe, "sc", hfile, qfile, "20", "4", out, "--gpus", str(gpus), "--batch", "50", "--q-row0",
+                               "300"], stdout=subprocess.DEVNULL)
+        got = np.loadtxt(out).reshape(120, 4, 4)
+        np.testing.assert_array_equal(got[:, :, 0].astype(np.int64) - 1, idx)
+        np.testing.assert_allclose(got[:, :, 1], score, rtol=1e-9, atol=1e-12)
+        np.testing.assert_array_equal(got[:, :, 2], dp)
+        np.testing.assert_array_equal(got[:, :, 3], di)
