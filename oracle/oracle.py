@@ -103,6 +103,37 @@ def sc_generate(xyz, inten, off, max_rho=45.0, nthreads=1):
     return hist
 
 
+def sc_generate_flip(xyz, inten, off, pca_flip, max_rho=45.0, nthreads=1):
+    """sign experiment: sc_generate with eigenvector k of scan s negated when bit k of pca_flip[s] is set"""
+    xyz = _f64(xyz).reshape(-1, 3)
+    inten = _f32(inten)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    ns = off.shape[0] - 1
+    flip = np.ascontiguousarray(pca_flip, dtype=np.int32)
+    assert flip.shape == (ns,)
+    hist = np.zeros((ns, 2 * SC_SIZE))
+    lib().orc_sc_generate_flip(_p(xyz, C.c_double), _p(inten, C.c_float), _p(off, C.c_int64), C.c_int(ns),
+                               C.c_double(max_rho), _p(flip, C.c_int32), _p(hist, C.c_double), C.c_int(nthreads))
+    return hist
+
+
+def m2dp_generate_flip(xyz, inten, off, pca_flip, svd_flip, max_rho=45.0, nthreads=1):
+    """sign experiment: m2dp_generate with per-scan PCA eigenvector flips (bits 0..2) and per-scan flips of the
+    dominant singular pair (bit 0: count matrix, bit 1: intensity matrix)"""
+    xyz = _f64(xyz).reshape(-1, 3)
+    inten = _f32(inten)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    ns = off.shape[0] - 1
+    pf = np.ascontiguousarray(pca_flip, dtype=np.int32)
+    sf = np.ascontiguousarray(svd_flip, dtype=np.int32)
+    assert pf.shape == (ns,) and sf.shape == (ns,)
+    hist = np.zeros((4 * ns, 2 * M2DP_SIZE))
+    lib().orc_m2dp_generate_flip(_p(xyz, C.c_double), _p(inten, C.c_float), _p(off, C.c_int64), C.c_int(ns),
+                                 C.c_double(max_rho), _p(pf, C.c_int32), _p(sf, C.c_int32), _p(hist, C.c_double),
+                                 C.c_int(nthreads))
+    return hist
+
+
 def m2dp_tables():
     x = np.zeros(3 * 64)
     y = np.zeros(3 * 64)

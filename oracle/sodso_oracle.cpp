@@ -122,6 +122,12 @@ void sym_eig3(const double a_in[9], double w[3], double v[9]) {
   }
 }
 
+// Sign experiment hooks (tests/test_sign_conventions.py): Eigen's eigenvector / singular-vector signs are
+// implementation-defined and unobservable here, so the tests flip OUR convention per scan and measure what changes.
+// bit k of t_pca_flip negates eigenvector k; t_svd_flip != 0 negates the dominant singular pair.
+static thread_local int t_pca_flip = 0;
+static thread_local int t_svd_flip = 0;
+
 // pts_align.h:7-46.  xyz AoS n x 3 -> out AoS n x 3 in the PCA frame
 // (x: least variance "up", y: middle, z: largest).  evec (optional) = 3x3
 // row-major, column k = k-th eigenvector.
@@ -146,6 +152,9 @@ void align_pca(const double* xyz, int n, double* out, double* evec, double* mean
   double cov[9] = {c00, c01, c02, c01, c11, c12, c02, c12, c22};
   double w[3], v[9];
   sym_eig3(cov, w, v);                                 // pts_align.h:31-34
+  for (int k = 0; k < 3; k++)
+    if (t_pca_flip & (1 << k))
+      for (int i = 0; i < 3; i++) v[i * 3 + k] = -v[i * 3 + k];
   for (int i = 0; i < n; i++) {                        // pts_align.h:37-45
     double x = xyz[3 * i + 0] - mx, y = xyz[3 * i + 1] - my, z = xyz[3 * i + 2] - mz;
     out[3 * i + 0] = (x * v[0] + y * v[3]) + z * v[6];
@@ -279,6 +288,7 @@ void svd_dominant(const double* A, int rows, int cols, double* u1, double* v1, d
   double su = 0;
   for (int k = 0; k < rows; k++) su += J[(size_t)k * rows + best];
   double sgn = (su < 0.0) ? -1.0 : 1.0;
+  if (t_svd_flip) sgn = -sgn;
   for (int k = 0; k < rows; k++) u1[k] = sgn * J[(size_t)k * rows + best];
   for (int k = 0; k < cols; k++)
     v1[k] = (sigma > 0.0) ? sgn * W[(size_t)best * cols + k] / sigma : 0.0;
@@ -317,8 +327,12 @@ void m2dp_signature(const double* pts, const float* inten, int n, double max_rho
       isum[k] = isum[k] > ave ? 1 : 0;
     }
   }
+  const int svd_bits = t_svd_flip;   // sign experiment: bit 0 = count matrix, bit 1 = intensity matrix
+  t_svd_flip = svd_bits & 1;
   svd_dominant(cnt.data(), M2DP_PQ, M2DP_SR, count_out, count_out + M2DP_PQ, nullptr);   // :94-98,107
+  t_svd_flip = svd_bits & 2;
   svd_dominant(isum.data(), M2DP_PQ, M2DP_SR, inten_out, inten_out + M2DP_PQ, nullptr);  // :100-108
+  t_svd_flip = svd_bits;
   if (A_cnt_out) std::memcpy(A_cnt_out, cnt.data(), sizeof(double) * cnt.size());
   if (A_int_out) std::memcpy(A_int_out, isum.data(), sizeof(double) * isum.size());
 }
@@ -350,6 +364,21 @@ void orc_sc_generate(const double* xyz, const float* inten, const int64_t* off, 
     int n = (int)(off[s + 1] - off[s]);
     sc_signature(xyz + 3 * b, inten + b, n, max_rho, hist + (size_t)s * 2 * SC_SIZE,
                  hist + (size_t)s * 2 * SC_SIZE + SC_SIZE);
+  }
+}
+
+// Sign experiment (tests/test_sign_conventions.py): as orc_sc_generate, with eigenvector k of scan s negated when
+// bit k of pca_flip[s] is set (what a different Eigen build could legitimately return, pts_align.h:31-39).
+void orc_sc_generate_flip(const double* xyz, const float* inten, const int64_t* off, int nscan,
+                          double max_rho, const int* pca_flip, double* hist, int nthreads) {
+#pragma omp parallel for schedule(dynamic) num_threads(nthreads > 0 ? nthreads : 1)
+  for (int s = 0; s < nscan; s++) {
+    int64_t b = off[s];
+    int n = (int)(off[s + 1] - off[s]);
+    t_pca_flip = pca_flip ? pca_flip[s] : 0;
+    sc_signature(xyz + 3 * b, inten + b, n, max_rho, hist + (size_t)s * 2 * SC_SIZE,
+                 hist + (size_t)s * 2 * SC_SIZE + SC_SIZE);
+    t_pca_flip = 0;
   }
 }
 
@@ -385,6 +414,22 @@ void orc_m2dp_frame(const double* xyz, const float* inten, int n, double max_rho
       m2dp_signature(var.data(), inten, n, max_rho, xp, yp, row, row + M2DP_SIG, nullptr, nullptr);
       sub++;
     }
+  }
+}
+
+// Sign experiment: as orc_m2dp_generate with per-scan PCA eigenvector flips (bits 0..2 of pca_flip[s]) and per-scan
+// flips of the dominant singular pair (svd_flip[s]: bit 0 = count matrix, bit 1 = intensity matrix; all 4 variants).
+void orc_m2dp_generate_flip(const double* xyz, const float* inten, const int64_t* off, int nscan, double max_rho,
+                            const int* pca_flip, const int* svd_flip, double* hist, int nthreads) {
+#pragma omp parallel for schedule(dynamic) num_threads(nthreads > 0 ? nthreads : 1)
+  for (int s = 0; s < nscan; s++) {
+    int64_t b = off[s];
+    int n = (int)(off[s + 1] - off[s]);
+    t_pca_flip = pca_flip ? pca_flip[s] : 0;
+    t_svd_flip = svd_flip ? svd_flip[s] : 0;
+    orc_m2dp_frame(xyz + 3 * b, inten + b, n, max_rho, hist + (size_t)s * 4 * 2 * M2DP_SIG);
+    t_pca_flip = 0;
+    t_svd_flip = 0;
   }
 }
 

@@ -514,7 +514,7 @@ int sodso_sc_scans_to_loops(sodso_ctx *c, const double *xyz, const float *inten,
   const bool streamed = host_pts && host_int && host_off && nscan >= c->stream_min_scans;
   std::vector<int> bounds{0};
   if (streamed) {
-    for (int b = 256; b < nscan; b += b < 512 ? 256 : CH) bounds.push_back(b);
+    for (int b = 256; b < nscan; b += (b < 512 || nscan - b <= 1024) ? 256 : CH) bounds.push_back(b);
   }
   bounds.push_back(nscan);
   const int nchunk = (int)bounds.size() - 1;
@@ -1158,8 +1158,9 @@ int db_stream_match_async(sodso_db *db, const double *xyz, const float *inten, c
   // chunk boundaries (multiples of the 256-row DB tile).  self: two 256-scan chunks first, the work that can be done
   // grows with the square of what has arrived
   std::vector<int> bounds{0};
-  if (streamed)
-    for (int b = self ? 256 : CH; b < n; b += (self && b < 512) ? 256 : CH) bounds.push_back(b);
+  if (streamed)   // (self: the last kilo-scan also goes in 256-scan chunks -- what is left to do after the last byte
+                  //  has landed is the L-shaped region of the final chunk)
+    for (int b = self ? 256 : CH; b < n; b += (self && (b < 512 || n - b <= 1024)) ? 256 : CH) bounds.push_back(b);
   bounds.push_back(n);
   const int nchunk = (int)bounds.size() - 1;
   const double *xd = xyz;

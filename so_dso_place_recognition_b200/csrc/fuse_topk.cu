@@ -115,6 +115,10 @@ row_stats_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, i
   if (threadIdx.x < STATS_W) stats[(size_t)row * STATS_W + threadIdx.x] = v[threadIdx.x];
 }
 
+// KL: length of the per-thread candidate list (1 for top-1, 8 for k <= 8, 0 = no lists: one row scan per selected entry)
+constexpr int TOPK_CAND_CAP = 96;   // entries at or below the selection bound that the single-scan path can hold
+
+template <int KL>
 __global__ void __launch_bounds__(FUSE_THREADS)
 fuse_topk_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, int n, int ldd,
                  const double *__restrict__ gstats, long long n_global, long long q_row0,
@@ -122,6 +126,9 @@ fuse_topk_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, i
                  double *__restrict__ score, double *__restrict__ dp_at, double *__restrict__ di_at) {
   __shared__ double ss[32];
   __shared__ long long si[32];
+  __shared__ double cand_f[TOPK_CAND_CAP];
+  __shared__ long long cand_j[TOPK_CAND_CAP];
+  __shared__ int cand_n;
   const int row = blockIdx.x;
   const float *p = d_p + (size_t)row * ldd, *q = d_i + (size_t)row * ldd;
   const double *st = gstats + (size_t)row * STATS_W;
@@ -133,14 +140,116 @@ fuse_topk_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, i
   double last_s = 0.0;
   long long last_i = -1;  // nothing selected yet
   // The two fp64 divisions per element are only needed to order the few entries around the k smallest.  A linear
-  // form a_p p + a_i q + c0 (two FMAs, |error| ~ 1e-13) is selected k times (cheap passes, ordered by (value, index));
-  // every entry of the exact top-k then lies at or below the k-th selected value + margin, and the exact expression
-  // of run_test.m:40-46 is evaluated only for those.  Rows with fewer than k finite unmasked entries, or with
-  // degenerate statistics, take the plain loop (bound = +inf admits everything, masked entries included).
+  // form a_p p + a_i q + c0 (two FMAs, |error| ~ 1e-13) is used to SELECT: every entry of the exact top-k lies at or
+  // below the k-th smallest linear value + margin, and the exact expression of run_test.m:40-46 is evaluated only for
+  // those.  Rows with fewer than k finite unmasked entries, or with degenerate statistics, take the plain loop (bound
+  // = +inf admits everything, masked entries included).
   const double a_p = p_weight / sd_p, a_i = 1.0 / sd_i, c0 = -(a_p * mu_p + a_i * mu_i);
   const bool lin_ok = isfinite(a_p) && isfinite(a_i) && isfinite(c0);
   double bound = INFINITY;
-  if (lin_ok) {
+  if (lin_ok && KL > 0) {
+    // ONE scan: every thread keeps the KL smallest (value, index) of its elements in registers (sorted), then k rounds
+    // of block arg-min over the list heads give the k-th smallest of the row
+    constexpr int KLL = KL > 0 ? KL : 1;
+    double lv[KLL];
+    long long lj[KLL];
+#pragma unroll
+    for (int t = 0; t < KLL; t++) {
+      lv[t] = 0.0;
+      lj[t] = -1;
+    }
+    for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
+      const long long jg = db_row0 + j;
+      long long dist = qg - jg;
+      if (dist < 0) dist = -dist;
+      if (dist < (long long)mask_width) continue;
+      const double fl = fma(a_p, (double)p[j], fma(a_i, (double)q[j], c0));
+      if (!isfinite(fl)) continue;
+      if (cand_less(fl, jg, lv[KLL - 1], lj[KLL - 1])) {
+        lv[KLL - 1] = fl;
+        lj[KLL - 1] = jg;
+#pragma unroll
+        for (int t = KLL - 1; t > 0; t--)
+          if (cand_less(lv[t], lj[t], lv[t - 1], lj[t - 1])) {
+            const double tv = lv[t];
+            const long long tj = lj[t];
+            lv[t] = lv[t - 1];
+            lj[t] = lj[t - 1];
+            lv[t - 1] = tv;
+            lj[t - 1] = tj;
+          }
+      }
+    }
+    double sel_s = 0.0;
+    bool enough = true;
+    for (int r = 0; r < k; r++) {
+      double bs = lv[0];
+      long long bi = lj[0];
+      block_argmin(bs, bi, ss, si);
+      if (bi < 0) {
+        enough = false;
+        break;
+      }
+      if (lj[0] == bi) {   // the winner pops its head
+#pragma unroll
+        for (int t = 0; t < KLL - 1; t++) {
+          lv[t] = lv[t + 1];
+          lj[t] = lj[t + 1];
+        }
+        lj[KLL - 1] = -1;
+      }
+      sel_s = bs;
+    }
+    if (enough) bound = sel_s + 1e-9 * (1.0 + fabs(sel_s));
+    if (enough) {
+      // second scan: the (typically exactly k) entries at or below the bound, evaluated exactly and sorted by one thread
+      if (threadIdx.x == 0) cand_n = 0;
+      __syncthreads();
+      for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
+        const long long jg = db_row0 + j;
+        long long dist = qg - jg;
+        if (dist < 0) dist = -dist;
+        if (dist < (long long)mask_width) continue;
+        if (!(fma(a_p, (double)p[j], fma(a_i, (double)q[j], c0)) <= bound)) continue;
+        const double f = p_weight * (((double)p[j] - mu_p) / sd_p) + ((double)q[j] - mu_i) / sd_i;   // run_test.m:40
+        if (f != f) continue;
+        const int slot = atomicAdd(&cand_n, 1);
+        if (slot < TOPK_CAND_CAP) {
+          cand_f[slot] = f;
+          cand_j[slot] = jg;
+        }
+      }
+      __syncthreads();
+      const int cn = cand_n;
+      if (cn <= TOPK_CAND_CAP) {
+        if (threadIdx.x == 0) {
+          for (int a = 1; a < cn; a++) {   // insertion sort by (score, global index)
+            const double f = cand_f[a];
+            const long long jg = cand_j[a];
+            int b = a - 1;
+            while (b >= 0 && cand_less(f, jg, cand_f[b], cand_j[b])) {
+              cand_f[b + 1] = cand_f[b];
+              cand_j[b + 1] = cand_j[b];
+              b--;
+            }
+            cand_f[b + 1] = f;
+            cand_j[b + 1] = jg;
+          }
+          for (int r = 0; r < k; r++) {
+            const size_t o = (size_t)row * k + r;
+            const bool have = r < cn;
+            const long long bi = have ? cand_j[r] : -1;
+            idx[o] = bi;
+            score[o] = have ? cand_f[r] : NAN;
+            if (dp_at) dp_at[o] = have ? (double)p[bi - db_row0] : NAN;
+            if (di_at) di_at[o] = have ? (double)q[bi - db_row0] : NAN;
+          }
+        }
+        return;
+      }
+      // more near-ties than the list holds: fall through to the scan-per-entry loop below with the bound as filter
+    }
+  } else if (lin_ok) {
     double sel_s = 0.0;
     long long sel_i = -1;
     bool enough = true;
@@ -297,9 +406,9 @@ cudaError_t launch_fuse_topk(const float *d_p, const float *d_i, int m, int n, i
                              double *score, double *dp_at, double *di_at, cudaStream_t st,
                              int64_t *launches) {
   if (m <= 0) return cudaSuccess;
-  fuse_topk_kernel<<<m, FUSE_THREADS, 0, st>>>(d_p, d_i, n, ldd, global_stats, n_global, q_row0,
-                                               db_row0, mask_width, p_weight, k, idx, score, dp_at,
-                                               di_at);
+  auto kern = k == 1 ? fuse_topk_kernel<1> : k <= 8 ? fuse_topk_kernel<8> : fuse_topk_kernel<0>;
+  kern<<<m, FUSE_THREADS, 0, st>>>(d_p, d_i, n, ldd, global_stats, n_global, q_row0, db_row0, mask_width, p_weight, k, idx,
+                                   score, dp_at, di_at);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

@@ -88,17 +88,19 @@ def test_fuse_top1_given_matrices(gpu_ctx, oracle):
     dp[:, 7] = -1.0
     dp[:, 200] = -1.0
     di[:, 7] = di[:, 200] = -1.0
-    dp[3, 50] = np.nan
+    dp[3, 50] = np.nan                                  # one NaN entry: omitted from the row statistics, row still ranked
+    dp[4, :] = np.nan                                   # an all-NaN channel row
     for mw in (0, 10, 100):
         idx, sc = api.fuse_top1(dp, di, mw)
         with np.errstate(all="ignore"):
             ridx, rsc = oracle.fuse_top1(dp, di, mw)
         np.testing.assert_array_equal(idx, ridx)
         np.testing.assert_allclose(sc, rsc, rtol=1e-10, equal_nan=True)
-        if mw == 0:                                     # NaN row: MATLAB min returns the first index
-            assert idx[3] == 0 and np.isnan(sc[3])
+        assert idx[3] == (7 if mw == 0 else 200) and np.isfinite(sc[3])     # MATLAB normalize omits NaN (run_test.m:40)
+        if mw == 0:                                     # all-NaN row: MATLAB min returns the first index
+            assert idx[4] == 0 and np.isnan(sc[4])
         else:                                           # ... but the mask overwrites NaN with Inf (run_test.m:47-53)
-            assert idx[3] == 0 and np.isinf(sc[3])
+            assert idx[4] == 0 and np.isinf(sc[4])
 
 
 def test_tc_equals_simt_at_scale(gpu_ctx, oracle):
