@@ -2,26 +2,35 @@
 // M2DP::getSignature (M2DP.cpp:38-109), one persistent CTA per SM (1024 threads), the whole batch in
 // one launch.
 //
-// Per scan: moments pass (HBM read) -> mean + 3x3 eigenproblem (pts_align.h) -> staging pass (L2 read):
-// the PCA-aligned points go to shared memory as fp32.  Per variant: 64 planes x n points are projected
-// and binned by (rho, theta) into a 64 x 128 count histogram (u32) and intensity-sum histogram (int32 when
-// the sums are provably exact, fp64 otherwise) with shared-memory atomics; the sums are binarised against
-// the float average intensity; the signature is the dominant left/right singular vector pair of each
-// 64 x 128 matrix.
+// Per scan: moments pass (HBM read) -> mean + 3x3 eigenproblem (pts_align.h).  Then, per sign variant, 64 planes x n
+// points are projected and binned by (rho, theta) into a 64 x 128 count histogram (u32) and intensity-sum histogram
+// (int32 when the sums are provably exact, fp64 otherwise) with shared-memory atomics; the sums are binarised against
+// the float average intensity; the signature is the dominant left / right singular vector pair of each 64 x 128 matrix.
 //
-// Binning: the bin of a (point, plane) pair is proposed in fp32 (6 FMAs, fast_turns, rsqrt) and accepted
-// only if both polar coordinates are further from a bin edge than 3x the fp32 error bound (which grows
-// like 1/rho for the angle); everything else takes the reference's fp64 expression (M2DP.cpp:56-63) on the
-// fp64 point re-read from L2.  The degenerate plane p=2,q=0, whose projection vectors are exactly zero
-// (SURVEY F8), puts every point into one of two bins depending on the signs of the zeros; it is handled
-// with one warp-aggregated update per 32 points.
+// Binning.  The bin of a (point, plane) pair is PROPOSED in fp32 and accepted only when both polar coordinates are
+// further from a bin edge than 3x the fp32 error bound; everything else takes the reference's fp64 expression
+// (M2DP.cpp:56-63) on the fp64 point re-read from L2.  The proposal needs no arctangent: with 16 sectors of 22.5
+// degrees the sector follows from the signs of (xp, yp), from |yp| > |xp| and from min/max against tan(22.5 deg), and
+// the distance to the nearest sector edge is the distance of that ratio to {0, tan 22.5, 1}; the ring comes from
+// sqrt(xp^2 + yp^2).  ~45 instructions per evaluation instead of ~100 with the polynomial angle.
 //
-// SVD: only the dominant pair is needed (M2DP.cpp:96-103).  G = A A^T (64 x 64, exact in integers) is
-// formed by the whole CTA, then four warps per matrix run the power iteration u <- G u / |G u| in fp64 from
-// the all-ones vector until the update falls below 1e-14 (both matrices concurrently), and
-// v = A^T u / sigma.  Both matrices are entrywise non-negative, so the iteration converges to the Perron
-// pair, which fixes the sign the same way as the oracle (sum(u) >= 0; Eigen's own sign is unobservable,
-// SURVEY §8c).
+// Variant sharing.  Variant v evaluates plane (p, q) with the vectors S_v xProj, S_v yProj, S_v = diag(dx, dy, dx dy)
+// (test_m2dp.cpp:47-57).  For the azimuths p = 1, 2, 3 the float table of M2DP.cpp:4-34 is exactly mirror symmetric:
+// S_{v+2} xProj[4-p][q] = -S_v xProj[p][q] and S_{v+2} yProj[4-p][q] = +S_v yProj[p][q] (checked on the host at launch),
+// so variant v+2's rows for those planes are variant v's with the sectors mapped s -> (7 - s) mod 16 -- not a single
+// evaluation is needed.  Variants are therefore processed in pairs (0, 2) and (1, 3): 64 + 16 planes per point and
+// pair instead of 128.  Evaluations inside the guard band are deferred to a small queue and replayed in fp64 for each
+// variant separately, so the result is bit-identical to processing the variants one by one.
+//
+// The degenerate plane p=2,q=0, whose projection vectors are exactly zero, puts every point into one of
+// two bins depending on the signs of the zeros; it is handled with one warp-aggregated update per 32 points.
+//
+// SVD: only the dominant pair is needed (M2DP.cpp:96-103).  G = A A^T (64 x 64, exact in 64-bit integers: 2 x 2 blocks
+// of the lower triangle per thread, lanes skewed along k so that any row assignment is free of bank conflicts), scaled
+// by a power of two, squared four times (G^16), then four warps run the power iteration u <- G u / |G u| in fp64 from
+// the all-ones vector until the update falls below 1e-14, and v = A^T u / sigma.  Both matrices are entrywise
+// non-negative, so the iteration converges to the Perron pair, which fixes the sign the same way as the oracle
+// (sum(u) >= 0; Eigen's own sign is unobservable).
 //
 // The projection table (xProj / yProj, M2DP.cpp:4-34) is computed on the host with float cosf/sinf exactly
 // like the reference constructor and passed in constant memory.
@@ -36,28 +45,31 @@ namespace sodso {
 namespace {
 
 constexpr int M2_THREADS = 1024;
-constexpr int M2_CAP = 4096;            // aligned points of a scan staged in shared memory (fp32)
 constexpr int HB = M2DP_PQ * M2DP_SR;   // 8192 histogram bins
 constexpr float M2_GUARD_R = 3e-5f;      // ring coordinate guard (see the binning loop)
-constexpr int SVD_WARPS = 4;            // warps per matrix in the power iteration
+constexpr int SVD_WARPS = 4;            // warps in the power iteration
+constexpr int QCAP = 4096;              // deferred (point, plane) evaluations of a pass (8 bytes each, in the T area)
+constexpr int GLD = M2DP_PQ + 4;        // leading dimension of the 64 x 64 fp64 workspaces: rows 32 B (mod 128 B) apart, so
+                                        // that the 8 x 4 fragment loads of the fp64 tensor-core squaring are conflict-free
+constexpr float TAN22 = 0.41421356237f;
 
 __constant__ double c_xproj[3 * M2DP_PQ];
 __constant__ double c_yproj[3 * M2DP_PQ];
-__constant__ float c_xproj32[3 * M2DP_PQ];
-__constant__ float c_yproj32[3 * M2DP_PQ];
+// fp32 proposal table: (x0, x1, x2, y0), (y1, y2, 0, 0) per plane; the plane index is warp-uniform, so the two
+// 16-byte reads are uniform constant loads, not shared-memory traffic
+__constant__ float4 c_tab4[2 * M2DP_PQ];
 
 struct M2Smem {
-  double hsum[HB];             // fp64 intensity sums (int32 in exact mode) -> binarised matrix as u32 in the
-                               // first half, G of the binarised matrix in the second half
-  double G0[M2DP_PQ * M2DP_PQ];  // Gram matrix of the count matrix
-  double T[M2DP_PQ * M2DP_PQ];   // squaring workspace
+  unsigned cnt[2][HB];          // count histograms of the two variants of a pair (A0 of the SVD)
+  int isum[2][HB];              // exact mode: intensity sums in units of 2^emin; then, in place, the binarised matrix.
+                                // inexact mode (one variant at a time): the 64 KB are HB fp64 sums
+  double G[M2DP_PQ * GLD];      // Gram matrix -> G^16
+  double T[M2DP_PQ * GLD];      // squaring workspace; during binning: the queue of deferred evaluations
   double scratch[11 * 32];
-  double uvec[2][M2DP_PQ], yv[2][M2DP_SR], red[2][SVD_WARPS], red2[2][SVD_WARPS], sig[2];
+  double uvec[M2DP_PQ], yv[M2DP_SR], red[SVD_WARPS], red2[SVD_WARPS], sig;
   double bc[16];
-  float4 tab[2 * M2DP_PQ];      // fp32 projection table: (x0, x1, x2, y0), (y1, y2, 0, 0) per plane
-  float ax[M2_CAP], ay[M2_CAP], az[M2_CAP];
-  unsigned hcnt[HB];
   int ibc[4];
+  int qn;
 };
 static_assert(sizeof(M2Smem) <= 227 * 1024, "shared memory");
 
@@ -65,35 +77,41 @@ struct ScanRef {
   const double *g;
   const float *gi;
   const double *bc;   // mean + eigenvectors (identity for pre-aligned input)
-  int n, nst;
+  int n;
   int identity;       // class contract (M2DP.h:18-20): the input is used as it is (signed zeros included)
-  double dx, dy, dz;  // sign variant
   double S_res_inv, R_res_inv;
 };
 
-// aligned + sign-flipped fp64 point i (pts_align.h:37-45, test_m2dp.cpp:49-53)
-__device__ __forceinline__ void aligned_point64(const ScanRef &R, int i, double &px, double &py, double &pz) {
-  double ax, ay, az;
+// aligned fp64 point i (pts_align.h:37-45), before the sign flips of a variant
+__device__ __forceinline__ void aligned_point64(const ScanRef &R, int i, double &ax, double &ay, double &az) {
   if (R.identity) {
     ax = R.g[3 * (size_t)i + 0];
     ay = R.g[3 * (size_t)i + 1];
     az = R.g[3 * (size_t)i + 2];
-    px = ax;   // (dx = dy = dz = 1; no multiplication either)
-    py = ay;
-    pz = az;
     return;
   }
   pca_rotate(R.bc, R.g[3 * (size_t)i + 0], R.g[3 * (size_t)i + 1], R.g[3 * (size_t)i + 2], ax, ay, az);
-  px = R.dx * ax;
-  py = R.dy * ay;
-  pz = R.dz * az;
 }
 
-// M2DP.cpp:56-68 in fp64, exactly the reference's expression: flat histogram index or -1
-__device__ __noinline__ int m2dp_bin_exact(const ScanRef &R, int i, int pq) {
+// sign pattern of variant var (test_m2dp.cpp:47-57: dx outer, dy inner, both in {-1, +1}); var < 0: identity
+__device__ __forceinline__ void variant_signs(int var, double &dx, double &dy, double &dz) {
+  dx = var < 0 ? 1.0 : ((var >> 1) ? 1.0 : -1.0);
+  dy = var < 0 ? 1.0 : ((var & 1) ? 1.0 : -1.0);
+  dz = dx * dy;
+}
+
+// M2DP.cpp:56-68 in fp64, exactly the reference's expression, for point i under variant var: flat histogram index or -1
+__device__ __noinline__ int m2dp_bin_exact(const ScanRef &R, int i, int pq, int var) {
   const double PI = 3.14159265358979323846;
   double px, py, pz;
   aligned_point64(R, i, px, py, pz);
+  if (!R.identity) {   // test_m2dp.cpp:49-53 (no multiplication at all for the class contract: signed zeros survive)
+    double dx, dy, dz;
+    variant_signs(var, dx, dy, dz);
+    px = dx * px;
+    py = dy * py;
+    pz = dz * pz;
+  }
   const double xp = (c_xproj[3 * pq] * px + c_xproj[3 * pq + 1] * py) + c_xproj[3 * pq + 2] * pz;
   const double yp = (c_yproj[3 * pq] * px + c_yproj[3 * pq + 1] * py) + c_yproj[3 * pq + 2] * pz;
   const double ang = (atan2(yp, xp) + PI) * R.S_res_inv;
@@ -104,168 +122,358 @@ __device__ __noinline__ int m2dp_bin_exact(const ScanRef &R, int i, int pq) {
   return sr < M2DP_SR ? pq * M2DP_SR + sr : -1;  // M2DP.cpp:66 (si == 16 aliases into ring ri+1)
 }
 
-// Y = X X for a symmetric 64 x 64 matrix (all threads): Y[i][j] = sum_k X[k][i] X[k][j]
-__device__ __forceinline__ void sym_square64(const double *X, double *Y) {
-  const int j = threadIdx.x & 63, i0 = (threadIdx.x >> 6) * 4;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll 4
-  for (int k = 0; k < M2DP_PQ; k++) {
-    const double xj = X[k * M2DP_PQ + j];
-    const double2 p = reinterpret_cast<const double2 *>(X + k * M2DP_PQ + i0)[0];
-    const double2 q = reinterpret_cast<const double2 *>(X + k * M2DP_PQ + i0)[1];
-    a0 = fma(p.x, xj, a0);
-    a1 = fma(p.y, xj, a1);
-    a2 = fma(q.x, xj, a2);
-    a3 = fma(q.y, xj, a3);
-  }
-  Y[(i0 + 0) * M2DP_PQ + j] = a0;
-  Y[(i0 + 1) * M2DP_PQ + j] = a1;
-  Y[(i0 + 2) * M2DP_PQ + j] = a2;
-  Y[(i0 + 3) * M2DP_PQ + j] = a3;
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 
-// dominant singular pairs of the two 64 x 128 matrices A0 (counts) and A1 (binarised), both u32 in shared
-// memory.  G0 / G1 / T: 64 x 64 fp64 workspaces.  Writes [u (64), v (128)] of each to out0 / out1.
+// fp32 proposal of the (ring, sector) bin of projected coordinates (xp, yp): sr = ri * 16 + si, or -1 when the point
+// is provably outside the 8 rings, and `safe` = the proposal is certainly the bin of the fp64 expression.
+//   error budget: xp, yp good to delta = 2e-5 m (|p| < 128 m, checked by the caller through r2_lim).  With
+//   mx = max(|xp|, |yp|), mn = min: a = mn / mx is good to 2 delta / mx + 3e-7, and the three decisions (sign pattern,
+//   |yp| > |xp|, a > tan 22.5) are right whenever a is further than that from {0, tan 22.5, 1}; accepted with a 3x
+//   margin.  Ring: rho * R_f good to 4e-6 + 1e-6 rings, accepted 3e-5 away from an edge.
+// Sector of the fp64 expression: si = floor(8 + phi / 22.5 deg), phi = atan2(yp, xp).  With k = floor(alpha / 22.5)
+// of the first-quadrant angle alpha = atan(|yp| / |xp|):  phi = alpha -> 8 + k;  180 - alpha -> 15 - k;
+// -alpha -> 7 - k;  alpha - 180 -> k   (never on an edge: those evaluations are not safe).
+__device__ __forceinline__ int propose_bin(float xp, float yp, float R_f, float r2_lim, bool &safe) {
+  const float ax = fabsf(xp), ay = fabsf(yp);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float r2 = __fmaf_rn(xp, xp, yp * yp);
+  const float rf = sqrt_approx(r2) * R_f;
+  const float fr = floorf(rf);
+  const float er = fabsf((rf - fr) - 0.5f);
+  const float inv = rcp_approx(mx);
+  const float a = mn * inv;
+  const float d = fminf(fminf(a, fabsf(a - TAN22)), 1.0f - a);
+  const float eg = __fmaf_rn(1.2e-4f, inv, 1e-6f);
+  const bool hi = a > TAN22, swap = ay > ax;
+  int k = hi ? 1 : 0;
+  k = swap ? 3 - k : k;
+  const unsigned sx = __float_as_uint(xp) >> 31, sy = __float_as_uint(yp) >> 31;   // 1 = negative
+  const int m7 = (sx != sy) ? 7 : 0;           // upper half plane: xp < 0 mirrors k; lower half: xp > 0 mirrors
+  const int sector = (int)((sy ^ 1u) << 3) + (k ^ m7);
+  // (a small radius needs no test of its own: eg grows like 1 / mx and d never exceeds 0.293)
+  safe = d > eg && er < 0.5f - M2_GUARD_R && r2 < r2_lim;
+  const int ri = __float2int_rz(fr);
+  return rf < (float)M2DP_NUM_R ? ri * M2DP_NUM_S + sector : -1;
+}
+
+// Y = X X for a symmetric 64 x 64 fp64 matrix (leading dimension GLD) on the fp64 tensor cores
+// (mma.sync.m8n8k4.f64: 256 multiply-adds per warp instruction instead of 32).  Warp w owns the 8 x 16 output strip
+// rows 8 (w / 4), columns 16 (w % 4); the B fragment X[k][j] is read as X[j][k] (symmetry), so both operands are 8 x 4
+// row-major reads.  Fragments (PTX ISA, m8n8k4 .f64): A[lane / 4][lane % 4], B[lane % 4][lane / 4],
+// C[lane / 4][2 (lane % 4) + {0, 1}].
+__device__ __forceinline__ void sym_square64(const double *X, double *Y) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = lane >> 2, c = lane & 3;
+  const int i0 = (warp >> 2) * 8, j0 = (warp & 3) * 16;
+  const double *pa = X + (i0 + r) * GLD + c, *pb0 = X + (j0 + r) * GLD + c, *pb1 = pb0 + 8 * GLD;
+  double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll 4
+  for (int k0 = 0; k0 < M2DP_PQ; k0 += 4) {
+    const double a = pa[k0], b0 = pb0[k0], b1 = pb1[k0];
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c00), "+d"(c01)
+                 : "d"(a), "d"(b0));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c10), "+d"(c11)
+                 : "d"(a), "d"(b1));
+  }
+  *reinterpret_cast<double2 *>(Y + (i0 + r) * GLD + j0 + 2 * c) = make_double2(c00, c01);
+  *reinterpret_cast<double2 *>(Y + (i0 + r) * GLD + j0 + 8 + 2 * c) = make_double2(c10, c11);
+}
+
+// dominant singular pair of the 64 x 128 matrix A (u32, shared memory).  G / T: 64 x 64 fp64 workspaces.
+// Writes [u (64), v (128)] to out.
 //   G = A A^T exactly (64-bit integers), scaled by a power of two to trace ~ 1;  G^16 by four squarings;
 //   power iteration with G^16 from the all-ones vector (Perron pair: entrywise non-negative);
 //   sigma = |A^T u|, v = A^T u / sigma.
-__device__ void dominant_pairs(const unsigned *A0, const unsigned *A1, double *G0, double *G1, double *T, M2Smem &S,
-                               double *out0, double *out1) {
+__device__ void dominant_pair(const unsigned *A, double *G, double *T, M2Smem &S, double *out) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // ---- Gram matrices: one (i, j <= i) entry per warp step, lanes split k (conflict-free LDS.128)
-  // warp w takes rows w and 63 - w of both matrices: 65 entries each, no index decoding
-  for (int m = 0; m < 2; m++) {
-    const unsigned *A = m ? A1 : A0;
-    double *G = m ? G1 : G0;
-#pragma unroll 1
-    for (int h = 0; h < 2; h++) {
-      const int i = h ? M2DP_PQ - 1 - warp : warp;
-      const uint4 a = reinterpret_cast<const uint4 *>(A + i * M2DP_SR)[lane];
-#pragma unroll 2
-      for (int j = 0; j <= i; j++) {
-        const uint4 b = reinterpret_cast<const uint4 *>(A + j * M2DP_SR)[lane];
-        unsigned long long acc = (unsigned long long)a.x * b.x + (unsigned long long)a.y * b.y +
-                                 (unsigned long long)a.z * b.z + (unsigned long long)a.w * b.w;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) {
-          G[i * M2DP_PQ + j] = (double)acc;
-          G[j * M2DP_PQ + i] = (double)acc;
-        }
-      }
+  // ---- Gram matrix: thread t < 528 owns the 2 x 2 block (bi, bj <= bi) of the lower block triangle.  Lane l walks k
+  // in 16-byte steps starting at step l, so the 8 lanes of a quarter-warp always hit 8 different 16-byte bank groups
+  // whatever rows they read (rows are 512 B apart); integer sums do not care about the order.
+  if (tid < 528) {
+    int bi = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
+    while ((bi + 1) * (bi + 2) / 2 <= tid) bi++;
+    while (bi * (bi + 1) / 2 > tid) bi--;
+    const int bj = tid - bi * (bi + 1) / 2;
+    const uint4 *r0 = reinterpret_cast<const uint4 *>(A + (2 * bi) * M2DP_SR);
+    const uint4 *r1 = reinterpret_cast<const uint4 *>(A + (2 * bi + 1) * M2DP_SR);
+    const uint4 *c0 = reinterpret_cast<const uint4 *>(A + (2 * bj) * M2DP_SR);
+    const uint4 *c1 = reinterpret_cast<const uint4 *>(A + (2 * bj + 1) * M2DP_SR);
+    unsigned long long g00 = 0, g01 = 0, g10 = 0, g11 = 0;
+#pragma unroll 4
+    for (int t = 0; t < M2DP_SR / 4; t++) {
+      const int k4 = (t + lane) & (M2DP_SR / 4 - 1);
+      const uint4 a0 = r0[k4], a1 = r1[k4], b0 = c0[k4], b1 = c1[k4];
+      g00 += (unsigned long long)a0.x * b0.x + (unsigned long long)a0.y * b0.y + (unsigned long long)a0.z * b0.z +
+             (unsigned long long)a0.w * b0.w;
+      g01 += (unsigned long long)a0.x * b1.x + (unsigned long long)a0.y * b1.y + (unsigned long long)a0.z * b1.z +
+             (unsigned long long)a0.w * b1.w;
+      g10 += (unsigned long long)a1.x * b0.x + (unsigned long long)a1.y * b0.y + (unsigned long long)a1.z * b0.z +
+             (unsigned long long)a1.w * b0.w;
+      g11 += (unsigned long long)a1.x * b1.x + (unsigned long long)a1.y * b1.y + (unsigned long long)a1.z * b1.z +
+             (unsigned long long)a1.w * b1.w;
     }
+    const int i0 = 2 * bi, j0 = 2 * bj;
+    G[i0 * GLD + j0] = (double)g00;
+    G[j0 * GLD + i0] = (double)g00;
+    G[i0 * GLD + j0 + 1] = (double)g01;
+    G[(j0 + 1) * GLD + i0] = (double)g01;
+    G[(i0 + 1) * GLD + j0] = (double)g10;
+    G[j0 * GLD + i0 + 1] = (double)g10;
+    G[(i0 + 1) * GLD + j0 + 1] = (double)g11;
+    G[(j0 + 1) * GLD + i0 + 1] = (double)g11;
   }
   __syncthreads();
   // ---- scale to trace in [1, 2) (exact, power of two), so that G^16 neither overflows nor underflows
-  if (warp < 2) {
-    double *G = warp ? G1 : G0;
-    double tr = G[lane * (M2DP_PQ + 1)] + G[(lane + 32) * (M2DP_PQ + 1)];
+  if (warp == 0) {
+    double tr = G[lane * (GLD + 1)] + G[(lane + 32) * (GLD + 1)];
     tr = warp_sum(tr);
     tr = __shfl_sync(0xffffffffu, tr, 0);
-    if (lane == 0) S.sig[warp] = tr > 0.0 ? scalbn(1.0, -ilogb(tr)) : 0.0;
+    if (lane == 0) S.sig = tr > 0.0 ? scalbn(1.0, -ilogb(tr)) : 0.0;
   }
   __syncthreads();
-  for (int e = tid; e < 2 * M2DP_PQ * M2DP_PQ; e += M2_THREADS) {
-    double *G = (e >> 12) ? G1 : G0;
-    G[e & 4095] *= S.sig[e >> 12];
+  {
+    const double sc = S.sig;
+    for (int e = tid; e < M2DP_PQ * GLD; e += M2_THREADS) G[e] *= sc;   // (the 4 padding columns are never read)
   }
   __syncthreads();
-  for (int m = 0; m < 2; m++) {
-    double *G = m ? G1 : G0;
-    sym_square64(G, T);   // G^2
-    __syncthreads();
-    sym_square64(T, G);   // G^4
-    __syncthreads();
-    sym_square64(G, T);   // G^8
-    __syncthreads();
-    sym_square64(T, G);   // G^16
-    __syncthreads();
-  }
-  if (tid < 2 * M2DP_PQ) S.uvec[tid >> 6][tid & 63] = 0.125;  // all-ones / |.| (Perron start)
+  sym_square64(G, T);   // G^2
   __syncthreads();
-  // ---- power iteration with G^16: SVD_WARPS warps per matrix, 2 threads per row, named barrier per matrix
-  if (warp < 2 * SVD_WARPS) {
-    const int m = warp / SVD_WARPS, wl = warp % SVD_WARPS;
-    const double *G = m ? G1 : G0;
-    const int t = wl * 32 + lane;          // 0..127
+  sym_square64(T, G);   // G^4
+  __syncthreads();
+  sym_square64(G, T);   // G^8
+  __syncthreads();
+  sym_square64(T, G);   // G^16
+  if (tid < M2DP_PQ) S.uvec[tid] = 0.125;  // all-ones / |.| (Perron start)
+  __syncthreads();
+  // ---- power iteration with G^16: SVD_WARPS warps, 2 threads per row, named barrier
+  if (warp < SVD_WARPS) {
+    const int t = warp * 32 + lane;          // 0..127
     const int row = t >> 1, half = t & 1;
-    const int bar_id = 1 + m, bar_n = SVD_WARPS * 32;
+    const int bar_n = SVD_WARPS * 32;
     for (int iter = 0; iter < 2000; iter++) {
       double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll 8
       for (int k = 0; k < 32; k += 2) {
         const int c = half * 32 + k;
-        acc0 = fma(G[c * M2DP_PQ + row], S.uvec[m][c], acc0);   // G symmetric: column access is conflict-free
-        acc1 = fma(G[(c + 1) * M2DP_PQ + row], S.uvec[m][c + 1], acc1);
+        acc0 = fma(G[c * GLD + row], S.uvec[c], acc0);   // G symmetric: column access is conflict-free
+        acc1 = fma(G[(c + 1) * GLD + row], S.uvec[c + 1], acc1);
       }
       double acc = acc0 + acc1;
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       double sq = half == 0 ? acc * acc : 0.0;
       sq = warp_sum(sq);
-      if (lane == 0) S.red[m][wl] = sq;
-      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");   // all reads of uvec done
+      if (lane == 0) S.red[warp] = sq;
+      asm volatile("bar.sync 1, %0;" ::"r"(bar_n) : "memory");   // all reads of uvec done
       double nn = 0.0;
 #pragma unroll
-      for (int w = 0; w < SVD_WARPS; w++) nn += S.red[m][w];
+      for (int w = 0; w < SVD_WARPS; w++) nn += S.red[w];
       if (nn == 0.0) break;  // zero matrix (uniform over the group)
       const double inv = 1.0 / sqrt(nn);
       double d2 = 0.0;
       if (half == 0) {
         const double nv = acc * inv;
-        const double d = nv - S.uvec[m][row];
+        const double d = nv - S.uvec[row];
         d2 = d * d;
-        S.uvec[m][row] = nv;
+        S.uvec[row] = nv;
       }
       d2 = warp_sum(d2);
-      if (lane == 0) S.red2[m][wl] = d2;
-      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");   // uvec / red2 complete
+      if (lane == 0) S.red2[warp] = d2;
+      asm volatile("bar.sync 1, %0;" ::"r"(bar_n) : "memory");   // uvec / red2 complete
       double dd = 0.0;
 #pragma unroll
-      for (int w = 0; w < SVD_WARPS; w++) dd += S.red2[m][w];
+      for (int w = 0; w < SVD_WARPS; w++) dd += S.red2[w];
       if (dd < 1e-29) break;
     }
   }
   __syncthreads();
-  // ---- y = A^T u (128 per matrix), sigma = |y|
-  if (tid < 2 * M2DP_SR) {
-    const int m = tid >> 7, col = tid & 127;
-    const unsigned *A = m ? A1 : A0;
+  // ---- y = A^T u (128), sigma = |y|
+  if (tid < M2DP_SR) {
     double acc = 0.0;
 #pragma unroll 8
-    for (int r = 0; r < M2DP_PQ; r++) acc = fma((double)A[r * M2DP_SR + col], S.uvec[m][r], acc);
-    S.yv[m][col] = acc;
+    for (int r = 0; r < M2DP_PQ; r++) acc = fma((double)A[r * M2DP_SR + tid], S.uvec[r], acc);
+    S.yv[tid] = acc;
     const double sq = warp_sum(acc * acc);
-    if (lane == 0) S.red[m][warp & 3] = sq;
+    if (lane == 0) S.red[warp] = sq;
   }
   __syncthreads();
   // ---- outputs: u, v = y / sigma  (zero matrix: u = e_0, v = 0, the oracle's convention)
-  for (int e = tid; e < 2 * M2DP_SIG; e += M2_THREADS) {
-    const int m = e / M2DP_SIG, k = e % M2DP_SIG;
-    double *out = m ? out1 : out0;
-    const double sigma = sqrt((S.red[m][0] + S.red[m][1]) + (S.red[m][2] + S.red[m][3]));
+  if (tid < M2DP_SIG) {
+    const double sigma = sqrt((S.red[0] + S.red[1]) + (S.red[2] + S.red[3]));
     double v;
-    if (k < M2DP_PQ)
-      v = sigma == 0.0 ? (k == 0 ? 1.0 : 0.0) : S.uvec[m][k];
+    if (tid < M2DP_PQ)
+      v = sigma == 0.0 ? (tid == 0 ? 1.0 : 0.0) : S.uvec[tid];
     else
-      v = sigma == 0.0 ? 0.0 : S.yv[m][k - M2DP_PQ] / sigma;
-    out[k] = v;
+      v = sigma == 0.0 ? 0.0 : S.yv[tid - M2DP_PQ] / sigma;
+    out[tid] = v;
   }
   __syncthreads();
+}
+
+// sector map of the mirrored twin plane: (xp, yp) -> (-xp, yp), i.e. phi -> 180 deg - phi
+__device__ __forceinline__ int mirror_sr(int sr) { return (sr & ~15) | ((7 - (sr & 15)) & 15); }
+
+// One binning pass over the points of a scan for variant `var` (var < 0: pre-aligned input, no sign flips):
+// planes [PQ0, PQ1) -- and the degenerate planes of the whole table -- into histogram slot `slot`.  EXACT: integer
+// intensity sums.  Evaluations inside the guard band are pushed to the queue when `defer` (replayed by the caller in
+// fp64), else evaluated in fp64 at once.
+template <int PQ0, int PQ1, bool EXACT>
+__device__ __forceinline__ void bin_pass(M2Smem &S, const ScanRef &R, int var, int slot, bool defer, float R_f,
+                                         float iscale, unsigned long long degen_mask, int degen_sr_pos,
+                                         int degen_sr_neg) {
+  const int lane = threadIdx.x & 31;
+  unsigned *hcnt = S.cnt[slot];
+  int *hisum = S.isum[slot];
+  double *hsum = reinterpret_cast<double *>(S.isum);   // inexact mode (single slot)
+  unsigned long long *queue = reinterpret_cast<unsigned long long *>(S.T);
+  double ddx, ddy, ddz;
+  variant_signs(var, ddx, ddy, ddz);
+  const float fdx = (float)ddx, fdy = (float)ddy, fdz = (float)ddz;
+  const int n = R.n;
+  for (int i0 = 0; i0 < n; i0 += M2_THREADS) {
+    const int i = i0 + threadIdx.x;
+    const bool act = i < n;
+    float px = 0.0f, py = 0.0f, pz = 0.0f, it = 0.0f;
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    if (act) {
+      it = R.gi[i];
+      aligned_point64(R, i, ax, ay, az);
+      px = fdx * (float)ax;
+      py = fdy * (float)ay;
+      pz = fdz * (float)az;
+    }
+    const int iv = (int)(it * iscale);
+    // the fp32 error bound assumes coordinates below 128 m (the staging crops at 45 m)
+    const float r2_lim = fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz))) < 128.0f ? 1e10f : -1.0f;
+    // planes whose projection vectors are exactly zero (p=2, q=0): xp = yp = -0 if all three
+    // coordinates are negative, +0 otherwise, and every point lands in one of two bins -> warp-aggregated
+    for (unsigned long long dm = degen_mask; dm; dm &= dm - 1) {
+      const int pq = __ffsll((long long)dm) - 1;
+      // signs of the flipped fp64 coordinates (a flip of +-0 flips the sign bit too; identity: untouched)
+      const bool neg = act && (signbit(ax) != (ddx < 0.0)) && (signbit(ay) != (ddy < 0.0)) && (signbit(az) != (ddz < 0.0));
+#pragma unroll
+      for (int cls = 0; cls < 2; cls++) {
+        const bool mine = act && (neg == (cls == 1));
+        const unsigned ball = __ballot_sync(0xffffffffu, mine);
+        const int sr = cls ? degen_sr_neg : degen_sr_pos;
+        if (ball == 0u || sr < 0) continue;
+        if (EXACT) {
+          const int sum = __reduce_add_sync(0xffffffffu, mine ? iv : 0);
+          if (lane == 0) {
+            atomicAdd(&hcnt[pq * M2DP_SR + sr], (unsigned)__popc(ball));
+            atomicAdd(&hisum[pq * M2DP_SR + sr], sum);
+          }
+        } else {
+          // the reference adds the intensities point by point (M2DP.cpp:71); fp64 sums of floats in another
+          // order differ only when the exact sum needs more than 53 bits
+          const double sum = warp_sum(mine ? (double)it : 0.0);
+          if (lane == 0) {
+            atomicAdd(&hcnt[pq * M2DP_SR + sr], (unsigned)__popc(ball));
+            atomicAdd(&hsum[pq * M2DP_SR + sr], sum);
+          }
+        }
+      }
+    }
+    static_assert(PQ0 % 4 == 0 && PQ1 % 4 == 0, "planes are walked in groups of four");
+    // four planes at a time: the four proposals are independent arithmetic (no branch, no vote in between), then one
+    // vote for the rare guard-band case, then the updates
+#pragma unroll 1
+    for (int pq4 = PQ0; pq4 < PQ1; pq4 += 4) {
+      const unsigned dm4 = (unsigned)(degen_mask >> pq4) & 0xfu;   // (warp-uniform)
+      int idx4[4];
+      bool uns = false;
+      unsigned unsafe_bits = 0u;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int pq = pq4 + u;
+        const float4 ta = c_tab4[2 * pq], tb = c_tab4[2 * pq + 1];   // (x0, x1, x2, y0), (y1, y2, -, -)
+        const float xp = __fmaf_rn(ta.z, pz, __fmaf_rn(ta.y, py, ta.x * px));
+        const float yp = __fmaf_rn(tb.y, pz, __fmaf_rn(tb.x, py, ta.w * px));
+        bool safe;
+        const int sr = propose_bin(xp, yp, R_f, r2_lim, safe);
+        const bool degen = (dm4 >> u) & 1u;
+        idx4[u] = (safe && sr >= 0 && !degen && act) ? pq * M2DP_SR + sr : -1;
+        const bool un = act && !safe && !degen;
+        uns = uns || un;
+        unsafe_bits |= un ? (1u << u) : 0u;
+      }
+      if (__any_sync(0xffffffffu, uns)) {   // rare
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (!((unsafe_bits >> u) & 1u)) continue;
+          const int pq = pq4 + u;
+          bool queued = false;
+          if (defer) {
+            const int slot_q = atomicAdd(&S.qn, 1);
+            if (slot_q < QCAP) {
+              queue[slot_q] = ((unsigned long long)(unsigned)i << 8) | (unsigned)pq;
+              queued = true;
+            }
+          }
+          // a full queue cannot be shared with the twin variant any more: flagged by qn > QCAP, the caller redoes the
+          // pair one variant at a time
+          if (!queued && !defer) idx4[u] = m2dp_bin_exact(R, i, pq, var);   // the reference's fp64 expression
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int idx = idx4[u];
+        if (idx >= 0) {
+          atomicAdd(&hcnt[idx], 1u);
+          if (EXACT)
+            atomicAdd(&hisum[idx], iv);  // exact integer multiple of 2^emin, |sum| < 2^24
+          else
+            atomicAdd(&hsum[idx], (double)it);
+        }
+      }
+    }
+  }
+}
+
+// binarise slot (M2DP.cpp:84-91) in place, then the two dominant pairs -> one output row of 2 x 192
+template <bool EXACT>
+__device__ __forceinline__ void finish_variant(M2Smem &S, int slot, float ave, double unscale, double *row) {
+  unsigned *hcnt = S.cnt[slot];
+  int *hisum = S.isum[slot];
+  const double *hsum = reinterpret_cast<const double *>(S.isum);
+  unsigned bv[HB / M2_THREADS];
+#pragma unroll
+  for (int k = 0; k < HB / M2_THREADS; k++) {
+    const int b = threadIdx.x + k * M2_THREADS;
+    const unsigned c = hcnt[b];
+    unsigned v = 0u;
+    if (c) {
+      const double sum = EXACT ? (double)hisum[b] * unscale : hsum[b];
+      v = (sum / (double)c) > (double)ave ? 1u : 0u;
+    }
+    bv[k] = v;
+  }
+  __syncthreads();
+  unsigned *bin_mat = reinterpret_cast<unsigned *>(hisum);   // (inexact mode: the first half of the fp64 sums)
+#pragma unroll
+  for (int k = 0; k < HB / M2_THREADS; k++) bin_mat[threadIdx.x + k * M2_THREADS] = bv[k];
+  __syncthreads();
+  dominant_pair(hcnt, S.G, S.T, S, row);                // M2DP.cpp:94-98,107
+  dominant_pair(bin_mat, S.G, S.T, S, row + M2DP_SIG);  // M2DP.cpp:100-108
 }
 
 __global__ void __launch_bounds__(M2_THREADS, 1)
 m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ inten,
                      const int64_t *__restrict__ off, int nscan, double S_res_inv, double R_res_inv,
-                     int variants, double *__restrict__ hist, unsigned long long degen_mask) {
+                     int variants, int mirror_ok, double *__restrict__ hist, unsigned long long degen_mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   M2Smem &S = *reinterpret_cast<M2Smem *>(smem_raw);
   const int lane = threadIdx.x & 31;
-  const unsigned dm_lo = (unsigned)degen_mask, dm_hi = (unsigned)(degen_mask >> 32);
-  if (threadIdx.x < M2DP_PQ) {
-    const int k = threadIdx.x;
-    S.tab[2 * k] = make_float4(c_xproj32[3 * k], c_xproj32[3 * k + 1], c_xproj32[3 * k + 2], c_yproj32[3 * k]);
-    S.tab[2 * k + 1] = make_float4(c_yproj32[3 * k + 1], c_yproj32[3 * k + 2], 0.0f, 0.0f);
-  }
   // the two bins of a plane with zero projection vectors: M2DP.cpp:59-63 evaluated at (+0, +0) and (-0, -0)
   int degen_sr_pos, degen_sr_neg;
   {
@@ -275,17 +483,14 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
     degen_sr_pos = sp < M2DP_SR ? sp : -1;
     degen_sr_neg = sn < M2DP_SR ? sn : -1;
   }
-  const float S_f = (float)M2DP_NUM_S, R_f = (float)R_res_inv;
-  int *h_isum = reinterpret_cast<int *>(S.hsum);
-  unsigned *bin_mat = reinterpret_cast<unsigned *>(S.hsum);            // first 32 KB of hsum
-  double *G1 = S.hsum + HB / 2;                                       // second 32 KB of hsum
+  const float R_f = (float)R_res_inv;
+  unsigned long long *queue = reinterpret_cast<unsigned long long *>(S.T);
 
   for (int scan = blockIdx.x; scan < nscan; scan += gridDim.x) {
     const int64_t p0 = off[scan];
     const int n = (int)(off[scan + 1] - p0);
     const double *g = xyz + 3 * p0;
     const float *gi = inten + p0;
-    const int nst = n < M2_CAP ? n : M2_CAP;
 
     // ---- pass 1 (HBM): moments about the first point (mean, scatter matrix) and intensity sums
     double s11[11];
@@ -349,155 +554,87 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
     const float iscale = exact && emin != (1 << 20) ? (float)ldexp(1.0, -emin) : 0.0f;
     const double unscale = exact && emin != (1 << 20) ? ldexp(1.0, emin) : 0.0;
 
-    // ---- pass 2 (L2): aligned points -> shared memory as fp32 (the proposal path only needs fp32)
-    for (int i = threadIdx.x; i < nst; i += M2_THREADS) {
-      double ax, ay, az;
-      if (variants) {
-        pca_rotate(S.bc, g[3 * (size_t)i + 0], g[3 * (size_t)i + 1], g[3 * (size_t)i + 2], ax, ay, az);
-      } else {
-        ax = g[3 * (size_t)i + 0];
-        ay = g[3 * (size_t)i + 1];
-        az = g[3 * (size_t)i + 2];
-      }
-      S.ax[i] = (float)ax;
-      S.ay[i] = (float)ay;
-      S.az[i] = (float)az;
-    }
-
+    ScanRef R;
+    R.g = g;
+    R.gi = gi;
+    R.bc = S.bc;
+    R.n = n;
+    R.identity = variants ? 0 : 1;
+    R.S_res_inv = S_res_inv;
+    R.R_res_inv = R_res_inv;
     const int nvar = variants ? 4 : 1;
+    double *rows = hist + (size_t)scan * nvar * 2 * M2DP_SIG;
+
+    bool paired_done[2] = {false, false};
+    if (variants && exact && mirror_ok) {
+      // ---- variant pairs (a, a + 2): rows of planes 16..63 of variant a + 2 are mirrored copies of variant a's
+      for (int a = 0; a < 2; a++) {
+        for (int b = threadIdx.x; b < 2 * HB; b += M2_THREADS) {
+          (&S.cnt[0][0])[b] = 0u;
+          (&S.isum[0][0])[b] = 0;
+        }
+        if (threadIdx.x == 0) S.qn = 0;
+        __syncthreads();
+        bin_pass<0, M2DP_PQ, true>(S, R, a, 0, true, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
+        __syncthreads();
+        const int qn = S.qn;
+        __syncthreads();           // (everybody has read qn before the next pass may reset it)
+        if (qn > QCAP) continue;   // (uniform) too many guard-band evaluations to share: one variant at a time below
+        // twin rows: plane (p, q) of variant a  ->  plane (4 - p, q) of variant a + 2, sectors mirrored
+        for (int b = threadIdx.x; b < (M2DP_PQ - M2DP_NUM_Q) * M2DP_SR; b += M2_THREADS) {
+          const int pq = M2DP_NUM_Q + b / M2DP_SR, sr = b % M2DP_SR;
+          if ((degen_mask >> pq) & 1ull) continue;
+          const int pq2 = (M2DP_NUM_P - pq / M2DP_NUM_Q) * M2DP_NUM_Q + pq % M2DP_NUM_Q;
+          S.cnt[1][pq2 * M2DP_SR + mirror_sr(sr)] = S.cnt[0][pq * M2DP_SR + sr];
+          S.isum[1][pq2 * M2DP_SR + mirror_sr(sr)] = S.isum[0][pq * M2DP_SR + sr];
+        }
+        __syncthreads();
+        // the planes of variant a + 2 that have no twin (p = 0) and its degenerate planes (sign rule of its own)
+        bin_pass<0, M2DP_NUM_Q, true>(S, R, a + 2, 1, false, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
+        // deferred evaluations: the reference's fp64 expression, for each variant on its own
+        for (int e = threadIdx.x; e < qn; e += M2_THREADS) {
+          const unsigned long long w = queue[e];
+          const int i = (int)(w >> 8), pq = (int)(w & 0xffu);
+          const int iv = (int)(gi[i] * iscale);
+          const int i0 = m2dp_bin_exact(R, i, pq, a);
+          if (i0 >= 0) {
+            atomicAdd(&S.cnt[0][i0], 1u);
+            atomicAdd(&S.isum[0][i0], iv);
+          }
+          if (pq >= M2DP_NUM_Q) {
+            const int pq2 = (M2DP_NUM_P - pq / M2DP_NUM_Q) * M2DP_NUM_Q + pq % M2DP_NUM_Q;
+            const int i1 = m2dp_bin_exact(R, i, pq2, a + 2);
+            if (i1 >= 0) {
+              atomicAdd(&S.cnt[1][i1], 1u);
+              atomicAdd(&S.isum[1][i1], iv);
+            }
+          }
+        }
+        __syncthreads();
+        finish_variant<true>(S, 0, ave, unscale, rows + (size_t)a * 2 * M2DP_SIG);
+        finish_variant<true>(S, 1, ave, unscale, rows + (size_t)(a + 2) * 2 * M2DP_SIG);
+        paired_done[a] = true;
+      }
+    }
+    // ---- one variant at a time: pre-aligned input (class contract), inexact intensity sums, or a pair that could
+    // not be shared
     for (int var = 0; var < nvar; var++) {
-      // test_m2dp.cpp:47-57: dx outer, dy inner, both in {-1, +1}
-      ScanRef R;
-      R.g = g;
-      R.gi = gi;
-      R.bc = S.bc;
-      R.n = n;
-      R.nst = nst;
-      R.identity = variants ? 0 : 1;
-      R.dx = variants ? ((var >> 1) ? 1.0 : -1.0) : 1.0;
-      R.dy = variants ? ((var & 1) ? 1.0 : -1.0) : 1.0;
-      R.dz = R.dx * R.dy;
-      R.S_res_inv = S_res_inv;
-      R.R_res_inv = R_res_inv;
-      const float fdx = (float)R.dx, fdy = (float)R.dy, fdz = (float)R.dz;
-      for (int b = threadIdx.x; b < HB; b += M2_THREADS) {
-        S.hcnt[b] = 0u;
-        S.hsum[b] = 0.0;
+      if (variants && paired_done[var & 1]) continue;
+      for (int b = threadIdx.x; b < 2 * HB; b += M2_THREADS) {
+        (&S.cnt[0][0])[b] = 0u;
+        (&S.isum[0][0])[b] = 0;
       }
       __syncthreads();
-      // ---- M2DP.cpp:47-74
-      for (int i0 = 0; i0 < n; i0 += M2_THREADS) {
-        const int i = i0 + threadIdx.x;
-        const bool act = i < n;
-        float px = 0.0f, py = 0.0f, pz = 0.0f, it = 0.0f;
-        if (act) {
-          it = gi[i];
-          if (i < nst) {
-            px = fdx * S.ax[i];
-            py = fdy * S.ay[i];
-            pz = fdz * S.az[i];
-          } else {
-            double ax, ay, az;
-            aligned_point64(R, i, ax, ay, az);
-            px = (float)ax;
-            py = (float)ay;
-            pz = (float)az;
-          }
-        }
-        const int iv = (int)(it * iscale);
-        // the fp32 error bound below assumes coordinates below 128 m (the staging crops at 45 m)
-        const float r2_lim = fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz))) < 128.0f ? 1e10f : -1.0f;
-        // planes whose projection vectors are exactly zero (p=2, q=0): xp = yp = -0 if all three
-        // coordinates are negative, +0 otherwise, and every point lands in one of two bins -> warp-aggregated
-        for (unsigned long long dm = degen_mask; dm; dm &= dm - 1) {
-          const int pq = __ffsll((long long)dm) - 1;
-          bool neg;
-          if (i < nst || !act) {
-            neg = px < 0.0f && py < 0.0f && pz < 0.0f;
-            // an fp32 coordinate that rounded to zero: decide on the fp64 point
-            if (act && (px == 0.0f || py == 0.0f || pz == 0.0f)) {
-              double ax, ay, az;
-              aligned_point64(R, i, ax, ay, az);
-              neg = signbit(ax) && signbit(ay) && signbit(az);
-            }
-          } else {
-            double ax, ay, az;
-            aligned_point64(R, i, ax, ay, az);
-            neg = signbit(ax) && signbit(ay) && signbit(az);
-          }
-#pragma unroll
-          for (int cls = 0; cls < 2; cls++) {
-            const bool mine = act && (neg == (cls == 1));
-            const unsigned ball = __ballot_sync(0xffffffffu, mine);
-            const int sr = cls ? degen_sr_neg : degen_sr_pos;
-            if (ball == 0u || sr < 0) continue;
-            if (exact) {
-              const int sum = __reduce_add_sync(0xffffffffu, mine ? iv : 0);
-              if (lane == 0) {
-                atomicAdd(&S.hcnt[pq * M2DP_SR + sr], (unsigned)__popc(ball));
-                atomicAdd(&h_isum[2 * (pq * M2DP_SR + sr)], sum);
-              }
-            } else {
-              // the reference adds the intensities point by point (M2DP.cpp:71); fp64 sums of floats in another
-              // order differ only when the exact sum needs more than 53 bits
-              const double sum = warp_sum(mine ? (double)it : 0.0);
-              if (lane == 0) {
-                atomicAdd(&S.hcnt[pq * M2DP_SR + sr], (unsigned)__popc(ball));
-                atomicAdd(&S.hsum[pq * M2DP_SR + sr], sum);
-              }
-            }
-          }
-        }
-#pragma unroll 2
-        for (int pq = 0; pq < M2DP_PQ; pq++) {
-          if (((pq < 32 ? dm_lo : dm_hi) >> (pq & 31)) & 1u) continue;
-          const float4 ta = S.tab[2 * pq], tb = S.tab[2 * pq + 1];   // (x0, x1, x2, y0), (y1, y2, -, -)
-          const float xp = __fmaf_rn(ta.z, pz, __fmaf_rn(ta.y, py, ta.x * px));
-          const float yp = __fmaf_rn(tb.y, pz, __fmaf_rn(tb.x, py, ta.w * px));
-          const float r2 = __fmaf_rn(xp, xp, yp * yp);
-          const float rinv = rsqrtf(r2);
-          const float tf = fast_turns(yp, xp) * S_f;
-          const float rf = r2 * rinv * R_f;
-          const float ft = floorf(tf), fr = floorf(rf);
-          // distance to the nearest bin edge = 0.5 - |frac - 0.5|
-          const float et = fabsf((tf - ft) - 0.5f), er = fabsf((rf - fr) - 0.5f);
-          // fp32 error of the proposal: the projections are good to 2e-5 m (|p| < 128 m), i.e. 5e-5 / rho sectors
-          // and 4e-6 rings, plus 4e-6 sectors from fast_turns and 3e-6 rings from rsqrt; accepted with a 3x margin
-          const bool safe = et < 0.5f - 2e-5f - 1.5e-4f * rinv && er < 0.5f - M2_GUARD_R && tf < (float)M2DP_NUM_S &&
-                            rf < (float)M2DP_NUM_R && r2 > 1e-2f && r2 < r2_lim;
-          int idx = safe ? pq * M2DP_SR + __float2int_rz(__fmaf_rn(fr, (float)M2DP_NUM_S, ft)) : -1;
-          if (__any_sync(0xffffffffu, act && !safe)) {   // rare: the reference's fp64 expression
-            if (act && !safe) idx = m2dp_bin_exact(R, i, pq);
-          }
-          if (act && idx >= 0) {
-            atomicAdd(&S.hcnt[idx], 1u);
-            if (exact)
-              atomicAdd(&h_isum[2 * idx], iv);  // exact integer multiple of 2^emin, |sum| < 2^24
-            else
-              atomicAdd(&S.hsum[idx], (double)it);
-          }
-        }
+      const int v = variants ? var : -1;
+      if (exact) {
+        bin_pass<0, M2DP_PQ, true>(S, R, v, 0, false, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
+        __syncthreads();
+        finish_variant<true>(S, 0, ave, unscale, rows + (size_t)var * 2 * M2DP_SIG);
+      } else {
+        bin_pass<0, M2DP_PQ, false>(S, R, v, 0, false, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
+        __syncthreads();
+        finish_variant<false>(S, 0, ave, unscale, rows + (size_t)var * 2 * M2DP_SIG);
       }
-      __syncthreads();
-      // ---- M2DP.cpp:84-91: binarise (registers first: the u32 matrix overwrites the sums in place)
-      unsigned bv[HB / M2_THREADS];
-#pragma unroll
-      for (int k = 0; k < HB / M2_THREADS; k++) {
-        const int b = threadIdx.x + k * M2_THREADS;
-        const unsigned c = S.hcnt[b];
-        unsigned v = 0u;
-        if (c) {
-          const double sum = exact ? (double)h_isum[2 * b] * unscale : S.hsum[b];
-          v = (sum / (double)c) > (double)ave ? 1u : 0u;
-        }
-        bv[k] = v;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < HB / M2_THREADS; k++) bin_mat[threadIdx.x + k * M2_THREADS] = bv[k];
-      __syncthreads();
-      double *row = hist + ((size_t)scan * nvar + var) * 2 * M2DP_SIG;
-      dominant_pairs(S.hcnt, bin_mat, S.G0, G1, S.T, S, row, row + M2DP_SIG);   // M2DP.cpp:94-108
     }
     __syncthreads();
   }
@@ -542,14 +679,12 @@ cudaError_t launch_m2dp_generate(const double *xyz, const float *inten, const in
   if (e != cudaSuccess) return e;
   e = cudaMemcpyToSymbolAsync(c_yproj, yp, sizeof(yp), 0, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return e;
-  float xp32[3 * M2DP_PQ], yp32[3 * M2DP_PQ];
-  for (int k = 0; k < 3 * M2DP_PQ; k++) {
-    xp32[k] = (float)xp[k];
-    yp32[k] = (float)yp[k];
+  float4 tab[2 * M2DP_PQ];
+  for (int k = 0; k < M2DP_PQ; k++) {
+    tab[2 * k] = make_float4((float)xp[3 * k], (float)xp[3 * k + 1], (float)xp[3 * k + 2], (float)yp[3 * k]);
+    tab[2 * k + 1] = make_float4((float)yp[3 * k + 1], (float)yp[3 * k + 2], 0.0f, 0.0f);
   }
-  e = cudaMemcpyToSymbolAsync(c_xproj32, xp32, sizeof(xp32), 0, cudaMemcpyHostToDevice, st);
-  if (e != cudaSuccess) return e;
-  e = cudaMemcpyToSymbolAsync(c_yproj32, yp32, sizeof(yp32), 0, cudaMemcpyHostToDevice, st);
+  e = cudaMemcpyToSymbolAsync(c_tab4, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(m2dp_generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(M2Smem));
   if (e != cudaSuccess) return e;
@@ -564,8 +699,23 @@ cudaError_t launch_m2dp_generate(const double *xyz, const float *inten, const in
     for (int c = 0; c < 3; c++) zero = zero && !std::signbit(xp[3 * k + c]) && !std::signbit(yp[3 * k + c]);
     if (zero) degen_mask |= 1ull << k;
   }
+  // variant sharing (see the file header): the rows of planes (p, q), p = 1..3, of variant a + 2 are mirrored copies of
+  // the rows of planes (4 - p, q) of variant a iff  S_{a+2} xProj[4-p][q] == -S_a xProj[p][q]  and
+  // S_{a+2} yProj[4-p][q] == S_a yProj[p][q]  hold EXACTLY (then the reference's fp64 expressions are mirror images too)
+  int mirror_ok = 1;
+  for (int a = 0; a < 2 && mirror_ok; a++) {
+    const double sa[3] = {-1.0, a ? 1.0 : -1.0, a ? -1.0 : 1.0};         // variant a:     dx = -1, dy, dx * dy
+    const double sb[3] = {1.0, a ? 1.0 : -1.0, a ? 1.0 : -1.0};          // variant a + 2: dx = +1, dy, dx * dy
+    for (int p = 1; p < M2DP_NUM_P && mirror_ok; p++)
+      for (int q = 0; q < M2DP_NUM_Q && mirror_ok; q++) {
+        const int k = p * M2DP_NUM_Q + q, k2 = (M2DP_NUM_P - p) * M2DP_NUM_Q + q;
+        for (int c = 0; c < 3; c++)
+          if (sb[c] * xp[3 * k2 + c] != -(sa[c] * xp[3 * k + c]) || sb[c] * yp[3 * k2 + c] != sa[c] * yp[3 * k + c]) mirror_ok = 0;
+        if (((degen_mask >> k) & 1ull) != ((degen_mask >> k2) & 1ull)) mirror_ok = 0;
+      }
+  }
   m2dp_generate_kernel<<<grid, M2_THREADS, sizeof(M2Smem), st>>>(xyz, inten, off, nscan, S_res_inv, R_res_inv,
-                                                                 do_align_and_variants ? 1 : 0, hist, degen_mask);
+                                                                 do_align_and_variants ? 1 : 0, mirror_ok, hist, degen_mask);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
