@@ -100,7 +100,11 @@ __device__ __forceinline__ void variant_signs(int var, double &dx, double &dy, d
   dz = dx * dy;
 }
 
-// M2DP.cpp:56-68 in fp64, exactly the reference's expression, for point i under variant var: flat histogram index or -1
+// M2DP.cpp:56-68 in fp64 for point i under variant var: flat histogram index or -1.  xp, yp and the ring are the
+// reference's own expressions.  The sector floor((atan2(yp, xp) + pi) * 16 / 2pi) is first decided without the
+// arctangent, by the comparisons of propose_bin carried out in fp64: the reference's angle is good to ~1e-15 sectors,
+// so outside a 1e-13 band around the sector edges (in units of min / max) the comparisons give its floor; inside the
+// band the reference's expression itself is evaluated.
 __device__ __noinline__ int m2dp_bin_exact(const ScanRef &R, int i, int pq, int var) {
   const double PI = 3.14159265358979323846;
   double px, py, pz;
@@ -114,12 +118,56 @@ __device__ __noinline__ int m2dp_bin_exact(const ScanRef &R, int i, int pq, int 
   }
   const double xp = (c_xproj[3 * pq] * px + c_xproj[3 * pq + 1] * py) + c_xproj[3 * pq + 2] * pz;
   const double yp = (c_yproj[3 * pq] * px + c_yproj[3 * pq + 1] * py) + c_yproj[3 * pq + 2] * pz;
-  const double ang = (atan2(yp, xp) + PI) * R.S_res_inv;
   const double rad = sqrt(xp * xp + yp * yp) * R.R_res_inv;
-  if (!(rad < (double)M2DP_SR) || !(ang < 32.0)) return -1;
-  const int si = (int)floor(ang), ri = (int)floor(rad);
+  if (!(rad < (double)M2DP_SR)) return -1;     // (also NaN)
+  const int ri = (int)floor(rad);
+  const double ax = fabs(xp), ay = fabs(yp);
+  const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+  const double T = 0.41421356237309503;        // tan(pi / 8)
+  const double tm = T * mx, band = 1e-13 * mx;
+  int si;
+  if (mn > band && fabs(mn - tm) > band && mx - mn > band && mx < 1e300) {
+    int k = mn > tm ? 1 : 0;
+    k = ay > ax ? 3 - k : k;
+    const bool sx = xp < 0.0, sy = yp < 0.0;
+    si = (sy ? 0 : 8) + (k ^ (sx != sy ? 7 : 0));
+  } else {
+    const double ang = (atan2(yp, xp) + PI) * R.S_res_inv;
+    if (!(ang < 32.0)) return -1;
+    si = (int)floor(ang);
+  }
   const int sr = ri * M2DP_NUM_S + si;  // M2DP.cpp:63
   return sr < M2DP_SR ? pq * M2DP_SR + sr : -1;  // M2DP.cpp:66 (si == 16 aliases into ring ri+1)
+}
+
+// the reference's bin of (point i, plane pq) under variant var, added to histogram slot `slot`
+template <bool EXACT>
+__device__ __forceinline__ void add_exact(M2Smem &S, const ScanRef &R, int i, int pq, int var, int slot, float iscale) {
+  const int idx = m2dp_bin_exact(R, i, pq, var);
+  if (idx < 0) return;
+  atomicAdd(&S.cnt[slot][idx], 1u);
+  if (EXACT)
+    atomicAdd(&S.isum[slot][idx], (int)(R.gi[i] * iscale));
+  else
+    atomicAdd(reinterpret_cast<double *>(S.isum) + idx, (double)R.gi[i]);
+}
+
+// plane of variant a + 2 that is the mirror image of plane pq (p >= 1) of variant a
+__device__ __forceinline__ int twin_plane(int pq) {
+  return (M2DP_NUM_P - pq / M2DP_NUM_Q) * M2DP_NUM_Q + pq % M2DP_NUM_Q;
+}
+
+// queue entry of a guard-band evaluation: point i, plane pq, histogram slot, and whether the twin plane of the
+// other variant of the pair (slot 1) has to be evaluated as well
+__device__ __forceinline__ unsigned long long queue_entry(int i, int pq, int slot, bool twin) {
+  return ((unsigned long long)(unsigned)i << 8) | (unsigned)(pq | (slot << 6) | (twin ? 0x80 : 0));
+}
+template <bool EXACT>
+__device__ __forceinline__ void run_entry(M2Smem &S, const ScanRef &R, unsigned long long w, int var_slot0,
+                                          int var_slot1, float iscale) {
+  const int i = (int)(w >> 8), pq = (int)(w & 0x3fu), slot = (int)((w >> 6) & 1u);
+  add_exact<EXACT>(S, R, i, pq, slot ? var_slot1 : var_slot0, slot, iscale);
+  if (w & 0x80u) add_exact<EXACT>(S, R, i, twin_plane(pq), var_slot1, 1, iscale);
 }
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -133,8 +181,8 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   return r;
 }
 
-// fp32 proposal of the (ring, sector) bin of projected coordinates (xp, yp): sr = ri * 16 + si, or -1 when the point
-// is provably outside the 8 rings, and `safe` = the proposal is certainly the bin of the fp64 expression.
+// fp32 proposal of the (ring, sector) bin of projected coordinates (xp, yp): sr = ri * 16 + si, `inside` = within the
+// 8 rings (M2DP.cpp:66), and `ok` = the proposal is certainly what the fp64 expression gives.
 //   error budget: xp, yp good to delta = 2e-5 m (|p| < 128 m, checked by the caller through r2_lim).  With
 //   mx = max(|xp|, |yp|), mn = min: a = mn / mx is good to 2 delta / mx + 3e-7, and the three decisions (sign pattern,
 //   |yp| > |xp|, a > tan 22.5) are right whenever a is further than that from {0, tan 22.5, 1}; accepted with a 3x
@@ -142,12 +190,16 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 // Sector of the fp64 expression: si = floor(8 + phi / 22.5 deg), phi = atan2(yp, xp).  With k = floor(alpha / 22.5)
 // of the first-quadrant angle alpha = atan(|yp| / |xp|):  phi = alpha -> 8 + k;  180 - alpha -> 15 - k;
 // -alpha -> 7 - k;  alpha - 180 -> k   (never on an edge: those evaluations are not safe).
-__device__ __forceinline__ int propose_bin(float xp, float yp, float R_f, float r2_lim, bool &safe) {
+__device__ __forceinline__ int propose_bin(float xp, float yp, float R_f, float r2_lim, bool &ok, bool &inside) {
   const float ax = fabsf(xp), ay = fabsf(yp);
   const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
   const float r2 = __fmaf_rn(xp, xp, yp * yp);
   const float rf = sqrt_approx(r2) * R_f;
-  const float fr = floorf(rf);
+  // floor(rf) for 0 <= rf < 2^22 without a conversion instruction: (rf - 0.5) + 1.5 * 2^23 rounds to the nearest
+  // integer, which is floor(rf) unless rf is within rounding of an integer -- and those are inside the ring guard
+  const float tr = (rf - 0.5f) + 12582912.0f;
+  const float fr = tr - 12582912.0f;
+  const int ri = (int)(__float_as_uint(tr) & 0x3fffffu);
   const float er = fabsf((rf - fr) - 0.5f);
   const float inv = rcp_approx(mx);
   const float a = mn * inv;
@@ -160,34 +212,46 @@ __device__ __forceinline__ int propose_bin(float xp, float yp, float R_f, float 
   const int m7 = (sx != sy) ? 7 : 0;           // upper half plane: xp < 0 mirrors k; lower half: xp > 0 mirrors
   const int sector = (int)((sy ^ 1u) << 3) + (k ^ m7);
   // (a small radius needs no test of its own: eg grows like 1 / mx and d never exceeds 0.293)
-  safe = d > eg && er < 0.5f - M2_GUARD_R && r2 < r2_lim;
-  const int ri = __float2int_rz(fr);
-  return rf < (float)M2DP_NUM_R ? ri * M2DP_NUM_S + sector : -1;
+  ok = d > eg && er < 0.5f - M2_GUARD_R && r2 < r2_lim;
+  inside = rf < (float)M2DP_NUM_R;
+  return ri * M2DP_NUM_S + sector;
 }
 
 // Y = X X for a symmetric 64 x 64 fp64 matrix (leading dimension GLD) on the fp64 tensor cores
-// (mma.sync.m8n8k4.f64: 256 multiply-adds per warp instruction instead of 32).  Warp w owns the 8 x 16 output strip
-// rows 8 (w / 4), columns 16 (w % 4); the B fragment X[k][j] is read as X[j][k] (symmetry), so both operands are 8 x 4
-// row-major reads.  Fragments (PTX ISA, m8n8k4 .f64): A[lane / 4][lane % 4], B[lane % 4][lane / 4],
+// (mma.sync.m8n8k4.f64: 256 multiply-adds per warp instruction instead of 32).  Warp w owns the 8 x 8 output
+// tile(s) listed below; the B fragment X[k][j] is read as X[j][k] (symmetry), so both operands are 8 x 4 row-major
+// reads.  Fragments (PTX ISA, m8n8k4 .f64): A[lane / 4][lane % 4], B[lane % 4][lane / 4],
 // C[lane / 4][2 (lane % 4) + {0, 1}].
 __device__ __forceinline__ void sym_square64(const double *X, double *Y) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = lane >> 2, c = lane & 3;
-  const int i0 = (warp >> 2) * 8, j0 = (warp & 3) * 16;
-  const double *pa = X + (i0 + r) * GLD + c, *pb0 = X + (j0 + r) * GLD + c, *pb1 = pb0 + 8 * GLD;
-  double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+  // Y is symmetric too: only the 36 tiles (I, J <= I) of the 8 x 8 tile grid are computed, the others are mirrored.
+  // Tile t = I (I + 1) / 2 + J; warp w takes tile w, warps 0..3 also tile 32 + w.
+  for (int t = warp; t < 36; t += 32) {
+    int I = 0;
+    while ((I + 1) * (I + 2) / 2 <= t) I++;
+    const int J = t - I * (I + 1) / 2;
+    const int i0 = I * 8, j0 = J * 8;
+    const double *pa = X + (i0 + r) * GLD + c, *pb = X + (j0 + r) * GLD + c;
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;   // two accumulator pairs: even / odd k steps (shorter chains)
 #pragma unroll 4
-  for (int k0 = 0; k0 < M2DP_PQ; k0 += 4) {
-    const double a = pa[k0], b0 = pb0[k0], b1 = pb1[k0];
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                 : "+d"(c00), "+d"(c01)
-                 : "d"(a), "d"(b0));
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                 : "+d"(c10), "+d"(c11)
-                 : "d"(a), "d"(b1));
+    for (int k0 = 0; k0 < M2DP_PQ; k0 += 8) {
+      const double a0 = pa[k0], b0 = pb[k0], a1 = pa[k0 + 4], b1 = pb[k0 + 4];
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                   : "+d"(c0), "+d"(c1)
+                   : "d"(a0), "d"(b0));
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                   : "+d"(e0), "+d"(e1)
+                   : "d"(a1), "d"(b1));
+    }
+    c0 += e0;
+    c1 += e1;
+    *reinterpret_cast<double2 *>(Y + (i0 + r) * GLD + j0 + 2 * c) = make_double2(c0, c1);
+    if (I != J) {
+      Y[(j0 + 2 * c) * GLD + i0 + r] = c0;
+      Y[(j0 + 2 * c + 1) * GLD + i0 + r] = c1;
+    }
   }
-  *reinterpret_cast<double2 *>(Y + (i0 + r) * GLD + j0 + 2 * c) = make_double2(c00, c01);
-  *reinterpret_cast<double2 *>(Y + (i0 + r) * GLD + j0 + 8 + 2 * c) = make_double2(c10, c11);
 }
 
 // dominant singular pair of the 64 x 128 matrix A (u32, shared memory).  G / T: 64 x 64 fp64 workspaces.
@@ -195,12 +259,27 @@ __device__ __forceinline__ void sym_square64(const double *X, double *Y) {
 //   G = A A^T exactly (64-bit integers), scaled by a power of two to trace ~ 1;  G^16 by four squarings;
 //   power iteration with G^16 from the all-ones vector (Perron pair: entrywise non-negative);
 //   sigma = |A^T u|, v = A^T u / sigma.
+template <bool BINARY>
 __device__ void dominant_pair(const unsigned *A, double *G, double *T, M2Smem &S, double *out) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (BINARY) {
+    // 0 / 1 matrix: rows as 128-bit masks (in the T area), G[i][j] = popcount(row_i & row_j)
+    unsigned *mask = reinterpret_cast<unsigned *>(T);
+    for (int w = warp; w < M2DP_PQ * 4; w += M2_THREADS / 32) {   // word w: row w / 4, columns 32 (w % 4) ..
+      const unsigned bit = __ballot_sync(0xffffffffu, A[(w >> 2) * M2DP_SR + (w & 3) * 32 + lane] != 0u);
+      if (lane == 0) mask[w] = bit;
+    }
+    __syncthreads();
+    for (int e = tid; e < M2DP_PQ * M2DP_PQ; e += M2_THREADS) {
+      const int i = e >> 6, j = e & 63;
+      const uint4 a = reinterpret_cast<const uint4 *>(mask)[i], b = reinterpret_cast<const uint4 *>(mask)[j];
+      G[i * GLD + j] = (double)(__popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w));
+    }
+  } else
   // ---- Gram matrix: thread t < 528 owns the 2 x 2 block (bi, bj <= bi) of the lower block triangle.  Lane l walks k
   // in 16-byte steps starting at step l, so the 8 lanes of a quarter-warp always hit 8 different 16-byte bank groups
   // whatever rows they read (rows are 512 B apart); integer sums do not care about the order.
-  if (tid < 528) {
+  if (tid < 528) {   // (count matrix)
     int bi = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
     while ((bi + 1) * (bi + 2) / 2 <= tid) bi++;
     while (bi * (bi + 1) / 2 > tid) bi--;
@@ -279,7 +358,15 @@ __device__ void dominant_pair(const unsigned *A, double *G, double *T, M2Smem &S
 #pragma unroll
       for (int w = 0; w < SVD_WARPS; w++) nn += S.red[w];
       if (nn == 0.0) break;  // zero matrix (uniform over the group)
-      const double inv = 1.0 / sqrt(nn);
+      // 1 / sqrt(nn): fp32 seed + three Newton steps (rel. error 1e-7 -> 1e-14 -> 1e-28 -> rounding), instead of the
+      // fp64 square root and division routines (the normalisation is on the critical path of every iteration)
+      double inv = (double)rsqrtf((float)nn);
+      {
+        const double hn = 0.5 * nn;
+        inv = inv * fma(-hn * inv, inv, 1.5);
+        inv = inv * fma(-hn * inv, inv, 1.5);
+        inv = inv * fma(-hn * inv, inv, 1.5);
+      }
       double d2 = 0.0;
       if (half == 0) {
         const double nv = acc * inv;
@@ -297,11 +384,19 @@ __device__ void dominant_pair(const unsigned *A, double *G, double *T, M2Smem &S
     }
   }
   __syncthreads();
-  // ---- y = A^T u (128), sigma = |y|
+  // ---- y = A^T u (128), sigma = |y|: 8 threads per column (8 rows each), partial sums through the T area
+  {
+    const int col = tid & (M2DP_SR - 1), part = tid >> 7;
+    double acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < M2DP_PQ / 8; r++) acc = fma((double)A[(part * 8 + r) * M2DP_SR + col], S.uvec[part * 8 + r], acc);
+    T[part * M2DP_SR + col] = acc;
+  }
+  __syncthreads();
   if (tid < M2DP_SR) {
     double acc = 0.0;
-#pragma unroll 8
-    for (int r = 0; r < M2DP_PQ; r++) acc = fma((double)A[r * M2DP_SR + tid], S.uvec[r], acc);
+#pragma unroll
+    for (int part = 0; part < 8; part++) acc += T[part * M2DP_SR + tid];
     S.yv[tid] = acc;
     const double sq = warp_sum(acc * acc);
     if (lane == 0) S.red[warp] = sq;
@@ -323,14 +418,13 @@ __device__ void dominant_pair(const unsigned *A, double *G, double *T, M2Smem &S
 // sector map of the mirrored twin plane: (xp, yp) -> (-xp, yp), i.e. phi -> 180 deg - phi
 __device__ __forceinline__ int mirror_sr(int sr) { return (sr & ~15) | ((7 - (sr & 15)) & 15); }
 
-// One binning pass over the points of a scan for variant `var` (var < 0: pre-aligned input, no sign flips):
-// planes [PQ0, PQ1) -- and the degenerate planes of the whole table -- into histogram slot `slot`.  EXACT: integer
-// intensity sums.  Evaluations inside the guard band are pushed to the queue when `defer` (replayed by the caller in
-// fp64), else evaluated in fp64 at once.
-template <int PQ0, int PQ1, bool EXACT>
-__device__ __forceinline__ void bin_pass(M2Smem &S, const ScanRef &R, int var, int slot, bool defer, float R_f,
-                                         float iscale, unsigned long long degen_mask, int degen_sr_pos,
-                                         int degen_sr_neg) {
+// One block of 1024 points (FULL: all lanes hold a point) of a binning pass.  EXACT: integer intensity sums.
+// Evaluations inside the guard band are pushed to the queue (replayed by the caller in fp64, replay_queue);
+// twin_var >= 0: the pass is variant a of a pair, and planes p >= 1 also stand for their twins of variant twin_var.
+template <int PQ0, int PQ1, bool EXACT, bool FULL>
+__device__ __forceinline__ void bin_block(M2Smem &S, const ScanRef &R, int var, int slot, int twin_var, float R_f,
+                                          float iscale, unsigned long long degen_mask, int degen_sr_pos,
+                                          int degen_sr_neg, int i0) {
   const int lane = threadIdx.x & 31;
   unsigned *hcnt = S.cnt[slot];
   int *hisum = S.isum[slot];
@@ -340,9 +434,9 @@ __device__ __forceinline__ void bin_pass(M2Smem &S, const ScanRef &R, int var, i
   variant_signs(var, ddx, ddy, ddz);
   const float fdx = (float)ddx, fdy = (float)ddy, fdz = (float)ddz;
   const int n = R.n;
-  for (int i0 = 0; i0 < n; i0 += M2_THREADS) {
+  {
     const int i = i0 + threadIdx.x;
-    const bool act = i < n;
+    const bool act = FULL || i < n;
     float px = 0.0f, py = 0.0f, pz = 0.0f, it = 0.0f;
     double ax = 0.0, ay = 0.0, az = 0.0;
     if (act) {
@@ -399,11 +493,11 @@ __device__ __forceinline__ void bin_pass(M2Smem &S, const ScanRef &R, int var, i
         const float4 ta = c_tab4[2 * pq], tb = c_tab4[2 * pq + 1];   // (x0, x1, x2, y0), (y1, y2, -, -)
         const float xp = __fmaf_rn(ta.z, pz, __fmaf_rn(ta.y, py, ta.x * px));
         const float yp = __fmaf_rn(tb.y, pz, __fmaf_rn(tb.x, py, ta.w * px));
-        bool safe;
-        const int sr = propose_bin(xp, yp, R_f, r2_lim, safe);
-        const bool degen = (dm4 >> u) & 1u;
-        idx4[u] = (safe && sr >= 0 && !degen && act) ? pq * M2DP_SR + sr : -1;
-        const bool un = act && !safe && !degen;
+        bool safe, inside;
+        const int sr = propose_bin(xp, yp, R_f, r2_lim, safe, inside);
+        const bool live = FULL ? !((dm4 >> u) & 1u) : (act && !((dm4 >> u) & 1u));
+        idx4[u] = (safe && inside && live) ? pq * M2DP_SR + sr : -1;
+        const bool un = live && !safe;
         uns = uns || un;
         unsafe_bits |= un ? (1u << u) : 0u;
       }
@@ -412,17 +506,17 @@ __device__ __forceinline__ void bin_pass(M2Smem &S, const ScanRef &R, int var, i
         for (int u = 0; u < 4; u++) {
           if (!((unsafe_bits >> u) & 1u)) continue;
           const int pq = pq4 + u;
-          bool queued = false;
-          if (defer) {
-            const int slot_q = atomicAdd(&S.qn, 1);
-            if (slot_q < QCAP) {
-              queue[slot_q] = ((unsigned long long)(unsigned)i << 8) | (unsigned)pq;
-              queued = true;
-            }
-          }
-          // a full queue cannot be shared with the twin variant any more: flagged by qn > QCAP, the caller redoes the
-          // pair one variant at a time
-          if (!queued && !defer) idx4[u] = m2dp_bin_exact(R, i, pq, var);   // the reference's fp64 expression
+          // deferred: replayed in fp64 by all threads in parallel after the pass (run_entry); a full queue is served
+          // on the spot
+          const bool twin = twin_var >= 0 && pq >= M2DP_NUM_Q;
+          const unsigned long long w = queue_entry(i, pq, slot, twin);
+          const int slot_q = atomicAdd(&S.qn, 1);
+          if (slot_q < QCAP)
+            queue[slot_q] = w;
+          else if (!twin)
+            run_entry<EXACT>(S, R, w, var, twin_var, iscale);
+          else
+            S.ibc[3] = 1;   // shared evaluations lost: the caller redoes the pair one variant at a time
         }
       }
 #pragma unroll
@@ -438,6 +532,28 @@ __device__ __forceinline__ void bin_pass(M2Smem &S, const ScanRef &R, int var, i
       }
     }
   }
+}
+
+// One binning pass over the points of a scan for variant `var` (var < 0: pre-aligned input, no sign flips):
+// planes [PQ0, PQ1) -- and the degenerate planes of the whole table -- into histogram slot `slot`.  Full blocks of
+// 1024 points take the variant without per-lane bounds handling.
+template <int PQ0, int PQ1, bool EXACT>
+__device__ __forceinline__ void bin_pass(M2Smem &S, const ScanRef &R, int var, int slot, int twin_var, float R_f,
+                                         float iscale, unsigned long long degen_mask, int degen_sr_pos,
+                                         int degen_sr_neg) {
+  int i0 = 0;
+  for (; i0 + M2_THREADS <= R.n; i0 += M2_THREADS)
+    bin_block<PQ0, PQ1, EXACT, true>(S, R, var, slot, twin_var, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg, i0);
+  if (i0 < R.n)
+    bin_block<PQ0, PQ1, EXACT, false>(S, R, var, slot, twin_var, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg, i0);
+}
+
+// the deferred evaluations of the passes since the queue was reset, one entry per thread
+template <bool EXACT>
+__device__ __forceinline__ void replay_queue(M2Smem &S, const ScanRef &R, int var_slot0, int var_slot1, float iscale) {
+  const unsigned long long *queue = reinterpret_cast<const unsigned long long *>(S.T);
+  const int qn = S.qn < QCAP ? S.qn : QCAP;
+  for (int e = threadIdx.x; e < qn; e += M2_THREADS) run_entry<EXACT>(S, R, queue[e], var_slot0, var_slot1, iscale);
 }
 
 // binarise slot (M2DP.cpp:84-91) in place, then the two dominant pairs -> one output row of 2 x 192
@@ -463,8 +579,8 @@ __device__ __forceinline__ void finish_variant(M2Smem &S, int slot, float ave, d
 #pragma unroll
   for (int k = 0; k < HB / M2_THREADS; k++) bin_mat[threadIdx.x + k * M2_THREADS] = bv[k];
   __syncthreads();
-  dominant_pair(hcnt, S.G, S.T, S, row);                // M2DP.cpp:94-98,107
-  dominant_pair(bin_mat, S.G, S.T, S, row + M2DP_SIG);  // M2DP.cpp:100-108
+  dominant_pair<false>(hcnt, S.G, S.T, S, row);               // M2DP.cpp:94-98,107
+  dominant_pair<true>(bin_mat, S.G, S.T, S, row + M2DP_SIG);  // M2DP.cpp:100-108
 }
 
 __global__ void __launch_bounds__(M2_THREADS, 1)
@@ -484,7 +600,6 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
     degen_sr_neg = sn < M2DP_SR ? sn : -1;
   }
   const float R_f = (float)R_res_inv;
-  unsigned long long *queue = reinterpret_cast<unsigned long long *>(S.T);
 
   for (int scan = blockIdx.x; scan < nscan; scan += gridDim.x) {
     const int64_t p0 = off[scan];
@@ -565,7 +680,30 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
     const int nvar = variants ? 4 : 1;
     double *rows = hist + (size_t)scan * nvar * 2 * M2DP_SIG;
 
-    bool paired_done[2] = {false, false};
+    // one variant on its own (pre-aligned input of the class contract, inexact intensity sums, asymmetric table, or a
+    // pair whose guard-band queue overflowed)
+    auto single_variant = [&](int var) {
+      for (int b = threadIdx.x; b < 2 * HB; b += M2_THREADS) {
+        (&S.cnt[0][0])[b] = 0u;
+        (&S.isum[0][0])[b] = 0;
+      }
+      if (threadIdx.x == 0) S.qn = 0;
+      __syncthreads();
+      const int v = variants ? var : -1;
+      if (exact) {
+        bin_pass<0, M2DP_PQ, true>(S, R, v, 0, -1, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
+        __syncthreads();
+        replay_queue<true>(S, R, v, v, iscale);
+        __syncthreads();
+        finish_variant<true>(S, 0, ave, unscale, rows + (size_t)var * 2 * M2DP_SIG);
+      } else {
+        bin_pass<0, M2DP_PQ, false>(S, R, v, 0, -1, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
+        __syncthreads();
+        replay_queue<false>(S, R, v, v, iscale);
+        __syncthreads();
+        finish_variant<false>(S, 0, ave, unscale, rows + (size_t)var * 2 * M2DP_SIG);
+      }
+    };
     if (variants && exact && mirror_ok) {
       // ---- variant pairs (a, a + 2): rows of planes 16..63 of variant a + 2 are mirrored copies of variant a's
       for (int a = 0; a < 2; a++) {
@@ -573,68 +711,39 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
           (&S.cnt[0][0])[b] = 0u;
           (&S.isum[0][0])[b] = 0;
         }
-        if (threadIdx.x == 0) S.qn = 0;
+        if (threadIdx.x == 0) {
+          S.qn = 0;
+          S.ibc[3] = 0;
+        }
         __syncthreads();
-        bin_pass<0, M2DP_PQ, true>(S, R, a, 0, true, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
+        bin_pass<0, M2DP_PQ, true>(S, R, a, 0, a + 2, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
         __syncthreads();
-        const int qn = S.qn;
-        __syncthreads();           // (everybody has read qn before the next pass may reset it)
-        if (qn > QCAP) continue;   // (uniform) too many guard-band evaluations to share: one variant at a time below
-        // twin rows: plane (p, q) of variant a  ->  plane (4 - p, q) of variant a + 2, sectors mirrored
+        if (S.ibc[3]) {   // (uniform) more guard-band evaluations than the queue holds
+          __syncthreads();
+          single_variant(a);
+          single_variant(a + 2);
+          continue;
+        }
+        // twin rows: plane (p, q) of variant a  ->  plane (4 - p, q) of variant a + 2, sectors mirrored (the guard-band
+        // evaluations are not in the histogram yet: they are replayed for each variant on its own below)
         for (int b = threadIdx.x; b < (M2DP_PQ - M2DP_NUM_Q) * M2DP_SR; b += M2_THREADS) {
           const int pq = M2DP_NUM_Q + b / M2DP_SR, sr = b % M2DP_SR;
           if ((degen_mask >> pq) & 1ull) continue;
-          const int pq2 = (M2DP_NUM_P - pq / M2DP_NUM_Q) * M2DP_NUM_Q + pq % M2DP_NUM_Q;
+          const int pq2 = twin_plane(pq);
           S.cnt[1][pq2 * M2DP_SR + mirror_sr(sr)] = S.cnt[0][pq * M2DP_SR + sr];
           S.isum[1][pq2 * M2DP_SR + mirror_sr(sr)] = S.isum[0][pq * M2DP_SR + sr];
         }
         __syncthreads();
         // the planes of variant a + 2 that have no twin (p = 0) and its degenerate planes (sign rule of its own)
-        bin_pass<0, M2DP_NUM_Q, true>(S, R, a + 2, 1, false, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
-        // deferred evaluations: the reference's fp64 expression, for each variant on its own
-        for (int e = threadIdx.x; e < qn; e += M2_THREADS) {
-          const unsigned long long w = queue[e];
-          const int i = (int)(w >> 8), pq = (int)(w & 0xffu);
-          const int iv = (int)(gi[i] * iscale);
-          const int i0 = m2dp_bin_exact(R, i, pq, a);
-          if (i0 >= 0) {
-            atomicAdd(&S.cnt[0][i0], 1u);
-            atomicAdd(&S.isum[0][i0], iv);
-          }
-          if (pq >= M2DP_NUM_Q) {
-            const int pq2 = (M2DP_NUM_P - pq / M2DP_NUM_Q) * M2DP_NUM_Q + pq % M2DP_NUM_Q;
-            const int i1 = m2dp_bin_exact(R, i, pq2, a + 2);
-            if (i1 >= 0) {
-              atomicAdd(&S.cnt[1][i1], 1u);
-              atomicAdd(&S.isum[1][i1], iv);
-            }
-          }
-        }
+        bin_pass<0, M2DP_NUM_Q, true>(S, R, a + 2, 1, -1, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
+        __syncthreads();
+        replay_queue<true>(S, R, a, a + 2, iscale);
         __syncthreads();
         finish_variant<true>(S, 0, ave, unscale, rows + (size_t)a * 2 * M2DP_SIG);
         finish_variant<true>(S, 1, ave, unscale, rows + (size_t)(a + 2) * 2 * M2DP_SIG);
-        paired_done[a] = true;
       }
-    }
-    // ---- one variant at a time: pre-aligned input (class contract), inexact intensity sums, or a pair that could
-    // not be shared
-    for (int var = 0; var < nvar; var++) {
-      if (variants && paired_done[var & 1]) continue;
-      for (int b = threadIdx.x; b < 2 * HB; b += M2_THREADS) {
-        (&S.cnt[0][0])[b] = 0u;
-        (&S.isum[0][0])[b] = 0;
-      }
-      __syncthreads();
-      const int v = variants ? var : -1;
-      if (exact) {
-        bin_pass<0, M2DP_PQ, true>(S, R, v, 0, false, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
-        __syncthreads();
-        finish_variant<true>(S, 0, ave, unscale, rows + (size_t)var * 2 * M2DP_SIG);
-      } else {
-        bin_pass<0, M2DP_PQ, false>(S, R, v, 0, false, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
-        __syncthreads();
-        finish_variant<false>(S, 0, ave, unscale, rows + (size_t)var * 2 * M2DP_SIG);
-      }
+    } else {
+      for (int var = 0; var < nvar; var++) single_variant(var);
     }
     __syncthreads();
   }
