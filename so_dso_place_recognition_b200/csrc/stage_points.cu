@@ -46,7 +46,12 @@ struct StageGeom {
   int nvox;   // number of distinct voxel indices (bitmap size)
 };
 
-// p_l = w2c * [p; 1]  (pts_preprocess.h:140-142; Eigen 3x4 * 4-vector: sequential sum over the 4 columns)
+// p_l = w2c * [p; 1]  (pts_preprocess.h:140-142).  Summation order: strictly left to right over the 4 columns, and
+// (x^2 + y^2) + z^2 for the norm -- the ORACLE's order (oracle/sodso_oracle.cpp, stage_transform).  Which order Eigen
+// 3.x uses for a fixed-size 3x4 * 4 product and for Vector3d::norm() (sequential or its unrolled pairwise
+// reduction) could not be checked here (no Eigen in the image), so "bit-identical staged point set" is a statement
+// about the oracle: against a real Eigen build a point within 1 ulp of the 45 m crop (pts_preprocess.h:144) or of a
+// voxel edge could be kept / dropped differently.
 __device__ __forceinline__ void to_camera(const double *__restrict__ w, const double *__restrict__ p, double *l) {
 #pragma unroll
   for (int r = 0; r < 3; r++)

@@ -44,9 +44,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (surfacing as a CUDA error) instead of hanging the GPU.  The clock is only
-// consulted every 4096 failed probes, so a waiting warp costs few issue slots.
+// Wait on an mbarrier phase.  Release builds spin on try_wait (which itself suspends the thread for a
+// hardware-defined time slice) without any bound: under compute-sanitizer, cuda-gdb, MPS time-slicing or a throttled
+// clock a legitimate wait can take arbitrarily long, and a trap would be a sticky context error that destroys every
+// resident database of the process.  -DSODSO_TC_DEBUG_WAIT compiles the bounded variant used while developing the
+// barrier protocol (a protocol bug then traps with a message instead of hanging the GPU).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+#ifdef SODSO_TC_DEBUG_WAIT
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
@@ -57,6 +61,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
       __trap();
     }
   }
+#else
+  (void)tag;
+  while (!mbar_try_wait(bar, parity)) {
+  }
+#endif
 }
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map, int c0, int c1,
                                                 uint32_t cluster_bar) {
