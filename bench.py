@@ -366,7 +366,8 @@ def run_ours(args):
                        "variants_per_pair": 120, "mask_width": MASK_WIDTH, "topk": 1,
                        "sharding": "DB rows, 5000 per GPU; queries = the scans of shard 0",
                        "path": "sodso_db_scans_query_sharded at every N: every (query, DB row) pair is computed "
-                               "(general match kernel); collectives = NCCL inside the library, on its stream",
+                               "(general match kernel); the per-batch exchange runs inside the library, on its stream",
+                       "exchange": ctx.comm_exchange if world > 1 else "none (one shard)",
                        "l2": "operands per step (DB 89 MB + queries 346 MB + distances 200 MB) exceed the 126 MB L2",
                        "planted_loop_top1_recovered": agree, "e2e_top1_identical": same_e2e,
                        "oracle_check": oracle_check},
@@ -527,6 +528,7 @@ def run_config4(ctx, dev, world, rank, local_rank):
         nb = len(batches)
         rec = {"workload": f"{n}-row Scan Context DB row-sharded over {world} GPU(s) ({nl} rows per GPU, resident), "
                            f"{m} queries streamed in batches of {B}, top-{k} (BASELINE configs[3])",
+               "exchange": ctx.comm_exchange if world > 1 else "none (one shard)",
                "n_db_total": n, "queries": m, "batch": B, "k": k,
                "pairs_s": m * n / (pipe_ms * 1e-3), "ms_per_batch": pipe_ms / nb,
                "pairs_s_one_call_per_batch_host_results": m * n / (lat_ms * 1e-3), "ms_per_batch_latency_mode": lat_ms / nb,

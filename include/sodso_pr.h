@@ -257,13 +257,25 @@ int sodso_comm_finalize(sodso_ctx *ctx);
 int sodso_comm_nranks(sodso_ctx *ctx);
 int sodso_comm_rank(sodso_ctx *ctx);
 int sodso_comm_nccl_version(void);   /* e.g. 22809; 0 if NCCL could not be bound */
+/* 1 if the per-batch exchange of the sharded queries runs over peer memory: sodso_comm_init also gives every rank a
+ * window in HBM that all ranks of the box can write over NVLink (cudaIpc between processes, peer access between threads
+ * of one process).  The partial row statistics and the per-shard candidate lists are then written by the producing
+ * kernels straight into every rank's window and the consuming kernels poll per-row flags -- no collective launch
+ * between the kernels of a batch; the statistics are summed in rank order, so every rank computes identical bits.
+ * 0: the windows could not be mapped on some rank (no peer access, IPC not permitted) and the exchange uses
+ * ncclAllReduce + ncclAllGather.  The peer-memory exchange is a latency optimisation for streaming batches (per row
+ * a system-scope fence and a few NVLink stores; two NCCL collectives cost ~45 us each whatever the batch size):
+ * batches of more than 512 queries take the NCCL path, as does the bulk exchange of query signatures. */
+int sodso_comm_exchange(sodso_ctx *ctx);
 
 /* run_test.m:25-57 for m queries against a database whose rows are sharded over the ranks of the context's
  * communicator.  COLLECTIVE: every rank calls it with the same queries and parameters and receives the same result,
  * the k best candidates per query over the WHOLE database (ascending fused score, lowest global index first on ties --
  * MATLAB's first minimum, run_test.m:57): idx m x k int64 global 0-based (-1 when fewer than k valid), score / d_p /
  * d_i m x k doubles (d_p / d_i optional).  On the stream, without any host synchronisation in between:
- * match -> partial row statistics -> ncclAllReduce -> fuse + mask + per-shard top-k -> ncclAllGather -> merge.
+ * match -> partial row statistics -> [exchange 1: sum over the shards] -> fuse + mask + per-shard top-k ->
+ * [exchange 2: all shards' lists] -> merge.  The exchanges are peer-memory writes from the producing kernels
+ * (sodso_comm_exchange) or ncclAllReduce / ncclAllGather.
  * DEVICE output pointers: the call returns as soon as the work is enqueued (sodso_ctx_sync, or stream order, before
  * the results are read; several batches can be in flight).  HOST output pointers: copied out, one synchronisation.
  * Without a communicator (or nranks == 1) the same path runs on the one shard, without collectives.

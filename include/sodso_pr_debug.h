@@ -28,6 +28,10 @@ int sodso_debug_set_sc_symmetry(sodso_ctx *ctx, int on);
  * gen_ctas = CTAs per SM of sc_generate_kernel (0 = default) */
 int sodso_debug_set_kernel_flags(int tc_flags, int gen_flags, int gen_ctas);
 
+/* on = 0: communicators created afterwards do not set up the peer-memory windows, so the sharded exchange runs on
+ * ncclAllReduce / ncclAllGather (tests compare the two transports) */
+int sodso_debug_set_peer_exchange(int on);
+
 /* the fp32 angle proposal atan2(num, den)/2pi + 1/2 that the generation kernels use to PROPOSE a polar bin (accepted
  * only outside an error-derived guard band around bin edges, otherwise SC.cpp:37 / M2DP.cpp:59 in fp64 decides);
  * exposed so that tests can check the error bound the guard band rests on */

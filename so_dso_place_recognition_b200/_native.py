@@ -88,6 +88,7 @@ _PROTOS = {
     "sodso_comm_nranks": (_i, [_vp]),
     "sodso_comm_rank": (_i, [_vp]),
     "sodso_comm_nccl_version": (_i, []),
+    "sodso_comm_exchange": (_i, [_vp]),
     "sodso_db_query_sharded": (_i, [_vp, _vp, _i, _i64, _i, _d, _i, _vp, _vp, _vp, _vp]),
     "sodso_db_finish_sharded": (_i, [_vp, _i64, _i, _d, _i, _vp, _vp, _vp, _vp]),
     "sodso_db_scans_query_sharded": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _i64, _i, _d, _i, _vp, _vp,
@@ -99,6 +100,7 @@ _DEBUG_PROTOS = {
     "sodso_debug_set_match_algo": (_i, [_vp, _i]),
     "sodso_debug_set_sc_symmetry": (_i, [_vp, _i]),
     "sodso_debug_set_kernel_flags": (_i, [_i, _i, _i]),
+    "sodso_debug_set_peer_exchange": (_i, [_i]),
     "sodso_debug_fast_turns": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "sodso_debug_sc_self_items": (_i64, [_i64, _i64, _i64]),
 }

@@ -111,6 +111,11 @@ class Context:
         N.check(N.lib().sodso_comm_finalize(self._h))
 
     @property
+    def comm_exchange(self) -> str:
+        """transport of the per-batch exchange of sharded queries: 'peer-memory' (NVLink writes from the kernels) or 'nccl'"""
+        return "peer-memory" if N.lib().sodso_comm_exchange(self._h) else "nccl"
+
+    @property
     def comm_nranks(self) -> int:
         return int(N.lib().sodso_comm_nranks(self._h))
 

@@ -259,7 +259,8 @@ int sodso_ctx_set_stream(sodso_ctx *c, void *s) {
 
 int sodso_ctx_sync(sodso_ctx *c) {
   CTX_CHECK(c);
-  return sync_ctx(c);
+  int rc = sync_ctx(c);
+  return rc ? rc : comm_check(c);
 }
 
 int sodso_ctx_set_stream_threshold(sodso_ctx *c, int min_scans) {

@@ -143,5 +143,6 @@ int db_stream_match_async(sodso_db *db, const double *xyz, const float *inten, c
                           bool self, double *hist_dev);
 // sharded.cu
 void comm_release(sodso_ctx *c);
+int comm_check(sodso_ctx *c);
 
 }  // namespace sodso

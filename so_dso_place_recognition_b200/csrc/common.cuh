@@ -170,13 +170,33 @@ cudaError_t launch_m2dp_match_tc(const double *hist1, int m, const double *hist2
                                  int ldd, void *workspace, int num_sms, cudaStream_t st, int64_t *launches);
 
 // fuse_topk.cu
+// Peer-memory exchange of a sharded query batch (csrc/sharded.cu): every rank owns a window in HBM that all ranks of
+// the box can write over NVLink (cudaIpc / peer access).  A window has two halves (batch parity), each with one slot
+// per SOURCE rank; a slot has a FIXED layout (so that stale bytes of an earlier batch shape can never be taken for a
+// flag): [sflag: PX_MAX_ROWS u32][lflag: PX_MAX_ROWS u32][stats: PX_MAX_ROWS x 6 f64][lists: 4 x m x k x 8 B].
+// Producers write their row's data into the slot `rank` of EVERY rank's window, fence, then write the batch epoch
+// into the row's flag; consumers poll their own window.
+constexpr int PX_MAX_ROWS = 8192;
+constexpr int PX_MAX_RANKS = 16;
+constexpr size_t PX_OFF_SFLAG = 0, PX_OFF_LFLAG = (size_t)PX_MAX_ROWS * 4, PX_OFF_STATS = (size_t)PX_MAX_ROWS * 8,
+                 PX_OFF_LISTS = PX_OFF_STATS + (size_t)PX_MAX_ROWS * STATS_W * 8;
+struct PeerExchange {
+  unsigned char *win[PX_MAX_RANKS];   // win[r] = rank r's window as seen from this GPU; nullptr in win[0] = no exchange
+  size_t slot_bytes;                  // bytes per (parity, source) slot
+  int nranks, rank;
+  unsigned epoch;                     // batch number, >= 1
+  int *err;                           // device word: set to 1 when a wait timed out
+};
 cudaError_t launch_row_stats(const float *d_p, const float *d_i, int m, int n, int ldd, double *stats,
-                             cudaStream_t st, int64_t *launches);
+                             cudaStream_t st, int64_t *launches, const PeerExchange *px = nullptr);
 cudaError_t launch_fuse_topk(const float *d_p, const float *d_i, int m, int n, int ldd,
                              const double *global_stats, int64_t n_global, int64_t q_row0,
                              int64_t db_row0, int mask_width, double p_weight, int k, int64_t *idx,
                              double *score, double *dp_at, double *di_at, cudaStream_t st,
-                             int64_t *launches);
+                             int64_t *launches, const PeerExchange *px = nullptr);
+// merge of the lists the peers have written into this rank's window (PeerExchange), m x k outputs
+cudaError_t launch_topk_merge_px(const PeerExchange &px, int m, int k, int64_t *out_idx, double *out_score,
+                                 double *out_d_p, double *out_d_i, cudaStream_t st, int64_t *launches);
 // fp64 variants for sodso_fuse_top1 (inputs are caller-supplied fp64 matrices; exact two-pass
 // statistics like run_test.m:40)
 cudaError_t launch_fuse_top1_f64(const double *d_p, const double *d_i, int m, int n, int mask_width,

@@ -3,6 +3,7 @@
 // Inf, first-index argmin (generalised to the k best for the row-sharded database).
 // One CTA per query row; all statistics in fp64 with a fixed reduction tree.
 #include <cmath>
+#include <cstring>
 
 #include "../../include/sodso_pr.h"
 #include "common.cuh"
@@ -87,12 +88,40 @@ __device__ __forceinline__ void block_argmin(double &s, long long &i, double *ss
   __syncthreads();
 }
 
+// ---- peer-memory exchange helpers (PeerExchange, common.cuh) ----
+__device__ __forceinline__ unsigned char *px_slot(const PeerExchange &px, int owner, int source) {
+  return px.win[owner] + ((size_t)(px.epoch & 1u) * px.nranks + source) * px.slot_bytes;
+}
+__device__ __forceinline__ void px_store_flag(unsigned *p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// poll a flag in this rank's own window until it carries the batch epoch; a peer that never arrives (crashed rank)
+// ends the wait after ~4 s with the error word set instead of hanging the GPU
+__device__ __forceinline__ void px_wait_flag(const unsigned *p, unsigned epoch, int *err) {
+  unsigned v;
+  long long t0 = 0;
+  unsigned spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (v == epoch) return;
+    if ((++spins & 0x3ffu) == 0) {
+      if (t0 == 0)
+        t0 = clock64();
+      else if (clock64() - t0 > 8000000000LL) {
+        *err = 1;
+        return;
+      }
+      __nanosleep(64);
+    }
+  }
+}
+
 // stats[row] = [sum(dp-c), sum((dp-c)^2), count(dp), sum(di-c), sum((di-c)^2), count(di)], c = STAT_SHIFT, over the
 // non-NaN entries only: MATLAB's normalize (run_test.m:40) computes its mean and std with 'omitnan', so the NaN column
 // of one zero-norm DB signature (processSC.m:15-20) stays NaN and every other candidate is still ranked.
 __global__ void __launch_bounds__(FUSE_THREADS)
 row_stats_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, int n, int ldd,
-                 double *__restrict__ stats) {
+                 double *__restrict__ stats, const PeerExchange px) {
   __shared__ double scratch[STATS_W * 32];
   const int row = blockIdx.x;
   const float *p = d_p + (size_t)row * ldd, *q = d_i + (size_t)row * ldd;
@@ -113,6 +142,37 @@ row_stats_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, i
   }
   block_sum_d<STATS_W>(v, scratch);
   if (threadIdx.x < STATS_W) stats[(size_t)row * STATS_W + threadIdx.x] = v[threadIdx.x];
+  // sharded database: this shard's partial statistics of the row go straight into every rank's window over NVLink
+  // (its own included); the consumer is fuse_topk_kernel on each rank
+  if (px.win[0] && threadIdx.x < px.nranks) {
+    unsigned char *slot = px_slot(px, threadIdx.x, px.rank);
+    double *dst = reinterpret_cast<double *>(slot + PX_OFF_STATS) + (size_t)row * STATS_W;
+#pragma unroll
+    for (int t = 0; t < STATS_W; t++) dst[t] = v[t];
+    __threadfence_system();
+    px_store_flag(reinterpret_cast<unsigned *>(slot + PX_OFF_SFLAG) + row, px.epoch);
+  }
+}
+
+// sharded database: the k candidates of this shard for `row` (just written by the calling thread to the local lists
+// [4][m][k] = idx | score | d_p | d_i) go into every rank's window; the consumer is topk_merge_px_kernel on each rank
+__device__ __forceinline__ void px_publish_row(const PeerExchange &px, int row, int m, int k, const int64_t *idx,
+                                               const double *score, const double *dp_at, const double *di_at) {
+  const size_t mk = (size_t)m * k, o = (size_t)row * k;
+  for (int r = 0; r < px.nranks; r++) {
+    unsigned char *slot = px_slot(px, r, px.rank);
+    long long *li = reinterpret_cast<long long *>(slot + PX_OFF_LISTS);
+    double *ls = reinterpret_cast<double *>(slot + PX_OFF_LISTS) + mk;
+    for (int t = 0; t < k; t++) {
+      li[o + t] = idx[o + t];
+      ls[o + t] = score[o + t];
+      ls[mk + o + t] = dp_at[o + t];
+      ls[2 * mk + o + t] = di_at[o + t];
+    }
+  }
+  __threadfence_system();
+  for (int r = 0; r < px.nranks; r++)
+    px_store_flag(reinterpret_cast<unsigned *>(px_slot(px, r, px.rank) + PX_OFF_LFLAG) + row, px.epoch);
 }
 
 // KL: length of the per-thread candidate list (1 for top-1, 8 for k <= 8, 0 = no lists: one row scan per selected entry)
@@ -123,15 +183,33 @@ __global__ void __launch_bounds__(FUSE_THREADS)
 fuse_topk_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, int n, int ldd,
                  const double *__restrict__ gstats, long long n_global, long long q_row0,
                  long long db_row0, int mask_width, double p_weight, int k, int64_t *__restrict__ idx,
-                 double *__restrict__ score, double *__restrict__ dp_at, double *__restrict__ di_at) {
+                 double *__restrict__ score, double *__restrict__ dp_at, double *__restrict__ di_at,
+                 const PeerExchange px) {
   __shared__ double ss[32];
   __shared__ long long si[32];
   __shared__ double cand_f[TOPK_CAND_CAP];
   __shared__ long long cand_j[TOPK_CAND_CAP];
   __shared__ int cand_n;
+  __shared__ double gsum[STATS_W];
   const int row = blockIdx.x;
   const float *p = d_p + (size_t)row * ldd, *q = d_i + (size_t)row * ldd;
   const double *st = gstats + (size_t)row * STATS_W;
+  if (px.win[0]) {
+    // sharded database: the row statistics over the WHOLE database (run_test.m:40) = the sum of the shards' partial
+    // statistics, which their row_stats_kernel wrote into this rank's window; summed in rank order, so every rank
+    // gets the same bits
+    if (threadIdx.x < px.nranks)
+      px_wait_flag(reinterpret_cast<const unsigned *>(px_slot(px, px.rank, threadIdx.x) + PX_OFF_SFLAG) + row, px.epoch, px.err);
+    __syncthreads();
+    if (threadIdx.x < STATS_W) {
+      double a = 0.0;
+      for (int s = 0; s < px.nranks; s++)
+        a += reinterpret_cast<const volatile double *>(px_slot(px, px.rank, s) + PX_OFF_STATS)[(size_t)row * STATS_W + threadIdx.x];
+      gsum[threadIdx.x] = a;
+    }
+    __syncthreads();
+    st = gsum;
+  }
   const double Np = st[2], Ni = st[5];   // non-NaN entries of the whole (global) row, per channel
   const double mu_p = STAT_SHIFT + st[0] / Np, mu_i = STAT_SHIFT + st[3] / Ni;
   const double sd_p = sqrt((st[1] - st[0] * st[0] / Np) / (Np - 1.0));
@@ -244,6 +322,7 @@ fuse_topk_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, i
             if (dp_at) dp_at[o] = have ? (double)p[bi - db_row0] : NAN;
             if (di_at) di_at[o] = have ? (double)q[bi - db_row0] : NAN;
           }
+          if (px.win[0]) px_publish_row(px, row, (int)gridDim.x, k, idx, score, dp_at, di_at);
         }
         return;
       }
@@ -326,6 +405,7 @@ fuse_topk_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, i
     last_s = bs;
     last_i = bi;
   }
+  if (px.win[0] && threadIdx.x == 0) px_publish_row(px, row, (int)gridDim.x, k, idx, score, dp_at, di_at);
 }
 
 // run_test.m:38-57 on caller-supplied fp64 matrices, two-pass statistics over the non-NaN entries like MATLAB normalize.
@@ -392,10 +472,16 @@ __global__ void f32_to_f64_kernel(const float *__restrict__ src, int rows, int c
 
 }  // namespace
 
+static PeerExchange no_exchange() {
+  PeerExchange px;
+  memset(&px, 0, sizeof(px));
+  return px;
+}
+
 cudaError_t launch_row_stats(const float *d_p, const float *d_i, int m, int n, int ldd, double *stats,
-                             cudaStream_t st, int64_t *launches) {
+                             cudaStream_t st, int64_t *launches, const PeerExchange *px) {
   if (m <= 0) return cudaSuccess;
-  row_stats_kernel<<<m, FUSE_THREADS, 0, st>>>(d_p, d_i, n, ldd, stats);
+  row_stats_kernel<<<m, FUSE_THREADS, 0, st>>>(d_p, d_i, n, ldd, stats, px ? *px : no_exchange());
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -404,11 +490,11 @@ cudaError_t launch_fuse_topk(const float *d_p, const float *d_i, int m, int n, i
                              const double *global_stats, int64_t n_global, int64_t q_row0,
                              int64_t db_row0, int mask_width, double p_weight, int k, int64_t *idx,
                              double *score, double *dp_at, double *di_at, cudaStream_t st,
-                             int64_t *launches) {
+                             int64_t *launches, const PeerExchange *px) {
   if (m <= 0) return cudaSuccess;
   auto kern = k == 1 ? fuse_topk_kernel<1> : k <= 8 ? fuse_topk_kernel<8> : fuse_topk_kernel<0>;
   kern<<<m, FUSE_THREADS, 0, st>>>(d_p, d_i, n, ldd, global_stats, n_global, q_row0, db_row0, mask_width, p_weight, k, idx,
-                                   score, dp_at, di_at);
+                                   score, dp_at, di_at, px ? *px : no_exchange());
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -490,6 +576,65 @@ __global__ void topk_merge_kernel(const int64_t *__restrict__ idx, const double 
       pos[best]++;
     }
   }
+}
+
+// The merge for the peer-memory exchange: the R lists of query q are in this rank's own window, one slot per source
+// rank; a thread first waits until every source has published its row.
+__global__ void topk_merge_px_kernel(const PeerExchange px, int m, int k, int64_t *__restrict__ out_idx,
+                                     double *__restrict__ out_score, double *__restrict__ out_d_p,
+                                     double *__restrict__ out_d_i) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= m) return;
+  const size_t mk = (size_t)m * k;
+  const volatile long long *li[PX_MAX_RANKS];
+  const volatile double *ls[PX_MAX_RANKS];
+  int pos[PX_MAX_RANKS];
+  for (int s = 0; s < px.nranks; s++) {
+    const unsigned char *slot = px_slot(px, px.rank, s);
+    px_wait_flag(reinterpret_cast<const unsigned *>(slot + PX_OFF_LFLAG) + q, px.epoch, px.err);
+    li[s] = reinterpret_cast<const volatile long long *>(slot + PX_OFF_LISTS);
+    ls[s] = reinterpret_cast<const volatile double *>(slot + PX_OFF_LISTS) + mk;
+    pos[s] = 0;
+  }
+  for (int r = 0; r < k; r++) {
+    int best = -1;
+    long long bidx = -1;
+    double bsc = 0.0;
+    for (int s = 0; s < px.nranks; s++) {
+      if (pos[s] >= k) continue;
+      const size_t o = (size_t)q * k + pos[s];
+      const long long id = li[s][o];
+      if (id < 0) continue;
+      const double sc = ls[s][o];
+      if (best < 0 || sc < bsc || (sc == bsc && id < bidx)) {
+        best = s;
+        bidx = id;
+        bsc = sc;
+      }
+    }
+    const size_t oo = (size_t)q * k + r;
+    if (best < 0) {
+      out_idx[oo] = -1;
+      out_score[oo] = NAN;
+      if (out_d_p) out_d_p[oo] = NAN;
+      if (out_d_i) out_d_i[oo] = NAN;
+    } else {
+      const size_t o = (size_t)q * k + pos[best];
+      out_idx[oo] = bidx;
+      out_score[oo] = bsc;
+      if (out_d_p) out_d_p[oo] = ls[best][mk + o];
+      if (out_d_i) out_d_i[oo] = ls[best][2 * mk + o];
+      pos[best]++;
+    }
+  }
+}
+
+cudaError_t launch_topk_merge_px(const PeerExchange &px, int m, int k, int64_t *out_idx, double *out_score,
+                                 double *out_d_p, double *out_d_i, cudaStream_t st, int64_t *launches) {
+  if (m <= 0) return cudaSuccess;
+  topk_merge_px_kernel<<<(m + 63) / 64, 64, 0, st>>>(px, m, k, out_idx, out_score, out_d_p, out_d_i);
+  if (launches) ++*launches;
+  return cudaGetLastError();
 }
 
 // shard_stride: elements between the lists of consecutive shards in each of the four arrays (0 = m * k, i.e. four

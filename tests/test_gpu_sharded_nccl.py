@@ -47,6 +47,7 @@ def _worker(rank, world, port, out):
     ctx = api.default_context(rank)
     sharded.init_comm(ctx)                                          # sodso_comm_init: NCCL inside the library
     assert ctx.comm_nranks == world and ctx.comm_rank == rank
+    exchange = ctx.comm_exchange                                    # 'peer-memory' where the GPUs can map each other
     xyz, inten, off, n = _data(world)
     row0, n_local = sharded.shard_rows(n, world, rank)
     hist_all = _plant_duplicates(api.sc_generate(xyz, inten, off, ctx=ctx), world)
@@ -82,7 +83,19 @@ def _worker(rank, world, port, out):
     r4 = db2.query_sharded(hist_q[:BATCH], int(qsel[0]), MASK, 2.0, K)
     db.close()
     db2.close()
+    # the same first batch with the other transport: a communicator without peer windows (ncclAllReduce + ncclAllGather)
+    from so_dso_place_recognition_b200 import _native as N
+    ctx.comm_finalize()
+    N.lib().sodso_debug_set_peer_exchange(0)
+    sharded.init_comm(ctx)
+    assert ctx.comm_exchange == "nccl"
+    db3 = api.SignatureDB("sc", hist_all[row0:row0 + n_local], global_row0=row0, ctx=ctx)
+    r5 = db3.query_sharded(hist_q[:BATCH], int(qsel[0]), MASK, 2.0, K)
+    db3.close()
+    N.lib().sodso_debug_set_peer_exchange(1)
     if rank == 0:
+        out["exchange"] = exchange
+        out["nccl_idx"], out["nccl_score"] = r5[0], r5[1]
         out["idx"] = np.concatenate([r[0] for r in res])
         out["score"] = np.concatenate([r[1] for r in res])
         out["dp"] = np.concatenate([r[2] for r in res])
@@ -118,9 +131,12 @@ def test_world2_sharded_cabi_matches_one_gpu(gpu_ctx):
     db = api.SignatureDB("sc", hist, global_row0=0)
     idx, score, dp, di = db.query_sharded(hist[qsel], int(qsel[0]), MASK, 2.0, K)
     db.close()
+    print("sharded exchange transport:", out["exchange"])
     np.testing.assert_array_equal(out["idx"], idx)
     np.testing.assert_allclose(out["score"], score, rtol=1e-9, atol=1e-12)
     np.testing.assert_array_equal(out["dp"], dp)
+    np.testing.assert_array_equal(out["nccl_idx"], idx[:BATCH])             # both transports, same lists
+    np.testing.assert_allclose(out["nccl_score"], score[:BATCH], rtol=1e-9, atol=1e-12)
     # the planted duplicates tie exactly and come out in global index order
     assert idx[5, :2].tolist() == [3000, ROWS_PER_GPU + 3001] and score[5, 0] == score[5, 1]
     assert idx[9, :2].tolist() == [ROWS_PER_GPU + 3002, ROWS_PER_GPU + 3003] and score[9, 0] == score[9, 1]
