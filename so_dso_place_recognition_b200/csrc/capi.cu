@@ -237,6 +237,7 @@ void sodso_ctx_destroy(sodso_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->xchg_stream) cudaStreamSynchronize(c->xchg_stream);
   comm_release(c);
   for (Buf *b : {&c->in_xyz, &c->in_inten, &c->in_off, &c->out_hist, &c->out_xyz, &c->out_evec, &c->h1,
                  &c->h2, &c->q_op, &c->db_op, &c->dp32, &c->di32, &c->dp64, &c->di64, &c->stats,
@@ -246,6 +247,11 @@ void sodso_ctx_destroy(sodso_ctx *c) {
   cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->own_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->xchg_stream) cudaStreamDestroy(c->xchg_stream);
+  for (int f = 0; f < 2; f++) {
+    if (c->ev_stats[f]) cudaEventDestroy(c->ev_stats[f]);
+    if (c->ev_done[f]) cudaEventDestroy(c->ev_done[f]);
+  }
   delete c;
 }
 
@@ -993,6 +999,8 @@ int sodso_staged_copy(sodso_staged *S, int32_t *ids, int64_t *scan_off, double *
 // the device; row0 == 0 also clears the binary-channel flags
 static int db_write_rows(sodso_db *db, const double *hist_dev, int row0, int rows, bool pad_tail) {
   sodso_ctx *c = db->ctx;
+  int jrc = join_xchg(c);   // (a pipelined query may still be reading the operand / results on the exchange stream)
+  if (jrc) return jrc;
   const size_t w = db->type == SODSO_TYPE_SC ? 2 * SC_SIZE : 2 * M2DP_SIG;
   if (db->type == SODSO_TYPE_M2DP) {
     SODSO_CUDA_CHECK(cudaMemcpyAsync(db->op.as<double>() + (size_t)4 * row0 * w, hist_dev, (size_t)4 * rows * w * sizeof(double),
@@ -1066,6 +1074,10 @@ int sodso_db_reserve(sodso_db *db, int capacity) {
   sodso_ctx *c = db->ctx;
   CTX_CHECK(c);
   if (capacity <= db->cap) return SODSO_OK;
+  {
+    int jrc = join_xchg(c);
+    if (jrc) return jrc;
+  }
   if (db->type == SODSO_TYPE_SC && db->op_algo == SODSO_ALGO_SIMT) {
     set_error("the fp32 cross-check database cannot grow");
     return SODSO_E_STATE;
@@ -1279,6 +1291,7 @@ int sodso_db_stream_match(sodso_db *db, const double *xyz, const float *inten, c
     return SODSO_E_STATE;
   }
   int rc;
+  if ((rc = join_xchg(c))) return rc;
   // queries: operand first (it gates every block)
   const double *hq;
   if ((rc = stage_in(c, hist1, (size_t)m * 2 * SC_SIZE, db->q_in, &hq))) return rc;
@@ -1291,8 +1304,9 @@ void sodso_db_destroy(sodso_db *db) {
   if (!db) return;
   cudaSetDevice(db->ctx->device);
   cudaStreamSynchronize(db->ctx->stream);
+  if (db->ctx->xchg_stream) cudaStreamSynchronize(db->ctx->xchg_stream);
   for (Buf *b : {&db->op, &db->q_in, &db->q_op, &db->dp, &db->di, &db->stats, &db->gstats, &db->idx,
-                 &db->score, &db->dpat, &db->diat, &db->ws, &db->q_hist, &db->pack, &db->gather, &db->q_xyz, &db->q_inten, &db->q_off})
+                 &db->score, &db->dpat, &db->diat, &db->ws, &db->q_hist, &db->pack, &db->gather, &db->q_xyz, &db->q_inten, &db->q_off, &db->dp2, &db->di2, &db->stats2, &db->pack2, &db->gstats2, &db->gather2})
     b->release();
   delete db;
 }
@@ -1367,6 +1381,7 @@ int sodso_db_match(sodso_db *db, const double *hist1, int m) {
     return SODSO_E_ARG;
   }
   int rc;
+  if ((rc = join_xchg(c))) return rc;
   if ((rc = db_match_async(db, hist1, m))) return rc;
   // hist1 may be pageable / pinned host memory or a device tensor the caller reuses: the call returns once the library
   // has finished reading it (and asynchronous kernel failures surface here, not in a later unrelated call)
@@ -1383,6 +1398,10 @@ int sodso_db_partial_stats(sodso_db *db, double *stats) {
   if (!db->matched) {
     set_error("db_partial_stats before db_match");
     return SODSO_E_STATE;
+  }
+  {
+    int jrc = join_xchg(c);
+    if (jrc) return jrc;
   }
   double *sd;
   int rc;
@@ -1406,6 +1425,10 @@ int sodso_db_topk(sodso_db *db, const double *global_stats, int64_t n_global, in
   if (!db->matched) {
     set_error("db_topk before db_match");
     return SODSO_E_STATE;
+  }
+  {
+    int jrc = join_xchg(c);
+    if (jrc) return jrc;
   }
   const double *gs;
   int rc;
@@ -1495,6 +1518,10 @@ int sodso_db_get_distances(sodso_db *db, float *d_p, float *d_i) {
   if (!db->matched) {
     set_error("db_get_distances before db_match");
     return SODSO_E_STATE;
+  }
+  {
+    int jrc = join_xchg(c);
+    if (jrc) return jrc;
   }
   const size_t bytes = (size_t)db->m * db->n * sizeof(float);
   if (d_p) SODSO_CUDA_CHECK(cudaMemcpyAsync(d_p, db->dp.p, bytes, cudaMemcpyDefault, c->stream));

@@ -63,6 +63,12 @@ struct sodso_ctx {
   bool ev_valid = false;
   std::string kname;
   sodso::CommState *comm = nullptr;
+  // pipelined sharded queries (device outputs): the exchange / fusion / merge of batch b runs on a second stream while
+  // the match of batch b + 1 runs on the main one
+  cudaStream_t xchg_stream = nullptr;
+  cudaEvent_t ev_stats[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  bool ev_done_rec[2] = {false, false};
+  unsigned batch_no = 0;               // sharded query batches on this context (epoch of the peer-memory exchange)
   // workspaces
   sodso::Buf in_xyz, in_inten, in_off, out_hist, out_xyz, out_evec;
   sodso::Buf h1, h2, q_op, db_op, dp32, di32, dp64, di64;
@@ -80,6 +86,7 @@ struct sodso_db {
   sodso::Buf q_in, q_op, dp, di, stats, gstats, idx, score, dpat, diat, ws;
   sodso::Buf q_hist, pack, gather;   // sharded query: generated query signatures, local / gathered top-k lists
   sodso::Buf q_xyz, q_inten, q_off;  // sharded query from scans: staged query points
+  sodso::Buf dp2, di2, stats2, pack2, gstats2, gather2;   // second buffer set of the pipelined sharded queries
   int m = 0;           // rows of the last match
   bool matched = false;
 };
@@ -131,6 +138,14 @@ int finish_out(sodso_ctx *c, T *dst, size_t count, const T *dev) {
 
 inline int sync_ctx(sodso_ctx *c) {
   SODSO_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (c->xchg_stream) SODSO_CUDA_CHECK(cudaStreamSynchronize(c->xchg_stream));
+  return SODSO_OK;
+}
+
+// the main stream waits for everything a pipelined sharded query has put on the exchange stream
+inline int join_xchg(sodso_ctx *c) {
+  for (int f = 0; f < 2; f++)
+    if (c->ev_done_rec[f]) SODSO_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_done[f], 0));
   return SODSO_OK;
 }
 

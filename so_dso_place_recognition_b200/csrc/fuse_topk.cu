@@ -154,25 +154,24 @@ row_stats_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, i
   }
 }
 
-// sharded database: the k candidates of this shard for `row` (just written by the calling thread to the local lists
-// [4][m][k] = idx | score | d_p | d_i) go into every rank's window; the consumer is topk_merge_px_kernel on each rank
+// sharded database: the k candidates of this shard for `row` (written by thread 0 to the local lists [4][m][k] = idx |
+// score | d_p | d_i) go into every rank's window; the consumer is topk_merge_px_kernel on each rank.  Called by ALL
+// threads of the CTA: one (rank, array, entry) store per thread, fence, barrier, then one flag store per rank.
 __device__ __forceinline__ void px_publish_row(const PeerExchange &px, int row, int m, int k, const int64_t *idx,
                                                const double *score, const double *dp_at, const double *di_at) {
+  __syncthreads();   // thread 0's local lists are complete (block-scope visibility)
   const size_t mk = (size_t)m * k, o = (size_t)row * k;
-  for (int r = 0; r < px.nranks; r++) {
-    unsigned char *slot = px_slot(px, r, px.rank);
-    long long *li = reinterpret_cast<long long *>(slot + PX_OFF_LISTS);
-    double *ls = reinterpret_cast<double *>(slot + PX_OFF_LISTS) + mk;
-    for (int t = 0; t < k; t++) {
-      li[o + t] = idx[o + t];
-      ls[o + t] = score[o + t];
-      ls[mk + o + t] = dp_at[o + t];
-      ls[2 * mk + o + t] = di_at[o + t];
-    }
+  for (int e = threadIdx.x; e < px.nranks * 4 * k; e += blockDim.x) {
+    const int r = e / (4 * k), a = (e / k) & 3, t = e % k;
+    long long *dst = reinterpret_cast<long long *>(px_slot(px, r, px.rank) + PX_OFF_LISTS) + (size_t)a * mk + o + t;
+    const long long v = a == 0 ? (long long)idx[o + t]
+                               : __double_as_longlong(a == 1 ? score[o + t] : a == 2 ? dp_at[o + t] : di_at[o + t]);
+    *dst = v;
   }
   __threadfence_system();
-  for (int r = 0; r < px.nranks; r++)
-    px_store_flag(reinterpret_cast<unsigned *>(px_slot(px, r, px.rank) + PX_OFF_LFLAG) + row, px.epoch);
+  __syncthreads();
+  if (threadIdx.x < px.nranks)
+    px_store_flag(reinterpret_cast<unsigned *>(px_slot(px, threadIdx.x, px.rank) + PX_OFF_LFLAG) + row, px.epoch);
 }
 
 // KL: length of the per-thread candidate list (1 for top-1, 8 for k <= 8, 0 = no lists: one row scan per selected entry)
@@ -322,8 +321,8 @@ fuse_topk_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, i
             if (dp_at) dp_at[o] = have ? (double)p[bi - db_row0] : NAN;
             if (di_at) di_at[o] = have ? (double)q[bi - db_row0] : NAN;
           }
-          if (px.win[0]) px_publish_row(px, row, (int)gridDim.x, k, idx, score, dp_at, di_at);
         }
+        if (px.win[0]) px_publish_row(px, row, (int)gridDim.x, k, idx, score, dp_at, di_at);
         return;
       }
       // more near-ties than the list holds: fall through to the scan-per-entry loop below with the bound as filter
@@ -405,7 +404,7 @@ fuse_topk_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, i
     last_s = bs;
     last_i = bi;
   }
-  if (px.win[0] && threadIdx.x == 0) px_publish_row(px, row, (int)gridDim.x, k, idx, score, dp_at, di_at);
+  if (px.win[0]) px_publish_row(px, row, (int)gridDim.x, k, idx, score, dp_at, di_at);
 }
 
 // run_test.m:38-57 on caller-supplied fp64 matrices, two-pass statistics over the non-NaN entries like MATLAB normalize.

@@ -104,7 +104,6 @@ struct CommState {
   int *h_err = nullptr;   // mapped pinned word: a consumer kernel whose wait timed out sets it
   int *d_err = nullptr;
   bool p2p = false;
-  unsigned epoch = 0;
 };
 
 constexpr size_t PX_WINDOW_BYTES = (size_t)64 << 20;
@@ -233,11 +232,31 @@ static void block_partition(int total, int world, int rank, int *first, int *cou
 
 // statistics -> (all-reduce) -> per-shard top-k -> (all-gather, merge) for the last match of `db`; outputs are DEVICE
 // pointers (idx, score required); everything is enqueued on the context's stream
+// pipelined: everything after the partial statistics (the exchanges, fusion, merge) goes to the context's exchange
+// stream, so that the caller's next batch can be matched on the main stream meanwhile (pipeline_begin has chosen the
+// buffer set and made the main stream wait for the batch that used it last).
 static int finish_sharded_async(sodso_db *db, int64_t q_row0, int mask_width, double p_weight, int k, int64_t *idx,
-                                double *score, double *d_p, double *d_i) {
+                                double *score, double *d_p, double *d_i, bool pipelined) {
   sodso_ctx *c = db->ctx;
   const int m = db->m, R = c->comm ? c->comm->nranks : 1;
   const size_t mk = (size_t)m * k;
+  const unsigned batch = ++c->batch_no;
+  const int f = (int)(batch & 1u);
+  cudaStream_t st2 = pipelined ? c->xchg_stream : c->stream;
+  // the statistics kernel (a producer of the exchange) stays on the main stream; `after_stats` moves to the other one
+  auto after_stats = [&]() -> int {
+    if (!pipelined) return SODSO_OK;
+    SODSO_CUDA_CHECK(cudaEventRecord(c->ev_stats[f], c->stream));
+    SODSO_CUDA_CHECK(cudaStreamWaitEvent(c->xchg_stream, c->ev_stats[f], 0));
+    return SODSO_OK;
+  };
+  auto done = [&]() -> int {
+    if (!pipelined) return SODSO_OK;
+    SODSO_CUDA_CHECK(cudaEventRecord(c->ev_done[f], c->xchg_stream));
+    c->ev_done_rec[f] = true;
+    return SODSO_OK;
+  };
+  int rc;
   SODSO_CUDA_CHECK(db->stats.reserve((size_t)m * STATS_W * sizeof(double)));
   // ---- peer-memory exchange: the partial statistics and the candidate lists are written by row_stats_kernel /
   // fuse_topk_kernel straight into every rank's window over NVLink, the consumers poll per-row flags: no collective
@@ -254,31 +273,32 @@ static int finish_sharded_async(sodso_db *db, int64_t q_row0, int mask_width, do
     px.slot_bytes = S->slot_bytes;
     px.nranks = R;
     px.rank = S->rank;
-    px.epoch = ++S->epoch;
+    px.epoch = batch;
     px.err = S->d_err;
     SODSO_CUDA_CHECK(db->pack.reserve(4 * mk * 8));
     int64_t *pi = db->pack.as<int64_t>();
     double *ps = db->pack.as<double>() + mk, *pp = ps + mk, *pd = pp + mk;
     SODSO_CUDA_CHECK(launch_row_stats(db->dp.as<float>(), db->di.as<float>(), m, db->n, db->n, db->stats.as<double>(),
                                       c->stream, &c->launches, &px));
+    if ((rc = after_stats())) return rc;
     SODSO_CUDA_CHECK(launch_fuse_topk(db->dp.as<float>(), db->di.as<float>(), m, db->n, db->n, db->stats.as<double>(), db->n,
-                                      q_row0, db->row0, mask_width, p_weight, k, pi, ps, pp, pd, c->stream, &c->launches, &px));
-    SODSO_CUDA_CHECK(launch_topk_merge_px(px, m, k, idx, score, d_p, d_i, c->stream, &c->launches));
-    return SODSO_OK;
+                                      q_row0, db->row0, mask_width, p_weight, k, pi, ps, pp, pd, st2, &c->launches, &px));
+    SODSO_CUDA_CHECK(launch_topk_merge_px(px, m, k, idx, score, d_p, d_i, st2, &c->launches));
+    return done();
   }
   SODSO_CUDA_CHECK(launch_row_stats(db->dp.as<float>(), db->di.as<float>(), m, db->n, db->n, db->stats.as<double>(),
                                     c->stream, &c->launches));
+  if ((rc = after_stats())) return rc;
   const double *gs = db->stats.as<double>();
   if (R > 1) {
     SODSO_CUDA_CHECK(db->gstats.reserve((size_t)m * STATS_W * sizeof(double)));
-    SODSO_NCCL_CHECK(nccl().AllReduce(db->stats.p, db->gstats.p, (size_t)m * STATS_W, ncclDouble, ncclSum, c->comm->comm,
-                                      c->stream));
+    SODSO_NCCL_CHECK(nccl().AllReduce(db->stats.p, db->gstats.p, (size_t)m * STATS_W, ncclDouble, ncclSum, c->comm->comm, st2));
     gs = db->gstats.as<double>();
   }
   if (R == 1) {
     SODSO_CUDA_CHECK(launch_fuse_topk(db->dp.as<float>(), db->di.as<float>(), m, db->n, db->n, gs, db->n, q_row0, db->row0,
-                                      mask_width, p_weight, k, idx, score, d_p, d_i, c->stream, &c->launches));
-    return SODSO_OK;
+                                      mask_width, p_weight, k, idx, score, d_p, d_i, st2, &c->launches));
+    return done();
   }
   // packed lists [4][m][k] of 8-byte entries (global index, fused score, d_p, d_i): one all-gather moves everything
   SODSO_CUDA_CHECK(db->pack.reserve(4 * mk * 8));
@@ -286,17 +306,46 @@ static int finish_sharded_async(sodso_db *db, int64_t q_row0, int mask_width, do
   int64_t *pi = db->pack.as<int64_t>();
   double *ps = db->pack.as<double>() + mk, *pp = ps + mk, *pd = pp + mk;
   SODSO_CUDA_CHECK(launch_fuse_topk(db->dp.as<float>(), db->di.as<float>(), m, db->n, db->n, gs, db->n, q_row0, db->row0,
-                                    mask_width, p_weight, k, pi, ps, pp, pd, c->stream, &c->launches));
-  SODSO_NCCL_CHECK(nccl().AllGather(db->pack.p, db->gather.p, 4 * mk * 8, ncclChar, c->comm->comm, c->stream));
+                                    mask_width, p_weight, k, pi, ps, pp, pd, st2, &c->launches));
+  SODSO_NCCL_CHECK(nccl().AllGather(db->pack.p, db->gather.p, 4 * mk * 8, ncclChar, c->comm->comm, st2));
   const int64_t *gi = db->gather.as<int64_t>();
   const double *gsc = db->gather.as<double>() + mk, *gp = gsc + mk, *gd = gp + mk;
-  SODSO_CUDA_CHECK(launch_topk_merge(gi, gsc, gp, gd, R, m, k, idx, score, d_p, d_i, c->stream, &c->launches, 4 * mk));
+  SODSO_CUDA_CHECK(launch_topk_merge(gi, gsc, gp, gd, R, m, k, idx, score, d_p, d_i, st2, &c->launches, 4 * mk));
+  return done();
+}
+
+// Pipelined mode of a sharded query: all outputs are device memory (nothing has to be copied out, so the call only
+// enqueues) and the context runs on its own stream.  Chooses the buffer set of this batch -- the one batch b - 2 used --
+// and makes the main stream wait until that batch has left the exchange stream; that wait is also the flow control of
+// the peer-memory exchange (a rank publishes batch b only after its merge of batch b - 2, i.e. after every rank has
+// consumed what batch b - 2 left in the windows).
+static bool can_pipeline(sodso_ctx *c, const int64_t *idx, const double *score, const double *d_p, const double *d_i) {
+  return c->stream == c->own_stream && is_device_ptr(idx) && is_device_ptr(score) && (!d_p || is_device_ptr(d_p)) &&
+         (!d_i || is_device_ptr(d_i));
+}
+static int pipeline_begin(sodso_db *db) {
+  sodso_ctx *c = db->ctx;
+  if (!c->xchg_stream) {
+    SODSO_CUDA_CHECK(cudaStreamCreateWithFlags(&c->xchg_stream, cudaStreamNonBlocking));
+    for (int f = 0; f < 2; f++) {
+      SODSO_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_stats[f], cudaEventDisableTiming));
+      SODSO_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_done[f], cudaEventDisableTiming));
+    }
+  }
+  const int f = (int)((c->batch_no + 1) & 1u);
+  if (c->ev_done_rec[f]) SODSO_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_done[f], 0));
+  std::swap(db->dp, db->dp2);
+  std::swap(db->di, db->di2);
+  std::swap(db->stats, db->stats2);
+  std::swap(db->gstats, db->gstats2);
+  std::swap(db->pack, db->pack2);
+  std::swap(db->gather, db->gather2);
   return SODSO_OK;
 }
 
 // host-or-device outputs around finish_sharded_async; synchronises only when something is copied to the host
 static int finish_sharded(sodso_db *db, int64_t q_row0, int mask_width, double p_weight, int k, int64_t *idx,
-                          double *score, double *d_p, double *d_i) {
+                          double *score, double *d_p, double *d_i, bool pipelined = false) {
   sodso_ctx *c = db->ctx;
   if (c->comm && c->comm->nranks > 16) {
     set_error("sharded query: at most 16 ranks");
@@ -310,7 +359,7 @@ static int finish_sharded(sodso_db *db, int64_t q_row0, int mask_width, double p
   if ((rc = stage_out(c, score, cnt, db->score, &sd))) return rc;
   if ((rc = stage_out(c, d_p, cnt, db->dpat, &pa))) return rc;
   if ((rc = stage_out(c, d_i, cnt, db->diat, &ia))) return rc;
-  if ((rc = finish_sharded_async(db, q_row0, mask_width, p_weight, k, id, sd, pa, ia))) return rc;
+  if ((rc = finish_sharded_async(db, q_row0, mask_width, p_weight, k, id, sd, pa, ia, pipelined))) return rc;
   const bool any_host = id != idx || sd != score || (d_p && pa != d_p) || (d_i && ia != d_i);
   if ((rc = finish_out(c, idx, cnt, id))) return rc;
   if ((rc = finish_out(c, score, cnt, sd))) return rc;
@@ -409,6 +458,8 @@ int sodso_db_finish_sharded(sodso_db *db, int64_t q_global_row0, int mask_width,
     set_error("db_finish_sharded before a match");
     return SODSO_E_STATE;
   }
+  int rc;
+  if ((rc = join_xchg(c))) return rc;
   return finish_sharded(db, q_global_row0, mask_width, p_weight, k, idx, score, d_p, d_i);
 }
 
@@ -421,8 +472,10 @@ int sodso_db_query_sharded(sodso_db *db, const double *hist1, int m, int64_t q_g
   sodso_ctx *c = db->ctx;
   CTX_CHECK(c);
   int rc;
+  const bool pipelined = can_pipeline(c, idx, score, d_p, d_i);
+  if ((rc = pipelined ? pipeline_begin(db) : join_xchg(c))) return rc;
   if ((rc = db_match_async(db, hist1, m))) return rc;
-  return finish_sharded(db, q_global_row0, mask_width, p_weight, k, idx, score, d_p, d_i);
+  return finish_sharded(db, q_global_row0, mask_width, p_weight, k, idx, score, d_p, d_i, pipelined);
 }
 
 int sodso_db_scans_query_sharded(sodso_db *db, const double *db_xyz, const float *db_inten, const int64_t *db_off,
@@ -453,6 +506,7 @@ int sodso_db_scans_query_sharded(sodso_db *db, const double *db_xyz, const float
     }
   }
   int rc;
+  if ((rc = join_xchg(c))) return rc;
   // the queries are the shard's own scans (same buffers, a self-match on this rank): they are binned once, while the
   // shard streams in.  Every pair is still computed -- see db_stream_match_async.
   const bool self = db_xyz && q_xyz == db_xyz && q_inten == db_inten && q_off == db_off && m_slice == m_total &&
