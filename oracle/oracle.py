@@ -5,8 +5,11 @@ the matcher (MATLAB's `*` is a multithreaded BLAS dgemm, so numpy+OpenBLAS is th
 stand-in for timing).  Only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs may import this module.
 
-parity unpinned: no golden signatures exist in the reference; the
-only pinned output is incoming_id_file.txt (tests/test_oracle_golden.py).
+parity unpinned for Eigen's arithmetic (decomposition signs, summation order): no golden
+signatures exist in the reference.  Pinned: incoming_id_file.txt
+(tests/test_oracle_golden.py) and, bit for bit, every statement of the reference's own
+descriptor sources compiled unchanged against oracle/eigen_shim (oracle/refsrc.py,
+tests/test_refsrc_pin.py).
 """
 from __future__ import annotations
 

@@ -5,12 +5,19 @@
 //  path of IRVLab/so_dso_place_recognition.  Only tests/, __graft_entry__.smoke()
 //  and bench.py's cpu_baseline / --impl reference legs may load this library.
 //
-//  PARITY STATUS: **parity unpinned** for descriptor values / distances / top-1.
+//  PARITY STATUS: **parity unpinned** for Eigen's arithmetic, pinned for everything else.
 //  The reference ships no golden signatures (history_*.txt is git-ignored,
-//  /root/reference/.gitignore:1) and cannot be compiled here (needs Eigen, ROS:
-//  PosesPts.h:1, test_sc.cpp:4).  What IS pinned: frame selection
-//  (incoming_id_file.txt of all 13 committed sequences, reproduced exactly by
-//  orc_stage_* below; see tests/test_oracle_golden.py).
+//  /root/reference/.gitignore:1) and cannot be built as shipped (Eigen, ROS, PCL, OpenCV through
+//  catkin: CMakeLists.txt:6-17).  What IS pinned:
+//   * frame selection: incoming_id_file.txt of all 13 committed sequences, reproduced exactly by
+//     orc_stage_* below (tests/test_oracle_golden.py);
+//   * every statement of the reference's own descriptor sources: SC.cpp, M2DP.cpp, DELIGHT.cpp,
+//     utils/pts_align.h, utils/pts_preprocess.h and PosesPts.h compile UNCHANGED against
+//     oracle/eigen_shim (`make refsrc` -> oracle/_ref/libsodso_refsrc.so) and equal this restatement
+//     BIT FOR BIT on synthetic, degenerate and real scans and on whole sequences, staged point order
+//     included (tests/test_refsrc_pin.py; committed outputs: tests/golden/refsrc_pin.npz).
+//  What is NOT pinned (hence "unpinned" stays in this header): the sign Eigen gives an eigenvector /
+//  singular vector and the order Eigen sums a product in -- the shim takes both from this file.
 //
 //  Third-party arithmetic not in /root/reference: Eigen3 (unpinned version,
 //  CMakeLists.txt:7) SelfAdjointEigenSolver / JacobiSVD.  Restated here by a

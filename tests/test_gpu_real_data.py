@@ -32,6 +32,20 @@ def test_generation_on_real_scans_of_three_sequences(gpu_ctx):
     np.testing.assert_array_equal(dl, g["delight_hist"])                          # integer histograms
 
 
+def test_generation_against_reference_source_outputs(gpu_ctx):
+    """refsrc_pin.npz holds what the reference's OWN sources (SC.cpp, M2DP.cpp, DELIGHT.cpp, pts_align.h, compiled
+    unchanged against oracle/eigen_shim; tests/golden/make_golden_refsrc.py) produce for 6 synthetic + 6 real scans,
+    at lidarRange 45 and 12 (the latter drops most points past the last ring, SC.cpp:42 / M2DP.cpp:66)."""
+    g = np.load(os.path.join(GOLDEN, "refsrc_pin.npz"))
+    for rho, tag in ((45.0, ""), (12.0, "_rho12")):
+        sc = api.sc_generate(g["xyz"], g["inten"], g["off"], rho)
+        np.testing.assert_array_equal(sc[:, 1200:], g["sc_hist" + tag][:, 1200:])
+        np.testing.assert_allclose(sc[:, :1200], g["sc_hist" + tag][:, :1200], rtol=0, atol=1e-9)
+        m2 = api.m2dp_generate(g["xyz"], g["inten"], g["off"], rho)
+        np.testing.assert_allclose(m2, g["m2dp_hist" + tag], rtol=0, atol=1e-9)
+    np.testing.assert_array_equal(api.delight_generate(g["xyz"], g["inten"], g["off"]), g["delight_hist"])
+
+
 def test_robotcar_cross_sequence_decision(gpu_ctx):
     g = np.load(os.path.join(GOLDEN, "robotcar_cross_sc.npz"))
     h1, h2 = _hist_sc(g["structure6_1"], g["intensity_bits_1"]), _hist_sc(g["structure6_2"], g["intensity_bits_2"])
