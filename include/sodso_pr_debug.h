@@ -28,6 +28,11 @@ int sodso_debug_set_sc_symmetry(sodso_ctx *ctx, int on);
  * gen_ctas = CTAs per SM of sc_generate_kernel (0 = default) */
 int sodso_debug_set_kernel_flags(int tc_flags, int gen_flags, int gen_ctas);
 
+/* per-phase clock sums of m2dp_generate_kernel (thread 0 of every CTA, summed over CTAs and scans), used by
+ * tools/profile_m2dp.py: enable != 0 allocates the 16-counter device buffer (the kernel then records), out16 != NULL
+ * synchronises, copies the counters out and clears them, enable = 0 frees the buffer (process-wide, current device) */
+int sodso_debug_phase_profile(int enable, unsigned long long *out16);
+
 /* on = 0: communicators created afterwards do not set up the peer-memory windows, so the sharded exchange runs on
  * ncclAllReduce / ncclAllGather (tests compare the two transports) */
 int sodso_debug_set_peer_exchange(int on);

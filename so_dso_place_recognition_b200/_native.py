@@ -100,6 +100,7 @@ _DEBUG_PROTOS = {
     "sodso_debug_set_match_algo": (_i, [_vp, _i]),
     "sodso_debug_set_sc_symmetry": (_i, [_vp, _i]),
     "sodso_debug_set_kernel_flags": (_i, [_i, _i, _i]),
+    "sodso_debug_phase_profile": (_i, [_i, C.c_void_p]),
     "sodso_debug_set_peer_exchange": (_i, [_i]),
     "sodso_debug_fast_turns": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "sodso_debug_sc_self_items": (_i64, [_i64, _i64, _i64]),

@@ -301,6 +301,24 @@ int sodso_debug_set_kernel_flags(int tc_flags, int gen_flags, int gen_ctas) {
   return SODSO_OK;
 }
 
+int sodso_debug_phase_profile(int enable, unsigned long long *out16) {
+  if (enable && !g_debug.prof) {
+    SODSO_CUDA_CHECK(cudaMalloc(&g_debug.prof, 16 * sizeof(unsigned long long)));
+    SODSO_CUDA_CHECK(cudaMemset(g_debug.prof, 0, 16 * sizeof(unsigned long long)));
+  }
+  if (out16) {
+    if (!g_debug.prof) return SODSO_E_ARG;
+    SODSO_CUDA_CHECK(cudaDeviceSynchronize());
+    SODSO_CUDA_CHECK(cudaMemcpy(out16, g_debug.prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    SODSO_CUDA_CHECK(cudaMemset(g_debug.prof, 0, 16 * sizeof(unsigned long long)));
+  }
+  if (!enable && g_debug.prof) {
+    cudaFree(g_debug.prof);
+    g_debug.prof = nullptr;
+  }
+  return SODSO_OK;
+}
+
 int64_t sodso_ctx_launch_count(sodso_ctx *c) { return c ? c->launches : 0; }
 
 double sodso_ctx_last_kernel_ms(sodso_ctx *c) {

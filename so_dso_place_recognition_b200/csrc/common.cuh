@@ -53,6 +53,7 @@ struct DebugFlags {
   int tc_flags = 0;    // sc_match_tc_kernel: 1 skip epilogue loads, 2 skip MMAs, 4 force generic mode
   int gen_flags = 2;   // sc_generate_kernel variant bits
   int gen_ctas = 0;    // CTAs per SM of sc_generate_kernel (0 = default)
+  unsigned long long *prof = nullptr;   // device buffer of 16 phase clock sums (sodso_debug_phase_profile)
 };
 extern DebugFlags g_debug;
 

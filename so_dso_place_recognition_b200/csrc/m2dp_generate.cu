@@ -49,9 +49,15 @@ constexpr int HB = M2DP_PQ * M2DP_SR;   // 8192 histogram bins
 constexpr float M2_GUARD_R = 3e-5f;      // ring coordinate guard (see the binning loop)
 constexpr int SVD_WARPS = 4;            // warps in the power iteration
 constexpr int QCAP = 4096;              // deferred (point, plane) evaluations of a pass (8 bytes each, in the T area)
-constexpr int GLD = M2DP_PQ + 4;        // leading dimension of the 64 x 64 fp64 workspaces: rows 32 B (mod 128 B) apart, so
-                                        // that the 8 x 4 fragment loads of the fp64 tensor-core squaring are conflict-free
+// the two SVD groups of a CTA: group 0 (count matrix: the integer Gram matrix is the bigger job) and group 1 (binarised
+// matrix) work at the same time on their own workspaces
+constexpr int SVD_G0 = 640, SVD_G1 = M2_THREADS - SVD_G0;
+constexpr int WS = M2DP_PQ * M2DP_PQ;   // doubles in a 64 x 64 workspace
 constexpr float TAN22 = 0.41421356237f;
+// cross-pair stash (global memory, per CTA): the p = 0 rows of variants 1 and 3, derived from those of variants 0 and 2
+constexpr int P0_BINS = M2DP_NUM_Q * M2DP_SR;        // 2048 bins of the 16 planes with p = 0
+constexpr int STASH_U32 = 4 * P0_BINS;               // [cnt slot 0 | cnt slot 1 | isum slot 0 | isum slot 1]
+constexpr int STASH_MAX_CTAS = 256;
 
 __constant__ double c_xproj[3 * M2DP_PQ];
 __constant__ double c_yproj[3 * M2DP_PQ];
@@ -63,15 +69,44 @@ struct M2Smem {
   unsigned cnt[2][HB];          // count histograms of the two variants of a pair (A0 of the SVD)
   int isum[2][HB];              // exact mode: intensity sums in units of 2^emin; then, in place, the binarised matrix.
                                 // inexact mode (one variant at a time): the 64 KB are HB fp64 sums
-  double G[M2DP_PQ * GLD];      // Gram matrix -> G^16
-  double T[M2DP_PQ * GLD];      // squaring workspace; during binning: the queue of deferred evaluations
+  double G[WS];                 // Gram matrix -> G^16 of SVD group 0 (swizzled 64 x 64, see gi())
+  double T[WS];                 // its squaring workspace; during binning: the queue of deferred evaluations
+                                // (SVD group 1 takes its two workspaces from the isum area, free once binarised)
+  unsigned bits[2][M2DP_PQ * 4];   // the binarised intensity matrices of the two slots: 128-bit row masks
   double scratch[11 * 32];
-  double uvec[M2DP_PQ], yv[M2DP_SR], red[SVD_WARPS], red2[SVD_WARPS], sig;
+  // per SVD group: power iteration state (two parities: unnormalised iterate, partial squared norms, partial squared
+  // updates), the result vectors, the Gram scale
+  double ubuf[2][2][M2DP_PQ], nrm[2][2][SVD_WARPS], upd[2][2][SVD_WARPS];
+  double uvec[2][M2DP_PQ], yv[2][M2DP_SR], red[2][SVD_WARPS], sig[2];
   double bc[16];
   int ibc[4];
   int qn;
+  int prof_on;                       // sodso_debug_phase_profile: thread 0 sums clock64 deltas per phase
+  long long prof_t;
+  unsigned long long prof[16];
 };
 static_assert(sizeof(M2Smem) <= 227 * 1024, "shared memory");
+static_assert(2 * WS * sizeof(double) <= sizeof(int) * 2 * HB, "SVD group 1's workspaces fit in the isum area");
+static_assert(QCAP * sizeof(unsigned long long) <= WS * sizeof(double), "the queue fits in T");
+
+// element (r, c) of a 64 x 64 fp64 workspace.  The column is XOR-swizzled by the row (4-double granules), so that the
+// 8 rows x 4 columns fragment loads of the fp64 tensor-core squaring hit 32 different 8-byte words of one aligned 256 B
+// span (conflict free) without padding the rows -- two workspaces are exactly the 64 KB of the isum area.
+__device__ __forceinline__ int gi(int r, int c) { return r * M2DP_PQ + (c ^ ((r & 7) << 2)); }
+__device__ __forceinline__ void group_sync(int g) {
+  asm volatile("bar.sync %0, %1;" ::"r"(8 + g), "r"(g ? SVD_G1 : SVD_G0) : "memory");
+}
+
+// phases: 0 moments + eigen-solve, 1 main binning pass, 2 twin-row copy, 3 binning of the p = 0 planes of the twin,
+// 4 queue replay, 5 binarise, 6 Gram (counts), 10 Gram (binary), 7 squarings, 8 power iteration, 9 v = A^T u + output
+#define M2_PROF(k)                                            \
+  do {                                                        \
+    if (S.prof_on && threadIdx.x == 0) {                      \
+      const long long t_ = clock64();                         \
+      S.prof[k] += (unsigned long long)(t_ - S.prof_t);       \
+      S.prof_t = t_;                                          \
+    }                                                         \
+  } while (0)
 
 struct ScanRef {
   const double *g;
@@ -162,12 +197,22 @@ __device__ __forceinline__ int twin_plane(int pq) {
 __device__ __forceinline__ unsigned long long queue_entry(int i, int pq, int slot, bool twin) {
   return ((unsigned long long)(unsigned)i << 8) | (unsigned)(pq | (slot << 6) | (twin ? 0x80 : 0));
 }
+// stash != nullptr (first pair of a scan): an entry of a p = 0 plane of variant v also stands for the same plane of
+// variant v ^ 1 (second pair), whose p = 0 rows are kept in the stash
 template <bool EXACT>
 __device__ __forceinline__ void run_entry(M2Smem &S, const ScanRef &R, unsigned long long w, int var_slot0,
-                                          int var_slot1, float iscale) {
+                                          int var_slot1, float iscale, unsigned *stash = nullptr) {
   const int i = (int)(w >> 8), pq = (int)(w & 0x3fu), slot = (int)((w >> 6) & 1u);
-  add_exact<EXACT>(S, R, i, pq, slot ? var_slot1 : var_slot0, slot, iscale);
+  const int var = slot ? var_slot1 : var_slot0;
+  add_exact<EXACT>(S, R, i, pq, var, slot, iscale);
   if (w & 0x80u) add_exact<EXACT>(S, R, i, twin_plane(pq), var_slot1, 1, iscale);
+  if (EXACT && stash && pq < M2DP_NUM_Q) {
+    const int idx = m2dp_bin_exact(R, i, pq, var ^ 1);
+    if (idx >= 0) {
+      atomicAdd(&stash[slot * P0_BINS + idx], 1u);
+      atomicAdd(reinterpret_cast<int *>(stash) + 2 * P0_BINS + slot * P0_BINS + idx, (int)(R.gi[i] * iscale));
+    }
+  }
 }
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -217,26 +262,27 @@ __device__ __forceinline__ int propose_bin(float xp, float yp, float R_f, float 
   return ri * M2DP_NUM_S + sector;
 }
 
-// Y = X X for a symmetric 64 x 64 fp64 matrix (leading dimension GLD) on the fp64 tensor cores
-// (mma.sync.m8n8k4.f64: 256 multiply-adds per warp instruction instead of 32).  Warp w owns the 8 x 8 output
-// tile(s) listed below; the B fragment X[k][j] is read as X[j][k] (symmetry), so both operands are 8 x 4 row-major
-// reads.  Fragments (PTX ISA, m8n8k4 .f64): A[lane / 4][lane % 4], B[lane % 4][lane / 4],
-// C[lane / 4][2 (lane % 4) + {0, 1}].
-__device__ __forceinline__ void sym_square64(const double *X, double *Y) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// Y = X X for a symmetric 64 x 64 fp64 matrix (swizzled, gi()) on the fp64 tensor cores (mma.sync.m8n8k4.f64: 256
+// multiply-adds per warp instruction instead of 32), by the 16 warps of one SVD group.  The B fragment X[k][j] is read
+// as X[j][k] (symmetry), so both operands are 8 x 4 row reads.  Fragments (PTX ISA, m8n8k4 .f64):
+// A[lane / 4][lane % 4], B[lane % 4][lane / 4], C[lane / 4][2 (lane % 4) + {0, 1}].
+__device__ __forceinline__ void sym_square64(const double *X, double *Y, int gwarp, int gwarps) {
+  const int lane = threadIdx.x & 31;
   const int r = lane >> 2, c = lane & 3;
   // Y is symmetric too: only the 36 tiles (I, J <= I) of the 8 x 8 tile grid are computed, the others are mirrored.
-  // Tile t = I (I + 1) / 2 + J; warp w takes tile w, warps 0..3 also tile 32 + w.
-  for (int t = warp; t < 36; t += 32) {
+  // Tile t = I (I + 1) / 2 + J; warp w of the group takes tiles w, w + gwarps, ...
+  for (int t = gwarp; t < 36; t += gwarps) {
     int I = 0;
     while ((I + 1) * (I + 2) / 2 <= t) I++;
     const int J = t - I * (I + 1) / 2;
     const int i0 = I * 8, j0 = J * 8;
-    const double *pa = X + (i0 + r) * GLD + c, *pb = X + (j0 + r) * GLD + c;
+    // rows i0 + r and j0 + r have (row & 7) == r: the swizzle of column k0 + c is ((k0 >> 2) ^ r) << 2 | c
+    const double *pa = X + (i0 + r) * M2DP_PQ + c, *pb = X + (j0 + r) * M2DP_PQ + c;
     double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;   // two accumulator pairs: even / odd k steps (shorter chains)
 #pragma unroll 4
     for (int k0 = 0; k0 < M2DP_PQ; k0 += 8) {
-      const double a0 = pa[k0], b0 = pb[k0], a1 = pa[k0 + 4], b1 = pb[k0 + 4];
+      const int o0 = ((k0 >> 2) ^ r) << 2, o1 = (((k0 >> 2) + 1) ^ r) << 2;
+      const double a0 = pa[o0], b0 = pb[o0], a1 = pa[o1], b1 = pb[o1];
       asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                    : "+d"(c0), "+d"(c1)
                    : "d"(a0), "d"(b0));
@@ -246,120 +292,125 @@ __device__ __forceinline__ void sym_square64(const double *X, double *Y) {
     }
     c0 += e0;
     c1 += e1;
-    *reinterpret_cast<double2 *>(Y + (i0 + r) * GLD + j0 + 2 * c) = make_double2(c0, c1);
+    *reinterpret_cast<double2 *>(Y + gi(i0 + r, j0 + 2 * c)) = make_double2(c0, c1);
     if (I != J) {
-      Y[(j0 + 2 * c) * GLD + i0 + r] = c0;
-      Y[(j0 + 2 * c + 1) * GLD + i0 + r] = c1;
+      Y[gi(j0 + 2 * c, i0 + r)] = c0;
+      Y[gi(j0 + 2 * c + 1, i0 + r)] = c1;
     }
   }
 }
 
-// dominant singular pair of the 64 x 128 matrix A (u32, shared memory).  G / T: 64 x 64 fp64 workspaces.
+// dominant singular pair of a 64 x 128 matrix, by the threads of SVD group g (named barriers; the two groups of a
+// CTA work on the count matrix and on the binarised intensity matrix of a variant at the same time).  A: the count
+// matrix (u32), or for BINARY the 128-bit row masks.  G / T: the group's 64 x 64 fp64 workspaces.
 // Writes [u (64), v (128)] to out.
 //   G = A A^T exactly (64-bit integers), scaled by a power of two to trace ~ 1;  G^16 by four squarings;
 //   power iteration with G^16 from the all-ones vector (Perron pair: entrywise non-negative);
 //   sigma = |A^T u|, v = A^T u / sigma.
 template <bool BINARY>
-__device__ void dominant_pair(const unsigned *A, double *G, double *T, M2Smem &S, double *out) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+__device__ void dominant_pair(const unsigned *A, double *G, double *T, M2Smem &S, int g, double *out) {
+  const int gsize = g ? SVD_G1 : SVD_G0, tid = threadIdx.x - (g ? SVD_G0 : 0), warp = tid >> 5, lane = tid & 31;
+  const int gwarps = gsize >> 5;
+  double *uvec = S.uvec[g], *yv = S.yv[g], *red = S.red[g];
   if (BINARY) {
-    // 0 / 1 matrix: rows as 128-bit masks (in the T area), G[i][j] = popcount(row_i & row_j)
-    unsigned *mask = reinterpret_cast<unsigned *>(T);
-    for (int w = warp; w < M2DP_PQ * 4; w += M2_THREADS / 32) {   // word w: row w / 4, columns 32 (w % 4) ..
-      const unsigned bit = __ballot_sync(0xffffffffu, A[(w >> 2) * M2DP_SR + (w & 3) * 32 + lane] != 0u);
-      if (lane == 0) mask[w] = bit;
-    }
-    __syncthreads();
-    for (int e = tid; e < M2DP_PQ * M2DP_PQ; e += M2_THREADS) {
+    // 0 / 1 matrix: G[i][j] = popcount(row_i & row_j)
+    for (int e = tid; e < M2DP_PQ * M2DP_PQ; e += gsize) {
       const int i = e >> 6, j = e & 63;
-      const uint4 a = reinterpret_cast<const uint4 *>(mask)[i], b = reinterpret_cast<const uint4 *>(mask)[j];
-      G[i * GLD + j] = (double)(__popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w));
+      const uint4 a = reinterpret_cast<const uint4 *>(A)[i], b = reinterpret_cast<const uint4 *>(A)[j];
+      G[gi(i, j)] = (double)(__popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w));
     }
-  } else
-  // ---- Gram matrix: thread t < 528 owns the 2 x 2 block (bi, bj <= bi) of the lower block triangle.  Lane l walks k
-  // in 16-byte steps starting at step l, so the 8 lanes of a quarter-warp always hit 8 different 16-byte bank groups
-  // whatever rows they read (rows are 512 B apart); integer sums do not care about the order.
-  if (tid < 528) {   // (count matrix)
-    int bi = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
-    while ((bi + 1) * (bi + 2) / 2 <= tid) bi++;
-    while (bi * (bi + 1) / 2 > tid) bi--;
-    const int bj = tid - bi * (bi + 1) / 2;
-    const uint4 *r0 = reinterpret_cast<const uint4 *>(A + (2 * bi) * M2DP_SR);
-    const uint4 *r1 = reinterpret_cast<const uint4 *>(A + (2 * bi + 1) * M2DP_SR);
-    const uint4 *c0 = reinterpret_cast<const uint4 *>(A + (2 * bj) * M2DP_SR);
-    const uint4 *c1 = reinterpret_cast<const uint4 *>(A + (2 * bj + 1) * M2DP_SR);
-    unsigned long long g00 = 0, g01 = 0, g10 = 0, g11 = 0;
+  } else {
+    // ---- Gram matrix: the 528 2 x 2 blocks (bi, bj <= bi) of the lower block triangle, one per thread.  Lane l walks k in 16-byte steps starting at step l, so the 8 lanes of a quarter-warp always
+    // hit 8 different 16-byte bank groups whatever rows they read (rows are 512 B apart); integer sums do not care
+    // about the order.
+    for (int blk = tid; blk < 528; blk += gsize) {
+      int bi = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);
+      while ((bi + 1) * (bi + 2) / 2 <= blk) bi++;
+      while (bi * (bi + 1) / 2 > blk) bi--;
+      const int bj = blk - bi * (bi + 1) / 2;
+      const uint4 *r0 = reinterpret_cast<const uint4 *>(A + (2 * bi) * M2DP_SR);
+      const uint4 *r1 = reinterpret_cast<const uint4 *>(A + (2 * bi + 1) * M2DP_SR);
+      const uint4 *c0 = reinterpret_cast<const uint4 *>(A + (2 * bj) * M2DP_SR);
+      const uint4 *c1 = reinterpret_cast<const uint4 *>(A + (2 * bj + 1) * M2DP_SR);
+      unsigned long long g00 = 0, g01 = 0, g10 = 0, g11 = 0;
 #pragma unroll 4
-    for (int t = 0; t < M2DP_SR / 4; t++) {
-      const int k4 = (t + lane) & (M2DP_SR / 4 - 1);
-      const uint4 a0 = r0[k4], a1 = r1[k4], b0 = c0[k4], b1 = c1[k4];
-      g00 += (unsigned long long)a0.x * b0.x + (unsigned long long)a0.y * b0.y + (unsigned long long)a0.z * b0.z +
-             (unsigned long long)a0.w * b0.w;
-      g01 += (unsigned long long)a0.x * b1.x + (unsigned long long)a0.y * b1.y + (unsigned long long)a0.z * b1.z +
-             (unsigned long long)a0.w * b1.w;
-      g10 += (unsigned long long)a1.x * b0.x + (unsigned long long)a1.y * b0.y + (unsigned long long)a1.z * b0.z +
-             (unsigned long long)a1.w * b0.w;
-      g11 += (unsigned long long)a1.x * b1.x + (unsigned long long)a1.y * b1.y + (unsigned long long)a1.z * b1.z +
-             (unsigned long long)a1.w * b1.w;
+      for (int t = 0; t < M2DP_SR / 4; t++) {
+        const int k4 = (t + lane) & (M2DP_SR / 4 - 1);
+        const uint4 a0 = r0[k4], a1 = r1[k4], b0 = c0[k4], b1 = c1[k4];
+        g00 += (unsigned long long)a0.x * b0.x + (unsigned long long)a0.y * b0.y + (unsigned long long)a0.z * b0.z +
+               (unsigned long long)a0.w * b0.w;
+        g01 += (unsigned long long)a0.x * b1.x + (unsigned long long)a0.y * b1.y + (unsigned long long)a0.z * b1.z +
+               (unsigned long long)a0.w * b1.w;
+        g10 += (unsigned long long)a1.x * b0.x + (unsigned long long)a1.y * b0.y + (unsigned long long)a1.z * b0.z +
+               (unsigned long long)a1.w * b0.w;
+        g11 += (unsigned long long)a1.x * b1.x + (unsigned long long)a1.y * b1.y + (unsigned long long)a1.z * b1.z +
+               (unsigned long long)a1.w * b1.w;
+      }
+      const int i0 = 2 * bi, j0 = 2 * bj;
+      G[gi(i0, j0)] = (double)g00;
+      G[gi(j0, i0)] = (double)g00;
+      G[gi(i0, j0 + 1)] = (double)g01;
+      G[gi(j0 + 1, i0)] = (double)g01;
+      G[gi(i0 + 1, j0)] = (double)g10;
+      G[gi(j0, i0 + 1)] = (double)g10;
+      G[gi(i0 + 1, j0 + 1)] = (double)g11;
+      G[gi(j0 + 1, i0 + 1)] = (double)g11;
     }
-    const int i0 = 2 * bi, j0 = 2 * bj;
-    G[i0 * GLD + j0] = (double)g00;
-    G[j0 * GLD + i0] = (double)g00;
-    G[i0 * GLD + j0 + 1] = (double)g01;
-    G[(j0 + 1) * GLD + i0] = (double)g01;
-    G[(i0 + 1) * GLD + j0] = (double)g10;
-    G[j0 * GLD + i0 + 1] = (double)g10;
-    G[(i0 + 1) * GLD + j0 + 1] = (double)g11;
-    G[(j0 + 1) * GLD + i0 + 1] = (double)g11;
   }
-  __syncthreads();
+  group_sync(g);
+  if (g == 0) M2_PROF(6);
   // ---- scale to trace in [1, 2) (exact, power of two), so that G^16 neither overflows nor underflows
   if (warp == 0) {
-    double tr = G[lane * (GLD + 1)] + G[(lane + 32) * (GLD + 1)];
+    double tr = G[gi(lane, lane)] + G[gi(lane + 32, lane + 32)];
     tr = warp_sum(tr);
     tr = __shfl_sync(0xffffffffu, tr, 0);
-    if (lane == 0) S.sig = tr > 0.0 ? scalbn(1.0, -ilogb(tr)) : 0.0;
+    if (lane == 0) S.sig[g] = tr > 0.0 ? scalbn(1.0, -ilogb(tr)) : 0.0;
   }
-  __syncthreads();
+  group_sync(g);
   {
-    const double sc = S.sig;
-    for (int e = tid; e < M2DP_PQ * GLD; e += M2_THREADS) G[e] *= sc;   // (the 4 padding columns are never read)
+    const double sc = S.sig[g];
+    for (int e = tid; e < WS; e += gsize) G[e] *= sc;
   }
-  __syncthreads();
-  sym_square64(G, T);   // G^2
-  __syncthreads();
-  sym_square64(T, G);   // G^4
-  __syncthreads();
-  sym_square64(G, T);   // G^8
-  __syncthreads();
-  sym_square64(T, G);   // G^16
-  if (tid < M2DP_PQ) S.uvec[tid] = 0.125;  // all-ones / |.| (Perron start)
-  __syncthreads();
-  // ---- power iteration with G^16: SVD_WARPS warps, 2 threads per row, named barrier
+  group_sync(g);
+  sym_square64(G, T, warp, gwarps);   // G^2
+  group_sync(g);
+  sym_square64(T, G, warp, gwarps);   // G^4
+  group_sync(g);
+  sym_square64(G, T, warp, gwarps);   // G^8
+  group_sync(g);
+  sym_square64(T, G, warp, gwarps);   // G^16
+  if (tid < M2DP_PQ) S.ubuf[g][0][tid] = 0.125;  // all-ones / |.| (Perron start)
+  if (tid < SVD_WARPS) {
+    S.nrm[g][0][tid] = 1.0 / SVD_WARPS;
+    S.upd[g][0][tid] = 1.0;
+  }
+  group_sync(g);
+  if (g == 0) M2_PROF(7);
+  // ---- power iteration with G^16: SVD_WARPS warps, 2 threads per row, ONE named barrier per iteration.  The iterate
+  // is kept unnormalised (w_k, parity k & 1) together with the partial sums of |w_k|^2; the normalisation of step k is
+  // applied by the readers in step k + 1 (u_k = w_k / |w_k|), and the size of the update |u_k - u_{k-1}|^2 is known one
+  // step later still -- the loop runs two steps past convergence, each step is half as long.
   if (warp < SVD_WARPS) {
     const int t = warp * 32 + lane;          // 0..127
     const int row = t >> 1, half = t & 1;
-    const int bar_n = SVD_WARPS * 32;
-    for (int iter = 0; iter < 2000; iter++) {
-      double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 8
-      for (int k = 0; k < 32; k += 2) {
-        const int c = half * 32 + k;
-        acc0 = fma(G[c * GLD + row], S.uvec[c], acc0);   // G symmetric: column access is conflict-free
-        acc1 = fma(G[(c + 1) * GLD + row], S.uvec[c + 1], acc1);
-      }
-      double acc = acc0 + acc1;
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      double sq = half == 0 ? acc * acc : 0.0;
-      sq = warp_sum(sq);
-      if (lane == 0) S.red[warp] = sq;
-      asm volatile("bar.sync 1, %0;" ::"r"(bar_n) : "memory");   // all reads of uvec done
-      double nn = 0.0;
+    const int bar_n = SVD_WARPS * 32, bar_id = 10 + g;
+    double u_prev = 0.125;                   // u_{k-1}[row]
+    int iter = 0;
+    for (; iter < 4000; iter++) {
+      const int p = iter & 1;
+      const double *w = S.ubuf[g][p];
+      double nn = 0.0, dd = 0.0;
 #pragma unroll
-      for (int w = 0; w < SVD_WARPS; w++) nn += S.red[w];
-      if (nn == 0.0) break;  // zero matrix (uniform over the group)
+      for (int k = 0; k < SVD_WARPS; k++) {
+        nn += S.nrm[g][p][k];
+        dd += S.upd[g][p][k];
+      }
+      if (nn == 0.0) {   // zero matrix (uniform over the group)
+        if (half == 0) uvec[row] = 0.0;
+        break;
+      }
       // 1 / sqrt(nn): fp32 seed + three Newton steps (rel. error 1e-7 -> 1e-14 -> 1e-28 -> rounding), instead of the
-      // fp64 square root and division routines (the normalisation is on the critical path of every iteration)
+      // fp64 square root and division routines; independent of the matrix-vector product below
       double inv = (double)rsqrtf((float)nn);
       {
         const double hn = 0.5 * nn;
@@ -367,56 +418,79 @@ __device__ void dominant_pair(const unsigned *A, double *G, double *T, M2Smem &S
         inv = inv * fma(-hn * inv, inv, 1.5);
         inv = inv * fma(-hn * inv, inv, 1.5);
       }
-      double d2 = 0.0;
-      if (half == 0) {
-        const double nv = acc * inv;
-        const double d = nv - S.uvec[row];
-        d2 = d * d;
-        S.uvec[row] = nv;
+      const double u_cur = w[row] * inv;     // u_k[row]
+      if (dd < 1e-29) {                      // |u_{k-1} - u_{k-2}|^2: converged (uniform over the group)
+        if (half == 0) uvec[row] = u_cur;
+        break;
       }
-      d2 = warp_sum(d2);
-      if (lane == 0) S.red2[warp] = d2;
-      asm volatile("bar.sync 1, %0;" ::"r"(bar_n) : "memory");   // uvec / red2 complete
-      double dd = 0.0;
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < 32; k += 2) {
+        const int c = half * 32 + k;
+        acc0 = fma(G[gi(c, row)], w[c], acc0);   // G symmetric: column access is conflict-free
+        acc1 = fma(G[gi(c + 1, row)], w[c + 1], acc1);
+      }
+      double acc = acc0 + acc1;
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc *= inv;                            // w_{k+1} = G^16 u_k
+      const double d = u_cur - u_prev;
+      u_prev = u_cur;
+      const double sq = warp_sum(half == 0 ? acc * acc : 0.0);
+      const double d2 = warp_sum(half == 0 ? d * d : 0.0);
+      if (half == 0) S.ubuf[g][p ^ 1][row] = acc;
+      if (lane == 0) {
+        S.nrm[g][p ^ 1][warp] = sq;
+        S.upd[g][p ^ 1][warp] = iter == 0 ? 1.0 : d2;
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");
+    }
+    if (S.prof_on && t == 0) atomicAdd(&S.prof[11 + g], (unsigned long long)iter);   // iterations per group
+  }
+  group_sync(g);
+  if (g == 0) M2_PROF(8);
+  // ---- y = A^T u (128), sigma = |y|: NP threads per column (64 / NP rows each), partial sums through the T area
+  {
+    constexpr int NP = BINARY ? 2 : 4;
+    static_assert(NP * M2DP_SR <= (BINARY ? SVD_G1 : SVD_G0), "threads of the group");
+    if (tid < NP * M2DP_SR) {
+      const int col = tid & (M2DP_SR - 1), part = tid >> 7;
+      double acc = 0.0;
 #pragma unroll
-      for (int w = 0; w < SVD_WARPS; w++) dd += S.red2[w];
-      if (dd < 1e-29) break;
+      for (int r = 0; r < M2DP_PQ / NP; r++) {
+        const int rr = part * (M2DP_PQ / NP) + r;
+        const double a = BINARY ? (double)((A[rr * 4 + (col >> 5)] >> (col & 31)) & 1u) : (double)A[rr * M2DP_SR + col];
+        acc = fma(a, uvec[rr], acc);
+      }
+      T[part * M2DP_SR + col] = acc;
+    }
+    group_sync(g);
+    if (tid < M2DP_SR) {
+      double acc = 0.0;
+#pragma unroll
+      for (int part = 0; part < NP; part++) acc += T[part * M2DP_SR + tid];
+      yv[tid] = acc;
+      const double sq = warp_sum(acc * acc);
+      if (lane == 0) red[warp] = sq;
     }
   }
-  __syncthreads();
-  // ---- y = A^T u (128), sigma = |y|: 8 threads per column (8 rows each), partial sums through the T area
-  {
-    const int col = tid & (M2DP_SR - 1), part = tid >> 7;
-    double acc = 0.0;
-#pragma unroll
-    for (int r = 0; r < M2DP_PQ / 8; r++) acc = fma((double)A[(part * 8 + r) * M2DP_SR + col], S.uvec[part * 8 + r], acc);
-    T[part * M2DP_SR + col] = acc;
-  }
-  __syncthreads();
-  if (tid < M2DP_SR) {
-    double acc = 0.0;
-#pragma unroll
-    for (int part = 0; part < 8; part++) acc += T[part * M2DP_SR + tid];
-    S.yv[tid] = acc;
-    const double sq = warp_sum(acc * acc);
-    if (lane == 0) S.red[warp] = sq;
-  }
-  __syncthreads();
+  group_sync(g);
   // ---- outputs: u, v = y / sigma  (zero matrix: u = e_0, v = 0, the oracle's convention)
   if (tid < M2DP_SIG) {
-    const double sigma = sqrt((S.red[0] + S.red[1]) + (S.red[2] + S.red[3]));
+    const double sigma = sqrt((red[0] + red[1]) + (red[2] + red[3]));
     double v;
     if (tid < M2DP_PQ)
-      v = sigma == 0.0 ? (tid == 0 ? 1.0 : 0.0) : S.uvec[tid];
+      v = sigma == 0.0 ? (tid == 0 ? 1.0 : 0.0) : uvec[tid];
     else
-      v = sigma == 0.0 ? 0.0 : S.yv[tid - M2DP_PQ] / sigma;
+      v = sigma == 0.0 ? 0.0 : yv[tid - M2DP_PQ] / sigma;
     out[tid] = v;
   }
-  __syncthreads();
+  if (g == 0) M2_PROF(9);
 }
 
 // sector map of the mirrored twin plane: (xp, yp) -> (-xp, yp), i.e. phi -> 180 deg - phi
 __device__ __forceinline__ int mirror_sr(int sr) { return (sr & ~15) | ((7 - (sr & 15)) & 15); }
+// sector map between the p = 0 planes of variants v and v ^ 1: (xp, yp) -> (xp, -yp), i.e. phi -> -phi
+__device__ __forceinline__ int mirror15_sr(int sr) { return sr ^ 15; }
 
 // One block of 1024 points (FULL: all lanes hold a point) of a binning pass.  EXACT: integer intensity sums.
 // Evaluations inside the guard band are pushed to the queue (replayed by the caller in fp64, replay_queue);
@@ -424,7 +498,7 @@ __device__ __forceinline__ int mirror_sr(int sr) { return (sr & ~15) | ((7 - (sr
 template <int PQ0, int PQ1, bool EXACT, bool FULL>
 __device__ __forceinline__ void bin_block(M2Smem &S, const ScanRef &R, int var, int slot, int twin_var, float R_f,
                                           float iscale, unsigned long long degen_mask, int degen_sr_pos,
-                                          int degen_sr_neg, int i0) {
+                                          int degen_sr_neg, int i0, float coord_lim) {
   const int lane = threadIdx.x & 31;
   unsigned *hcnt = S.cnt[slot];
   int *hisum = S.isum[slot];
@@ -447,8 +521,9 @@ __device__ __forceinline__ void bin_block(M2Smem &S, const ScanRef &R, int var, 
       pz = fdz * (float)az;
     }
     const int iv = (int)(it * iscale);
-    // the fp32 error bound assumes coordinates below 128 m (the staging crops at 45 m)
-    const float r2_lim = fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz))) < 128.0f ? 1e10f : -1.0f;
+    // the fp32 error bound assumes coordinates below coord_lim = 128 m (the staging crops at 45 m); 64 m when the
+    // p = 0 rows also stand for the other pair's (see the host check in launch_m2dp_generate)
+    const float r2_lim = fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz))) < coord_lim ? 1e10f : -1.0f;
     // planes whose projection vectors are exactly zero (p=2, q=0): xp = yp = -0 if all three
     // coordinates are negative, +0 otherwise, and every point lands in one of two bins -> warp-aggregated
     for (unsigned long long dm = degen_mask; dm; dm &= dm - 1) {
@@ -513,9 +588,10 @@ __device__ __forceinline__ void bin_block(M2Smem &S, const ScanRef &R, int var, 
           const int slot_q = atomicAdd(&S.qn, 1);
           if (slot_q < QCAP)
             queue[slot_q] = w;
-          else if (!twin)
+          else if (!twin) {
             run_entry<EXACT>(S, R, w, var, twin_var, iscale);
-          else
+            if (pq < M2DP_NUM_Q) S.ibc[1] = 1;   // ... and the p = 0 rows of this pass cannot seed the second pair
+          } else
             S.ibc[3] = 1;   // shared evaluations lost: the caller redoes the pair one variant at a time
         }
       }
@@ -540,56 +616,77 @@ __device__ __forceinline__ void bin_block(M2Smem &S, const ScanRef &R, int var, 
 template <int PQ0, int PQ1, bool EXACT>
 __device__ __forceinline__ void bin_pass(M2Smem &S, const ScanRef &R, int var, int slot, int twin_var, float R_f,
                                          float iscale, unsigned long long degen_mask, int degen_sr_pos,
-                                         int degen_sr_neg) {
+                                         int degen_sr_neg, float coord_lim = 128.0f) {
   int i0 = 0;
   for (; i0 + M2_THREADS <= R.n; i0 += M2_THREADS)
-    bin_block<PQ0, PQ1, EXACT, true>(S, R, var, slot, twin_var, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg, i0);
+    bin_block<PQ0, PQ1, EXACT, true>(S, R, var, slot, twin_var, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg, i0,
+                                     coord_lim);
   if (i0 < R.n)
-    bin_block<PQ0, PQ1, EXACT, false>(S, R, var, slot, twin_var, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg, i0);
+    bin_block<PQ0, PQ1, EXACT, false>(S, R, var, slot, twin_var, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg, i0,
+                                      coord_lim);
 }
 
 // the deferred evaluations of the passes since the queue was reset, one entry per thread
 template <bool EXACT>
-__device__ __forceinline__ void replay_queue(M2Smem &S, const ScanRef &R, int var_slot0, int var_slot1, float iscale) {
+__device__ __forceinline__ void replay_queue(M2Smem &S, const ScanRef &R, int var_slot0, int var_slot1, float iscale,
+                                             unsigned *stash = nullptr) {
   const unsigned long long *queue = reinterpret_cast<const unsigned long long *>(S.T);
   const int qn = S.qn < QCAP ? S.qn : QCAP;
-  for (int e = threadIdx.x; e < qn; e += M2_THREADS) run_entry<EXACT>(S, R, queue[e], var_slot0, var_slot1, iscale);
+  for (int e = threadIdx.x; e < qn; e += M2_THREADS)
+    run_entry<EXACT>(S, R, queue[e], var_slot0, var_slot1, iscale, stash);
 }
 
-// binarise slot (M2DP.cpp:84-91) in place, then the two dominant pairs -> one output row of 2 x 192
+// binarise the slots [slot0, slot0 + nslot) (M2DP.cpp:84-91) into 128-bit row masks, then per slot the two dominant
+// pairs -- count matrix on SVD group 0, binarised matrix on group 1, at the same time -- -> output rows of 2 x 192
 template <bool EXACT>
-__device__ __forceinline__ void finish_variant(M2Smem &S, int slot, float ave, double unscale, double *row) {
-  unsigned *hcnt = S.cnt[slot];
-  int *hisum = S.isum[slot];
+__device__ __forceinline__ void finish_variants(M2Smem &S, int nslot, float ave, double unscale, double *row0,
+                                                double *row1) {
+  const int lane = threadIdx.x & 31;
   const double *hsum = reinterpret_cast<const double *>(S.isum);
-  unsigned bv[HB / M2_THREADS];
+  for (int slot = 0; slot < nslot; slot++) {
+    const unsigned *hcnt = S.cnt[slot];
+    const int *hisum = S.isum[slot];
 #pragma unroll
-  for (int k = 0; k < HB / M2_THREADS; k++) {
-    const int b = threadIdx.x + k * M2_THREADS;
-    const unsigned c = hcnt[b];
-    unsigned v = 0u;
-    if (c) {
-      const double sum = EXACT ? (double)hisum[b] * unscale : hsum[b];
-      v = (sum / (double)c) > (double)ave ? 1u : 0u;
+    for (int k = 0; k < HB / M2_THREADS; k++) {
+      const int b = threadIdx.x + k * M2_THREADS;   // a warp holds 32 consecutive columns of one row
+      const unsigned c = hcnt[b];
+      bool v = false;
+      if (c) {
+        const double sum = EXACT ? (double)hisum[b] * unscale : hsum[b];
+        v = (sum / (double)c) > (double)ave;
+      }
+      const unsigned word = __ballot_sync(0xffffffffu, v);
+      if (lane == 0) S.bits[slot][b >> 5] = word;
     }
-    bv[k] = v;
+  }
+  __syncthreads();   // the isum area is free from here on: SVD group 1's workspaces
+  M2_PROF(5);
+  const int g = threadIdx.x >= SVD_G0 ? 1 : 0;
+  double *G1 = reinterpret_cast<double *>(&S.isum[0][0]);
+  for (int slot = 0; slot < nslot; slot++) {
+    double *row = slot ? row1 : row0;
+    if (g == 0)
+      dominant_pair<false>(S.cnt[slot], S.G, S.T, S, 0, row);                 // M2DP.cpp:94-98,107
+    else
+      dominant_pair<true>(S.bits[slot], G1, G1 + WS, S, 1, row + M2DP_SIG);   // M2DP.cpp:100-108
   }
   __syncthreads();
-  unsigned *bin_mat = reinterpret_cast<unsigned *>(hisum);   // (inexact mode: the first half of the fp64 sums)
-#pragma unroll
-  for (int k = 0; k < HB / M2_THREADS; k++) bin_mat[threadIdx.x + k * M2_THREADS] = bv[k];
-  __syncthreads();
-  dominant_pair<false>(hcnt, S.G, S.T, S, row);               // M2DP.cpp:94-98,107
-  dominant_pair<true>(bin_mat, S.G, S.T, S, row + M2DP_SIG);  // M2DP.cpp:100-108
 }
 
 __global__ void __launch_bounds__(M2_THREADS, 1)
 m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ inten,
                      const int64_t *__restrict__ off, int nscan, double S_res_inv, double R_res_inv,
-                     int variants, int mirror_ok, double *__restrict__ hist, unsigned long long degen_mask) {
+                     int variants, int mirror_ok, double *__restrict__ hist, unsigned long long degen_mask,
+                     unsigned *__restrict__ stash_all, unsigned long long *__restrict__ prof) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   M2Smem &S = *reinterpret_cast<M2Smem *>(smem_raw);
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    S.prof_on = prof != nullptr;
+    S.prof_t = clock64();
+    for (int k = 0; k < 16; k++) S.prof[k] = 0ull;
+  }
+  __syncthreads();
   // the two bins of a plane with zero projection vectors: M2DP.cpp:59-63 evaluated at (+0, +0) and (-0, -0)
   int degen_sr_pos, degen_sr_neg;
   {
@@ -600,6 +697,8 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
     degen_sr_neg = sn < M2DP_SR ? sn : -1;
   }
   const float R_f = (float)R_res_inv;
+  // mirror_ok bit 1: the p = 0 planes of variants v and v ^ 1 are mirror images to within the guard band (host check)
+  unsigned *stash = (mirror_ok & 2) && stash_all ? stash_all + (size_t)blockIdx.x * STASH_U32 : nullptr;
 
   for (int scan = blockIdx.x; scan < nscan; scan += gridDim.x) {
     const int64_t p0 = off[scan];
@@ -665,6 +764,7 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
       S.ibc[2] = __float_as_int(a);
     }
     __syncthreads();
+    M2_PROF(0);
     const float ave = (exact ? (float)s11[9] : __int_as_float(S.ibc[2])) / (float)n;  // M2DP.cpp:81
     const float iscale = exact && emin != (1 << 20) ? (float)ldexp(1.0, -emin) : 0.0f;
     const double unscale = exact && emin != (1 << 20) ? ldexp(1.0, emin) : 0.0;
@@ -695,17 +795,20 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
         __syncthreads();
         replay_queue<true>(S, R, v, v, iscale);
         __syncthreads();
-        finish_variant<true>(S, 0, ave, unscale, rows + (size_t)var * 2 * M2DP_SIG);
+        finish_variants<true>(S, 1, ave, unscale, rows + (size_t)var * 2 * M2DP_SIG, nullptr);
       } else {
         bin_pass<0, M2DP_PQ, false>(S, R, v, 0, -1, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
         __syncthreads();
         replay_queue<false>(S, R, v, v, iscale);
         __syncthreads();
-        finish_variant<false>(S, 0, ave, unscale, rows + (size_t)var * 2 * M2DP_SIG);
+        finish_variants<false>(S, 1, ave, unscale, rows + (size_t)var * 2 * M2DP_SIG, nullptr);
       }
     };
-    if (variants && exact && mirror_ok) {
-      // ---- variant pairs (a, a + 2): rows of planes 16..63 of variant a + 2 are mirrored copies of variant a's
+    if (variants && exact && (mirror_ok & 1)) {
+      // ---- variant pairs (a, a + 2): rows of planes 16..63 of variant a + 2 are mirrored copies of variant a's.
+      // Across the pairs, the p = 0 rows of variants 1 and 3 are mirrored copies of those of variants 0 and 2: they
+      // travel through the stash (evaluations inside the guard band are replayed for each variant on its own).
+      bool seeded = false;   // (uniform) the stash holds the p = 0 rows of the second pair
       for (int a = 0; a < 2; a++) {
         for (int b = threadIdx.x; b < 2 * HB; b += M2_THREADS) {
           (&S.cnt[0][0])[b] = 0u;
@@ -714,10 +817,22 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
         if (threadIdx.x == 0) {
           S.qn = 0;
           S.ibc[3] = 0;
+          if (a == 0) S.ibc[1] = 0;
         }
         __syncthreads();
-        bin_pass<0, M2DP_PQ, true>(S, R, a, 0, a + 2, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
+        if (a == 1 && seeded) {
+          for (int b = threadIdx.x; b < 2 * P0_BINS; b += M2_THREADS) {   // (L1 may hold lines of an earlier scan)
+            const int slot = b / P0_BINS, r = b % P0_BINS;
+            S.cnt[slot][r] = __ldcg(stash + b);
+            S.isum[slot][r] = (int)__ldcg(stash + 2 * P0_BINS + b);
+          }
+          bin_pass<M2DP_NUM_Q, M2DP_PQ, true>(S, R, a, 0, a + 2, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
+        } else {
+          bin_pass<0, M2DP_PQ, true>(S, R, a, 0, a + 2, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg,
+                                     a == 0 && stash ? 64.0f : 128.0f);
+        }
         __syncthreads();
+        M2_PROF(1);
         if (S.ibc[3]) {   // (uniform) more guard-band evaluations than the queue holds
           __syncthreads();
           single_variant(a);
@@ -734,19 +849,40 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
           S.isum[1][pq2 * M2DP_SR + mirror_sr(sr)] = S.isum[0][pq * M2DP_SR + sr];
         }
         __syncthreads();
-        // the planes of variant a + 2 that have no twin (p = 0) and its degenerate planes (sign rule of its own)
-        bin_pass<0, M2DP_NUM_Q, true>(S, R, a + 2, 1, -1, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
+        M2_PROF(2);
+        // the planes of variant a + 2 that have no twin in this pair (p = 0; seeded: none) and its degenerate planes
+        // (sign rule of its own)
+        if (a == 1 && seeded)
+          bin_pass<0, 0, true>(S, R, a + 2, 1, -1, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
+        else
+          bin_pass<0, M2DP_NUM_Q, true>(S, R, a + 2, 1, -1, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg,
+                                        a == 0 && stash ? 64.0f : 128.0f);
         __syncthreads();
-        replay_queue<true>(S, R, a, a + 2, iscale);
+        M2_PROF(3);
+        unsigned *seed = nullptr;
+        if (a == 0 && stash && !S.ibc[1]) {   // (uniform) p = 0 rows of variants 0 / 2 -> variants 1 / 3
+          for (int b = threadIdx.x; b < 2 * P0_BINS; b += M2_THREADS) {
+            const int slot = b / P0_BINS, r = b % P0_BINS;
+            stash[slot * P0_BINS + mirror15_sr(r)] = S.cnt[slot][r];
+            stash[2 * P0_BINS + slot * P0_BINS + mirror15_sr(r)] = (unsigned)S.isum[slot][r];
+          }
+          seed = stash;
+          seeded = true;
+          __syncthreads();
+        }
+        replay_queue<true>(S, R, a, a + 2, iscale, seed);
         __syncthreads();
-        finish_variant<true>(S, 0, ave, unscale, rows + (size_t)a * 2 * M2DP_SIG);
-        finish_variant<true>(S, 1, ave, unscale, rows + (size_t)(a + 2) * 2 * M2DP_SIG);
+        M2_PROF(4);
+        finish_variants<true>(S, 2, ave, unscale, rows + (size_t)a * 2 * M2DP_SIG, rows + (size_t)(a + 2) * 2 * M2DP_SIG);
       }
     } else {
       for (int var = 0; var < nvar; var++) single_variant(var);
     }
     __syncthreads();
   }
+  if (prof && threadIdx.x == 0)
+    for (int k = 0; k < 16; k++)
+      if (S.prof[k]) atomicAdd(&prof[k], S.prof[k]);
 }
 
 // M2DP::M2DP (M2DP.cpp:4-34) -- float azimuth / elevation and float cos/sin products, like the reference
@@ -776,10 +912,10 @@ void build_tables(double *xproj, double *yproj) {
 
 }  // namespace
 
-size_t m2dp_generate_workspace_bytes(int, bool) { return 256; }
+size_t m2dp_generate_workspace_bytes(int, bool) { return (size_t)STASH_MAX_CTAS * STASH_U32 * sizeof(unsigned); }
 
 cudaError_t launch_m2dp_generate(const double *xyz, const float *inten, const int64_t *off, int nscan,
-                                 double max_rho, bool do_align_and_variants, double *hist, void *, size_t,
+                                 double max_rho, bool do_align_and_variants, double *hist, void *ws, size_t ws_bytes,
                                  int num_sms, cudaStream_t st, int64_t *launches) {
   if (nscan <= 0) return cudaSuccess;
   double xp[3 * M2DP_PQ], yp[3 * M2DP_PQ];
@@ -800,6 +936,7 @@ cudaError_t launch_m2dp_generate(const double *xyz, const float *inten, const in
   const double S_res_inv = M2DP_NUM_S / (2.0 * 3.14159265358979323846);  // M2DP.cpp:32
   const double R_res_inv = M2DP_NUM_R / max_rho;                          // M2DP.cpp:33
   int grid = nscan < num_sms ? nscan : num_sms;
+  if (grid > STASH_MAX_CTAS) grid = STASH_MAX_CTAS;
   unsigned long long degen_mask = 0;   // planes with exactly zero projection vectors (M2DP.cpp:21-25 at p=2, q=0)
   for (int k = 0; k < M2DP_PQ; k++) {
     bool zero = true;
@@ -823,8 +960,31 @@ cudaError_t launch_m2dp_generate(const double *xyz, const float *inten, const in
         if (((degen_mask >> k) & 1ull) != ((degen_mask >> k2) & 1ull)) mirror_ok = 0;
       }
   }
+  // cross-pair sharing: the p = 0 planes of variants v and v ^ 1 (v = 0, 2) see the projected point mirrored,
+  // (xp, yp) -> (xp, -yp), up to the residue of cosf(-pi/2f) = -4.4e-8 in the float table: with eps_tab the largest
+  // deviation of a table entry from the exact mirror image, the fp64 coordinates of variant v ^ 1 differ from the
+  // mirrored ones of variant v by at most 2 * 64 m * eps_tab = 1.1e-5 m for points inside 64 m (the x row has no
+  // deviating x entry).  The fp32 proposal of such a point is good to 1e-5 m and accepted only 6e-5 m or more away from
+  // every bin edge, so an accepted proposal of variant v is also the mirrored bin of variant v ^ 1; everything else is
+  // replayed in fp64 for each variant on its own.
+  if (mirror_ok && ws && ws_bytes >= (size_t)grid * STASH_U32 * sizeof(unsigned)) {
+    double eps_tab = 0.0;
+    for (int v = 0; v < 4; v += 2) {
+      const double s0[3] = {v ? 1.0 : -1.0, -1.0, v ? -1.0 : 1.0};   // variant v:     dx, dy = -1, dx * dy
+      const double s1[3] = {v ? 1.0 : -1.0, 1.0, v ? 1.0 : -1.0};    // variant v ^ 1: dx, dy = +1, dx * dy
+      for (int q = 0; q < M2DP_NUM_Q; q++)
+        for (int c = 0; c < 3; c++) {
+          eps_tab = std::fmax(eps_tab, std::fabs(s1[c] * xp[3 * q + c] - s0[c] * xp[3 * q + c]));
+          eps_tab = std::fmax(eps_tab, std::fabs(s1[c] * yp[3 * q + c] + s0[c] * yp[3 * q + c]));
+        }
+    }
+    bool p0_degen = false;
+    for (int q = 0; q < M2DP_NUM_Q; q++) p0_degen = p0_degen || ((degen_mask >> q) & 1ull);
+    if (eps_tab * 128.0 <= 2e-5 && !p0_degen) mirror_ok |= 2;
+  }
   m2dp_generate_kernel<<<grid, M2_THREADS, sizeof(M2Smem), st>>>(xyz, inten, off, nscan, S_res_inv, R_res_inv,
-                                                                 do_align_and_variants ? 1 : 0, mirror_ok, hist, degen_mask);
+                                                                 do_align_and_variants ? 1 : 0, mirror_ok, hist, degen_mask,
+                                                                 static_cast<unsigned *>(ws), g_debug.prof);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
