@@ -49,9 +49,10 @@ constexpr int HB = M2DP_PQ * M2DP_SR;   // 8192 histogram bins
 constexpr float M2_GUARD_R = 3e-5f;      // ring coordinate guard (see the binning loop)
 constexpr int SVD_WARPS = 4;            // warps in the power iteration
 constexpr int QCAP = 4096;              // deferred (point, plane) evaluations of a pass (8 bytes each, in the T area)
-// the two SVD groups of a CTA: group 0 (count matrix: the integer Gram matrix is the bigger job) and group 1 (binarised
-// matrix) work at the same time on their own workspaces
-constexpr int SVD_G0 = 640, SVD_G1 = M2_THREADS - SVD_G0;
+// the two SVD groups of a CTA work at the same time on their own workspaces: each takes one variant of a pair (count
+// matrix, then binarised matrix), so that both are in the same phase -- the tensor-core squarings of one group do not
+// sit in front of the dependent fp64 chains of the other's power iteration
+constexpr int SVD_G0 = 512, SVD_G1 = M2_THREADS - SVD_G0;
 constexpr int WS = M2DP_PQ * M2DP_PQ;   // doubles in a 64 x 64 workspace
 constexpr float TAN22 = 0.41421356237f;
 // cross-pair stash (global memory, per CTA): the p = 0 rows of variants 1 and 3, derived from those of variants 0 and 2
@@ -74,8 +75,8 @@ struct M2Smem {
                                 // (SVD group 1 takes its two workspaces from the isum area, free once binarised)
   unsigned bits[2][M2DP_PQ * 4];   // the binarised intensity matrices of the two slots: 128-bit row masks
   double scratch[11 * 32];
-  // per SVD group: power iteration state (two parities: unnormalised iterate, partial squared norms, partial squared
-  // updates), the result vectors, the Gram scale
+  // per SVD group: power iteration state, the result vectors, the Gram scale
+  // per SVD group, two parities: the unnormalised iterate, partial squared norms, partial squared updates
   double ubuf[2][2][M2DP_PQ], nrm[2][2][SVD_WARPS], upd[2][2][SVD_WARPS];
   double uvec[2][M2DP_PQ], yv[2][M2DP_SR], red[2][SVD_WARPS], sig[2];
   double bc[16];
@@ -300,10 +301,70 @@ __device__ __forceinline__ void sym_square64(const double *X, double *Y, int gwa
   }
 }
 
-// dominant singular pair of a 64 x 128 matrix, by the threads of SVD group g (named barriers; the two groups of a
-// CTA work on the count matrix and on the binarised intensity matrix of a variant at the same time).  A: the count
-// matrix (u32), or for BINARY the 128-bit row masks.  G / T: the group's 64 x 64 fp64 workspaces.
-// Writes [u (64), v (128)] to out.
+// Gram matrix G = A A^T of a 64 x 128 count matrix, exact in 64-bit integers: the 528 2 x 2 blocks (bi, bj <= bi) of the
+// lower block triangle.  A job is one block (NSPLIT = 1) or one block restricted to the k-steps of one lane
+// (leftover jobs, spread over a warp and reduced by shuffles).  Lane l walks k in 16-byte steps starting at step l, so
+// the 8 lanes of a quarter-warp always hit 8 different 16-byte bank groups whatever rows they read (rows are 512 B
+// apart); integer sums do not care about the order.
+__device__ __forceinline__ void gram_block(const unsigned *A, double *G, int blk, int lane, bool whole) {
+  int bi = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);
+  while ((bi + 1) * (bi + 2) / 2 <= blk) bi++;
+  while (bi * (bi + 1) / 2 > blk) bi--;
+  const int bj = blk - bi * (bi + 1) / 2;
+  const uint4 *r0 = reinterpret_cast<const uint4 *>(A + (2 * bi) * M2DP_SR);
+  const uint4 *r1 = reinterpret_cast<const uint4 *>(A + (2 * bi + 1) * M2DP_SR);
+  const uint4 *c0 = reinterpret_cast<const uint4 *>(A + (2 * bj) * M2DP_SR);
+  const uint4 *c1 = reinterpret_cast<const uint4 *>(A + (2 * bj + 1) * M2DP_SR);
+  unsigned long long g00 = 0, g01 = 0, g10 = 0, g11 = 0;
+  const int steps = whole ? M2DP_SR / 4 : 1;   // whole: every k-step; otherwise the lane's own step, summed over the warp
+#pragma unroll 4
+  for (int t = 0; t < steps; t++) {
+    const int k4 = (t + lane) & (M2DP_SR / 4 - 1);
+    const uint4 a0 = r0[k4], a1 = r1[k4], b0 = c0[k4], b1 = c1[k4];
+    g00 += (unsigned long long)a0.x * b0.x + (unsigned long long)a0.y * b0.y + (unsigned long long)a0.z * b0.z +
+           (unsigned long long)a0.w * b0.w;
+    g01 += (unsigned long long)a0.x * b1.x + (unsigned long long)a0.y * b1.y + (unsigned long long)a0.z * b1.z +
+           (unsigned long long)a0.w * b1.w;
+    g10 += (unsigned long long)a1.x * b0.x + (unsigned long long)a1.y * b0.y + (unsigned long long)a1.z * b0.z +
+           (unsigned long long)a1.w * b0.w;
+    g11 += (unsigned long long)a1.x * b1.x + (unsigned long long)a1.y * b1.y + (unsigned long long)a1.z * b1.z +
+           (unsigned long long)a1.w * b1.w;
+  }
+  if (!whole) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      g00 += __shfl_xor_sync(0xffffffffu, g00, o);
+      g01 += __shfl_xor_sync(0xffffffffu, g01, o);
+      g10 += __shfl_xor_sync(0xffffffffu, g10, o);
+      g11 += __shfl_xor_sync(0xffffffffu, g11, o);
+    }
+    if (lane != 0) return;
+  }
+  const int i0 = 2 * bi, j0 = 2 * bj;
+  G[gi(i0, j0)] = (double)g00;
+  G[gi(j0, i0)] = (double)g00;
+  G[gi(i0, j0 + 1)] = (double)g01;
+  G[gi(j0 + 1, i0)] = (double)g01;
+  G[gi(i0 + 1, j0)] = (double)g10;
+  G[gi(j0, i0 + 1)] = (double)g10;
+  G[gi(i0 + 1, j0 + 1)] = (double)g11;
+  G[gi(j0 + 1, i0 + 1)] = (double)g11;
+}
+
+// the Gram matrices of nmat (1 or 2) count matrices by all threads of the CTA: one block per thread, the 32 blocks
+// that are left over when nmat = 2 (1056 jobs, 1024 threads) one per warp
+constexpr int GRAM_BLOCKS = 528;
+__device__ __forceinline__ void gram_counts_cta(const unsigned *A0, double *G0, const unsigned *A1, double *G1, int nmat) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int njobs = nmat * GRAM_BLOCKS;
+  if (tid < njobs) gram_block(tid < GRAM_BLOCKS ? A0 : A1, tid < GRAM_BLOCKS ? G0 : G1, tid % GRAM_BLOCKS, lane, true);
+  const int left = M2_THREADS + warp;   // (warp-uniform)
+  if (left < njobs) gram_block(A1, G1, left - GRAM_BLOCKS, lane, false);
+}
+
+// dominant singular pair of a 64 x 128 matrix, by the threads of SVD group g (named barriers).  A: the count matrix
+// (u32; its Gram matrix is already in G, gram_counts_cta), or for BINARY the 128-bit row masks.  G / T: the group's
+// 64 x 64 fp64 workspaces.  Writes [u (64), v (128)] to out.
 //   G = A A^T exactly (64-bit integers), scaled by a power of two to trace ~ 1;  G^16 by four squarings;
 //   power iteration with G^16 from the all-ones vector (Perron pair: entrywise non-negative);
 //   sigma = |A^T u|, v = A^T u / sigma.
@@ -319,45 +380,8 @@ __device__ void dominant_pair(const unsigned *A, double *G, double *T, M2Smem &S
       const uint4 a = reinterpret_cast<const uint4 *>(A)[i], b = reinterpret_cast<const uint4 *>(A)[j];
       G[gi(i, j)] = (double)(__popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w));
     }
-  } else {
-    // ---- Gram matrix: the 528 2 x 2 blocks (bi, bj <= bi) of the lower block triangle, one per thread.  Lane l walks k in 16-byte steps starting at step l, so the 8 lanes of a quarter-warp always
-    // hit 8 different 16-byte bank groups whatever rows they read (rows are 512 B apart); integer sums do not care
-    // about the order.
-    for (int blk = tid; blk < 528; blk += gsize) {
-      int bi = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);
-      while ((bi + 1) * (bi + 2) / 2 <= blk) bi++;
-      while (bi * (bi + 1) / 2 > blk) bi--;
-      const int bj = blk - bi * (bi + 1) / 2;
-      const uint4 *r0 = reinterpret_cast<const uint4 *>(A + (2 * bi) * M2DP_SR);
-      const uint4 *r1 = reinterpret_cast<const uint4 *>(A + (2 * bi + 1) * M2DP_SR);
-      const uint4 *c0 = reinterpret_cast<const uint4 *>(A + (2 * bj) * M2DP_SR);
-      const uint4 *c1 = reinterpret_cast<const uint4 *>(A + (2 * bj + 1) * M2DP_SR);
-      unsigned long long g00 = 0, g01 = 0, g10 = 0, g11 = 0;
-#pragma unroll 4
-      for (int t = 0; t < M2DP_SR / 4; t++) {
-        const int k4 = (t + lane) & (M2DP_SR / 4 - 1);
-        const uint4 a0 = r0[k4], a1 = r1[k4], b0 = c0[k4], b1 = c1[k4];
-        g00 += (unsigned long long)a0.x * b0.x + (unsigned long long)a0.y * b0.y + (unsigned long long)a0.z * b0.z +
-               (unsigned long long)a0.w * b0.w;
-        g01 += (unsigned long long)a0.x * b1.x + (unsigned long long)a0.y * b1.y + (unsigned long long)a0.z * b1.z +
-               (unsigned long long)a0.w * b1.w;
-        g10 += (unsigned long long)a1.x * b0.x + (unsigned long long)a1.y * b0.y + (unsigned long long)a1.z * b0.z +
-               (unsigned long long)a1.w * b0.w;
-        g11 += (unsigned long long)a1.x * b1.x + (unsigned long long)a1.y * b1.y + (unsigned long long)a1.z * b1.z +
-               (unsigned long long)a1.w * b1.w;
-      }
-      const int i0 = 2 * bi, j0 = 2 * bj;
-      G[gi(i0, j0)] = (double)g00;
-      G[gi(j0, i0)] = (double)g00;
-      G[gi(i0, j0 + 1)] = (double)g01;
-      G[gi(j0 + 1, i0)] = (double)g01;
-      G[gi(i0 + 1, j0)] = (double)g10;
-      G[gi(j0, i0 + 1)] = (double)g10;
-      G[gi(i0 + 1, j0 + 1)] = (double)g11;
-      G[gi(j0 + 1, i0 + 1)] = (double)g11;
-    }
+    group_sync(g);
   }
-  group_sync(g);
   if (g == 0) M2_PROF(6);
   // ---- scale to trace in [1, 2) (exact, power of two), so that G^16 neither overflows nor underflows
   if (warp == 0) {
@@ -384,12 +408,18 @@ __device__ void dominant_pair(const unsigned *A, double *G, double *T, M2Smem &S
     S.nrm[g][0][tid] = 1.0 / SVD_WARPS;
     S.upd[g][0][tid] = 1.0;
   }
-  group_sync(g);
+  // CTA-wide (both groups call dominant_pair the same number of times): the two groups stay in the same phase, the
+  // DMMA bursts of one do not sit in front of the dependent fp64 chains of the other's power iteration
+  __syncthreads();
   if (g == 0) M2_PROF(7);
-  // ---- power iteration with G^16: SVD_WARPS warps, 2 threads per row, ONE named barrier per iteration.  The iterate
-  // is kept unnormalised (w_k, parity k & 1) together with the partial sums of |w_k|^2; the normalisation of step k is
-  // applied by the readers in step k + 1 (u_k = w_k / |w_k|), and the size of the update |u_k - u_{k-1}|^2 is known one
-  // step later still -- the loop runs two steps past convergence, each step is half as long.
+  // ---- power iteration with G^16: SVD_WARPS warps, 2 threads per row, ONE named barrier per step.  The iterate is kept
+  // unnormalised (w_k, parity k & 1) together with the partial sums of |w_k|^2; the normalisation of step k is applied
+  // by the readers in step k + 1 (u_k = w_k / |w_k|), and the size of the update |u_k - u_{k-1}|^2 is known one step
+  // later still -- the loop runs two steps past convergence, each step is shorter.  A step is one long chain of
+  // dependent instructions (~2.4k clocks): tried and not faster, 8 threads per row on all 16 warps with per-warp partial
+  // sums (3.9k: the SM-wide shared-memory and fp64 pipes pay for the redundant sums) and the same with G^16 held in
+  // registers, the norm from each row group's own copy of w and the convergence test folded into the barrier
+  // (bar.red.or; 2.8k).
   if (warp < SVD_WARPS) {
     const int t = warp * 32 + lane;          // 0..127
     const int row = t >> 1, half = t & 1;
@@ -410,7 +440,7 @@ __device__ void dominant_pair(const unsigned *A, double *G, double *T, M2Smem &S
         break;
       }
       // 1 / sqrt(nn): fp32 seed + three Newton steps (rel. error 1e-7 -> 1e-14 -> 1e-28 -> rounding), instead of the
-      // fp64 square root and division routines; independent of the matrix-vector product below
+      // fp64 square root and division routines
       double inv = (double)rsqrtf((float)nn);
       {
         const double hn = 0.5 * nn;
@@ -444,14 +474,14 @@ __device__ void dominant_pair(const unsigned *A, double *G, double *T, M2Smem &S
       }
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");
     }
-    if (S.prof_on && t == 0) atomicAdd(&S.prof[11 + g], (unsigned long long)iter);   // iterations per group
+    if (S.prof_on && t == 0) atomicAdd(&S.prof[11 + g], (unsigned long long)iter);   // steps per group
   }
-  group_sync(g);
+  __syncthreads();   // (see above)
   if (g == 0) M2_PROF(8);
   // ---- y = A^T u (128), sigma = |y|: NP threads per column (64 / NP rows each), partial sums through the T area
   {
-    constexpr int NP = BINARY ? 2 : 4;
-    static_assert(NP * M2DP_SR <= (BINARY ? SVD_G1 : SVD_G0), "threads of the group");
+    constexpr int NP = 4;
+    static_assert(NP * M2DP_SR <= SVD_G0 && NP * M2DP_SR <= SVD_G1, "threads of a group");
     if (tid < NP * M2DP_SR) {
       const int col = tid & (M2DP_SR - 1), part = tid >> 7;
       double acc = 0.0;
@@ -662,13 +692,19 @@ __device__ __forceinline__ void finish_variants(M2Smem &S, int nslot, float ave,
   __syncthreads();   // the isum area is free from here on: SVD group 1's workspaces
   M2_PROF(5);
   const int g = threadIdx.x >= SVD_G0 ? 1 : 0;
-  double *G1 = reinterpret_cast<double *>(&S.isum[0][0]);
-  for (int slot = 0; slot < nslot; slot++) {
-    double *row = slot ? row1 : row0;
-    if (g == 0)
-      dominant_pair<false>(S.cnt[slot], S.G, S.T, S, 0, row);                 // M2DP.cpp:94-98,107
-    else
-      dominant_pair<true>(S.bits[slot], G1, G1 + WS, S, 1, row + M2DP_SIG);   // M2DP.cpp:100-108
+  double *G1 = reinterpret_cast<double *>(&S.isum[0][0]), *T1 = G1 + WS;
+  gram_counts_cta(S.cnt[0], S.G, S.cnt[1], G1, nslot);
+  __syncthreads();
+  M2_PROF(6);
+  if (nslot == 2) {
+    // group g: variant of slot g, count matrix then binarised matrix (M2DP.cpp:94-98,107 and 100-108)
+    double *row = g ? row1 : row0, *Gg = g ? G1 : S.G, *Tg = g ? T1 : S.T;
+    dominant_pair<false>(S.cnt[g], Gg, Tg, S, g, row);
+    dominant_pair<true>(S.bits[g], Gg, Tg, S, g, row + M2DP_SIG);
+  } else if (g == 0) {
+    dominant_pair<false>(S.cnt[0], S.G, S.T, S, 0, row0);
+  } else {
+    dominant_pair<true>(S.bits[0], G1, T1, S, 1, row0 + M2DP_SIG);
   }
   __syncthreads();
 }

@@ -24,4 +24,4 @@ tot = sum(v[:11])
 for k in sorted(names):
     print("%-18s %6.2f %%  %8.0f clk/scan" % (names[k], 100.0 * v[k] / tot, v[k] / n))
 print("total clk/scan", tot / n)
-print("power iterations per SVD: count %.1f, binary %.1f" % (v[11] / (4.0 * n), v[12] / (4.0 * n)))
+print("power iterations per SVD: group 0 %.1f, group 1 %.1f" % (v[11] / (4.0 * n), v[12] / (4.0 * n)))
