@@ -306,6 +306,9 @@ __device__ __forceinline__ void sym_square64(const double *X, double *Y, int gwa
 // (leftover jobs, spread over a warp and reduced by shuffles).  Lane l walks k in 16-byte steps starting at step l, so
 // the 8 lanes of a quarter-warp always hit 8 different 16-byte bank groups whatever rows they read (rows are 512 B
 // apart); integer sums do not care about the order.
+// ACC = unsigned when the scan has fewer than 65536 points (every entry of G is at most n * max count <= n^2 < 2^32:
+// full-rate 32-bit multiply-adds), unsigned long long otherwise.
+template <typename ACC>
 __device__ __forceinline__ void gram_block(const unsigned *A, double *G, int blk, int lane, bool whole) {
   int bi = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);
   while ((bi + 1) * (bi + 2) / 2 <= blk) bi++;
@@ -315,20 +318,16 @@ __device__ __forceinline__ void gram_block(const unsigned *A, double *G, int blk
   const uint4 *r1 = reinterpret_cast<const uint4 *>(A + (2 * bi + 1) * M2DP_SR);
   const uint4 *c0 = reinterpret_cast<const uint4 *>(A + (2 * bj) * M2DP_SR);
   const uint4 *c1 = reinterpret_cast<const uint4 *>(A + (2 * bj + 1) * M2DP_SR);
-  unsigned long long g00 = 0, g01 = 0, g10 = 0, g11 = 0;
+  ACC g00 = 0, g01 = 0, g10 = 0, g11 = 0;
   const int steps = whole ? M2DP_SR / 4 : 1;   // whole: every k-step; otherwise the lane's own step, summed over the warp
 #pragma unroll 4
   for (int t = 0; t < steps; t++) {
     const int k4 = (t + lane) & (M2DP_SR / 4 - 1);
     const uint4 a0 = r0[k4], a1 = r1[k4], b0 = c0[k4], b1 = c1[k4];
-    g00 += (unsigned long long)a0.x * b0.x + (unsigned long long)a0.y * b0.y + (unsigned long long)a0.z * b0.z +
-           (unsigned long long)a0.w * b0.w;
-    g01 += (unsigned long long)a0.x * b1.x + (unsigned long long)a0.y * b1.y + (unsigned long long)a0.z * b1.z +
-           (unsigned long long)a0.w * b1.w;
-    g10 += (unsigned long long)a1.x * b0.x + (unsigned long long)a1.y * b0.y + (unsigned long long)a1.z * b0.z +
-           (unsigned long long)a1.w * b0.w;
-    g11 += (unsigned long long)a1.x * b1.x + (unsigned long long)a1.y * b1.y + (unsigned long long)a1.z * b1.z +
-           (unsigned long long)a1.w * b1.w;
+    g00 += (ACC)a0.x * b0.x + (ACC)a0.y * b0.y + (ACC)a0.z * b0.z + (ACC)a0.w * b0.w;
+    g01 += (ACC)a0.x * b1.x + (ACC)a0.y * b1.y + (ACC)a0.z * b1.z + (ACC)a0.w * b1.w;
+    g10 += (ACC)a1.x * b0.x + (ACC)a1.y * b0.y + (ACC)a1.z * b0.z + (ACC)a1.w * b0.w;
+    g11 += (ACC)a1.x * b1.x + (ACC)a1.y * b1.y + (ACC)a1.z * b1.z + (ACC)a1.w * b1.w;
   }
   if (!whole) {
 #pragma unroll
@@ -354,12 +353,14 @@ __device__ __forceinline__ void gram_block(const unsigned *A, double *G, int blk
 // the Gram matrices of nmat (1 or 2) count matrices by all threads of the CTA: one block per thread, the 32 blocks
 // that are left over when nmat = 2 (1056 jobs, 1024 threads) one per warp
 constexpr int GRAM_BLOCKS = 528;
+template <typename ACC>
 __device__ __forceinline__ void gram_counts_cta(const unsigned *A0, double *G0, const unsigned *A1, double *G1, int nmat) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int njobs = nmat * GRAM_BLOCKS;
-  if (tid < njobs) gram_block(tid < GRAM_BLOCKS ? A0 : A1, tid < GRAM_BLOCKS ? G0 : G1, tid % GRAM_BLOCKS, lane, true);
+  if (tid < njobs)
+    gram_block<ACC>(tid < GRAM_BLOCKS ? A0 : A1, tid < GRAM_BLOCKS ? G0 : G1, tid % GRAM_BLOCKS, lane, true);
   const int left = M2_THREADS + warp;   // (warp-uniform)
-  if (left < njobs) gram_block(A1, G1, left - GRAM_BLOCKS, lane, false);
+  if (left < njobs) gram_block<ACC>(A1, G1, left - GRAM_BLOCKS, lane, false);
 }
 
 // dominant singular pair of a 64 x 128 matrix, by the threads of SVD group g (named barriers).  A: the count matrix
@@ -669,7 +670,7 @@ __device__ __forceinline__ void replay_queue(M2Smem &S, const ScanRef &R, int va
 // binarise the slots [slot0, slot0 + nslot) (M2DP.cpp:84-91) into 128-bit row masks, then per slot the two dominant
 // pairs -- count matrix on SVD group 0, binarised matrix on group 1, at the same time -- -> output rows of 2 x 192
 template <bool EXACT>
-__device__ __forceinline__ void finish_variants(M2Smem &S, int nslot, float ave, double unscale, double *row0,
+__device__ __forceinline__ void finish_variants(M2Smem &S, int nslot, int n, float ave, double unscale, double *row0,
                                                 double *row1) {
   const int lane = threadIdx.x & 31;
   const double *hsum = reinterpret_cast<const double *>(S.isum);
@@ -682,8 +683,13 @@ __device__ __forceinline__ void finish_variants(M2Smem &S, int nslot, float ave,
       const unsigned c = hcnt[b];
       bool v = false;
       if (c) {
-        const double sum = EXACT ? (double)hisum[b] * unscale : hsum[b];
-        v = (sum / (double)c) > (double)ave;
+        // M2DP.cpp:87-88: (sum / count) > ave.  Exact mode: sum and ave * count are exact in fp64 (integers in units of
+        // 2^emin resp. of ulp(ave); count < 2^29), and a quotient that differs from ave at all differs by more than
+        // ulp(ave) / count >> 2^-53 ave, so the rounded quotient compares like the exact one: no division.
+        if (EXACT && c < (1u << 29))
+          v = (double)hisum[b] * unscale > (double)ave * (double)c;
+        else
+          v = ((EXACT ? (double)hisum[b] * unscale : hsum[b]) / (double)c) > (double)ave;
       }
       const unsigned word = __ballot_sync(0xffffffffu, v);
       if (lane == 0) S.bits[slot][b >> 5] = word;
@@ -693,7 +699,10 @@ __device__ __forceinline__ void finish_variants(M2Smem &S, int nslot, float ave,
   M2_PROF(5);
   const int g = threadIdx.x >= SVD_G0 ? 1 : 0;
   double *G1 = reinterpret_cast<double *>(&S.isum[0][0]), *T1 = G1 + WS;
-  gram_counts_cta(S.cnt[0], S.G, S.cnt[1], G1, nslot);
+  if (n < 65536)
+    gram_counts_cta<unsigned>(S.cnt[0], S.G, S.cnt[1], G1, nslot);
+  else
+    gram_counts_cta<unsigned long long>(S.cnt[0], S.G, S.cnt[1], G1, nslot);
   __syncthreads();
   M2_PROF(6);
   if (nslot == 2) {
@@ -831,13 +840,13 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
         __syncthreads();
         replay_queue<true>(S, R, v, v, iscale);
         __syncthreads();
-        finish_variants<true>(S, 1, ave, unscale, rows + (size_t)var * 2 * M2DP_SIG, nullptr);
+        finish_variants<true>(S, 1, n, ave, unscale, rows + (size_t)var * 2 * M2DP_SIG, nullptr);
       } else {
         bin_pass<0, M2DP_PQ, false>(S, R, v, 0, -1, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
         __syncthreads();
         replay_queue<false>(S, R, v, v, iscale);
         __syncthreads();
-        finish_variants<false>(S, 1, ave, unscale, rows + (size_t)var * 2 * M2DP_SIG, nullptr);
+        finish_variants<false>(S, 1, n, ave, unscale, rows + (size_t)var * 2 * M2DP_SIG, nullptr);
       }
     };
     if (variants && exact && (mirror_ok & 1)) {
@@ -909,7 +918,7 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
         replay_queue<true>(S, R, a, a + 2, iscale, seed);
         __syncthreads();
         M2_PROF(4);
-        finish_variants<true>(S, 2, ave, unscale, rows + (size_t)a * 2 * M2DP_SIG, rows + (size_t)(a + 2) * 2 * M2DP_SIG);
+        finish_variants<true>(S, 2, n, ave, unscale, rows + (size_t)a * 2 * M2DP_SIG, rows + (size_t)(a + 2) * 2 * M2DP_SIG);
       }
     } else {
       for (int var = 0; var < nvar; var++) single_variant(var);
