@@ -264,40 +264,59 @@ __device__ __forceinline__ int propose_bin(float xp, float yp, float R_f, float 
 }
 
 // Y = X X for a symmetric 64 x 64 fp64 matrix (swizzled, gi()) on the fp64 tensor cores (mma.sync.m8n8k4.f64: 256
-// multiply-adds per warp instruction instead of 32), by the 16 warps of one SVD group.  The B fragment X[k][j] is read
+// multiply-adds per warp instruction instead of 32), by the warps of one SVD group.  The B fragment X[k][j] is read
 // as X[j][k] (symmetry), so both operands are 8 x 4 row reads.  Fragments (PTX ISA, m8n8k4 .f64):
 // A[lane / 4][lane % 4], B[lane % 4][lane / 4], C[lane / 4][2 (lane % 4) + {0, 1}].
+// Y is symmetric too: only the 36 tiles (I, J <= I) of the 8 x 8 tile grid are computed, the others are mirrored.  A
+// warp takes a run of up to three tiles of one tile row, which share the A fragment: 15 runs, 51 fragment loads per 36
+// DMMAs instead of 72 (a squaring pair costs as many shared-memory wavefronts as tensor clocks: 8.1k -> 6.7k clocks).
+// (2 x 2 tile blocks need fewer loads still, 44, but leave 14 warps with a 64-DMMA chain: 7.2k.)
+__constant__ unsigned char c_sq_runs[15][3] = {   // (I, first J, tiles)
+    {7, 0, 3}, {7, 3, 3}, {6, 0, 3}, {5, 0, 3}, {5, 3, 3}, {4, 0, 3}, {2, 0, 3}, {7, 6, 2},
+    {6, 3, 2}, {6, 5, 2}, {4, 3, 2}, {3, 0, 2}, {3, 2, 2}, {1, 0, 2}, {0, 0, 1}};
+
+template <int N>
+__device__ __forceinline__ void sq_run(const double *X, double *Y, int I, int J0, int r, int c) {
+  const int i0 = I * 8;
+  // rows i0 + r and 8 J + r have (row & 7) == r: the swizzle of column k0 + c is ((k0 >> 2) ^ r) << 2 | c
+  const double *pa = X + (i0 + r) * M2DP_PQ + c, *pb = X + (J0 * 8 + r) * M2DP_PQ + c;
+  double acc[N][2];
+#pragma unroll
+  for (int t = 0; t < N; t++) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll 4
+  for (int k0 = 0; k0 < M2DP_PQ; k0 += 4) {
+    const int o = ((k0 >> 2) ^ r) << 2;
+    const double a = pa[o];
+#pragma unroll
+    for (int t = 0; t < N; t++) {
+      const double b = pb[t * 8 * M2DP_PQ + o];
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                   : "+d"(acc[t][0]), "+d"(acc[t][1])
+                   : "d"(a), "d"(b));
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < N; t++) {
+    const int J = J0 + t, j0 = J * 8;
+    *reinterpret_cast<double2 *>(Y + gi(i0 + r, j0 + 2 * c)) = make_double2(acc[t][0], acc[t][1]);
+    if (I != J) {
+      Y[gi(j0 + 2 * c, i0 + r)] = acc[t][0];
+      Y[gi(j0 + 2 * c + 1, i0 + r)] = acc[t][1];
+    }
+  }
+}
+
 __device__ __forceinline__ void sym_square64(const double *X, double *Y, int gwarp, int gwarps) {
   const int lane = threadIdx.x & 31;
   const int r = lane >> 2, c = lane & 3;
-  // Y is symmetric too: only the 36 tiles (I, J <= I) of the 8 x 8 tile grid are computed, the others are mirrored.
-  // Tile t = I (I + 1) / 2 + J; warp w of the group takes tiles w, w + gwarps, ...
-  for (int t = gwarp; t < 36; t += gwarps) {
-    int I = 0;
-    while ((I + 1) * (I + 2) / 2 <= t) I++;
-    const int J = t - I * (I + 1) / 2;
-    const int i0 = I * 8, j0 = J * 8;
-    // rows i0 + r and j0 + r have (row & 7) == r: the swizzle of column k0 + c is ((k0 >> 2) ^ r) << 2 | c
-    const double *pa = X + (i0 + r) * M2DP_PQ + c, *pb = X + (j0 + r) * M2DP_PQ + c;
-    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;   // two accumulator pairs: even / odd k steps (shorter chains)
-#pragma unroll 4
-    for (int k0 = 0; k0 < M2DP_PQ; k0 += 8) {
-      const int o0 = ((k0 >> 2) ^ r) << 2, o1 = (((k0 >> 2) + 1) ^ r) << 2;
-      const double a0 = pa[o0], b0 = pb[o0], a1 = pa[o1], b1 = pb[o1];
-      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                   : "+d"(c0), "+d"(c1)
-                   : "d"(a0), "d"(b0));
-      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                   : "+d"(e0), "+d"(e1)
-                   : "d"(a1), "d"(b1));
-    }
-    c0 += e0;
-    c1 += e1;
-    *reinterpret_cast<double2 *>(Y + gi(i0 + r, j0 + 2 * c)) = make_double2(c0, c1);
-    if (I != J) {
-      Y[gi(j0 + 2 * c, i0 + r)] = c0;
-      Y[gi(j0 + 2 * c + 1, i0 + r)] = c1;
-    }
+  for (int u = gwarp; u < 15; u += gwarps) {
+    const int I = c_sq_runs[u][0], J0 = c_sq_runs[u][1], n = c_sq_runs[u][2];   // (warp-uniform)
+    if (n == 3)
+      sq_run<3>(X, Y, I, J0, r, c);
+    else if (n == 2)
+      sq_run<2>(X, Y, I, J0, r, c);
+    else
+      sq_run<1>(X, Y, I, J0, r, c);
   }
 }
 
@@ -361,6 +380,60 @@ __device__ __forceinline__ void gram_counts_cta(const unsigned *A0, double *G0, 
     gram_block<ACC>(tid < GRAM_BLOCKS ? A0 : A1, tid < GRAM_BLOCKS ? G0 : G1, tid % GRAM_BLOCKS, lane, true);
   const int left = M2_THREADS + warp;   // (warp-uniform)
   if (left < njobs) gram_block<ACC>(A1, G1, left - GRAM_BLOCKS, lane, false);
+}
+
+// The same for scans of fewer than 65536 points (32-bit sums are exact), with 4 x 4 blocks: the 136 blocks (qi, qj <= qi)
+// of the lower block triangle, each split along k between the two lanes of a pair -- 272 jobs per matrix.  A 4 x 4 block
+// needs 8 row loads per 16 products where the 2 x 2 block needs 4 per 4: the shared-memory wavefronts, which bound
+// this phase, are halved.  Lane skew: the lanes of a quarter-warp read k-steps that differ mod 8 (conflict free).
+__device__ __forceinline__ void gram_counts_cta_small(const unsigned *A0, double *G0, const unsigned *A1, double *G1,
+                                                      int nmat) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid >= nmat * 272) return;   // (whole warps: 272 = 8.5 warps, 544 = 17 warps; partial warp: see the shuffles below)
+  const int khalf = tid & 1, job = tid >> 1, m = job >= 136 ? 1 : 0, blk = job - 136 * m;
+  const unsigned *A = m ? A1 : A0;
+  double *G = m ? G1 : G0;
+  int qi = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);
+  while ((qi + 1) * (qi + 2) / 2 <= blk) qi++;
+  while (qi * (qi + 1) / 2 > blk) qi--;
+  const int qj = blk - qi * (qi + 1) / 2;
+  const uint4 *ra = reinterpret_cast<const uint4 *>(A + (4 * qi) * M2DP_SR);
+  const uint4 *rb = reinterpret_cast<const uint4 *>(A + (4 * qj) * M2DP_SR);
+  unsigned g[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) g[i][j] = 0u;
+  const int skew = (lane >> 1) + 4 * khalf;
+#pragma unroll 2
+  for (int t = 0; t < M2DP_SR / 8; t++) {   // the 16 k-steps (of 4 columns) of this half
+    const int k4 = khalf * (M2DP_SR / 8) + ((t + skew) & (M2DP_SR / 8 - 1));
+    uint4 a[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) a[i] = ra[i * (M2DP_SR / 4) + k4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint4 b = rb[j * (M2DP_SR / 4) + k4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) g[i][j] += a[i].x * b.x + a[i].y * b.y + a[i].z * b.z + a[i].w * b.w;
+    }
+  }
+  // the two halves of k; then lane 0 of the pair stores the block, lane 1 its transpose
+  const unsigned pair_mask = 3u << (lane & ~1);
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) g[i][j] += __shfl_xor_sync(pair_mask, g[i][j], 1);
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int gi_ = 4 * qi + i, gj_ = 4 * qj + j;
+      if (khalf == 0)
+        G[gi(gi_, gj_)] = (double)g[i][j];
+      else
+        G[gi(gj_, gi_)] = (double)g[i][j];
+    }
 }
 
 // dominant singular pair of a 64 x 128 matrix, by the threads of SVD group g (named barriers).  A: the count matrix
@@ -629,7 +702,7 @@ __device__ __forceinline__ void bin_block(M2Smem &S, const ScanRef &R, int var, 
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const int idx = idx4[u];
-        if (idx >= 0) {
+        if (idx >= 0) {   // (branch-free updates that add 0 to a dump bin were tried: 1 % slower)
           atomicAdd(&hcnt[idx], 1u);
           if (EXACT)
             atomicAdd(&hisum[idx], iv);  // exact integer multiple of 2^emin, |sum| < 2^24
@@ -700,7 +773,7 @@ __device__ __forceinline__ void finish_variants(M2Smem &S, int nslot, int n, flo
   const int g = threadIdx.x >= SVD_G0 ? 1 : 0;
   double *G1 = reinterpret_cast<double *>(&S.isum[0][0]), *T1 = G1 + WS;
   if (n < 65536)
-    gram_counts_cta<unsigned>(S.cnt[0], S.G, S.cnt[1], G1, nslot);
+    gram_counts_cta_small(S.cnt[0], S.G, S.cnt[1], G1, nslot);
   else
     gram_counts_cta<unsigned long long>(S.cnt[0], S.G, S.cnt[1], G1, nslot);
   __syncthreads();
