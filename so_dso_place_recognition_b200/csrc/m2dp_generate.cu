@@ -76,8 +76,8 @@ struct M2Smem {
   unsigned bits[2][M2DP_PQ * 4];   // the binarised intensity matrices of the two slots: 128-bit row masks
   double scratch[11 * 32];
   // per SVD group: power iteration state, the result vectors, the Gram scale
-  // per SVD group, two parities: the unnormalised iterate, partial squared norms, partial squared updates
-  double ubuf[2][2][M2DP_PQ], nrm[2][2][SVD_WARPS], upd[2][2][SVD_WARPS];
+  // per SVD group, two parities: the unnormalised iterate, partial squared norms
+  double ubuf[2][2][M2DP_PQ], nrm[2][2][SVD_WARPS];
   double uvec[2][M2DP_PQ], yv[2][M2DP_SR], red[2][SVD_WARPS], sig[2];
   double bc[16];
   int ibc[4];
@@ -478,22 +478,18 @@ __device__ void dominant_pair(const unsigned *A, double *G, double *T, M2Smem &S
   group_sync(g);
   sym_square64(T, G, warp, gwarps);   // G^16
   if (tid < M2DP_PQ) S.ubuf[g][0][tid] = 0.125;  // all-ones / |.| (Perron start)
-  if (tid < SVD_WARPS) {
-    S.nrm[g][0][tid] = 1.0 / SVD_WARPS;
-    S.upd[g][0][tid] = 1.0;
-  }
+  if (tid < SVD_WARPS) S.nrm[g][0][tid] = 1.0 / SVD_WARPS;
   // CTA-wide (both groups call dominant_pair the same number of times): the two groups stay in the same phase, the
   // DMMA bursts of one do not sit in front of the dependent fp64 chains of the other's power iteration
   __syncthreads();
   if (g == 0) M2_PROF(7);
   // ---- power iteration with G^16: SVD_WARPS warps, 2 threads per row, ONE named barrier per step.  The iterate is kept
   // unnormalised (w_k, parity k & 1) together with the partial sums of |w_k|^2; the normalisation of step k is applied
-  // by the readers in step k + 1 (u_k = w_k / |w_k|), and the size of the update |u_k - u_{k-1}|^2 is known one step
-  // later still -- the loop runs two steps past convergence, each step is shorter.  A step is one long chain of
-  // dependent instructions (~2.4k clocks): tried and not faster, 8 threads per row on all 16 warps with per-warp partial
-  // sums (3.9k: the SM-wide shared-memory and fp64 pipes pay for the redundant sums) and the same with G^16 held in
-  // registers, the norm from each row group's own copy of w and the convergence test folded into the barrier
-  // (bar.red.or; 2.8k).
+  // by the readers in step k + 1 (u_k = w_k / |w_k|).  The barrier also ORs "my row of u moved by more than 2e-15 in
+  // this step" (bar.red): all quiet = converged, u_k is the result (w_{k+1} has been computed for nothing).
+  // A step is one long chain of dependent instructions (~2.4k clocks): tried and not faster, 8 threads per row on all
+  // 16 warps with per-warp partial sums (3.9k: the SM-wide shared-memory and fp64 pipes pay for the redundant sums)
+  // and the same with G^16 held in registers and the norm from each row group's own copy of w (2.8k).
   if (warp < SVD_WARPS) {
     const int t = warp * 32 + lane;          // 0..127
     const int row = t >> 1, half = t & 1;
@@ -503,12 +499,9 @@ __device__ void dominant_pair(const unsigned *A, double *G, double *T, M2Smem &S
     for (; iter < 4000; iter++) {
       const int p = iter & 1;
       const double *w = S.ubuf[g][p];
-      double nn = 0.0, dd = 0.0;
+      double nn = 0.0;
 #pragma unroll
-      for (int k = 0; k < SVD_WARPS; k++) {
-        nn += S.nrm[g][p][k];
-        dd += S.upd[g][p][k];
-      }
+      for (int k = 0; k < SVD_WARPS; k++) nn += S.nrm[g][p][k];
       if (nn == 0.0) {   // zero matrix (uniform over the group)
         if (half == 0) uvec[row] = 0.0;
         break;
@@ -523,10 +516,6 @@ __device__ void dominant_pair(const unsigned *A, double *G, double *T, M2Smem &S
         inv = inv * fma(-hn * inv, inv, 1.5);
       }
       const double u_cur = w[row] * inv;     // u_k[row]
-      if (dd < 1e-29) {                      // |u_{k-1} - u_{k-2}|^2: converged (uniform over the group)
-        if (half == 0) uvec[row] = u_cur;
-        break;
-      }
       double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll 8
       for (int k = 0; k < 32; k += 2) {
@@ -537,16 +526,22 @@ __device__ void dominant_pair(const unsigned *A, double *G, double *T, M2Smem &S
       double acc = acc0 + acc1;
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc *= inv;                            // w_{k+1} = G^16 u_k
-      const double d = u_cur - u_prev;
+      const unsigned moved = iter == 0 || fabs(u_cur - u_prev) > 2e-15 ? 1u : 0u;
       u_prev = u_cur;
       const double sq = warp_sum(half == 0 ? acc * acc : 0.0);
-      const double d2 = warp_sum(half == 0 ? d * d : 0.0);
       if (half == 0) S.ubuf[g][p ^ 1][row] = acc;
-      if (lane == 0) {
-        S.nrm[g][p ^ 1][warp] = sq;
-        S.upd[g][p ^ 1][warp] = iter == 0 ? 1.0 : d2;
+      if (lane == 0) S.nrm[g][p ^ 1][warp] = sq;
+      unsigned any_moved;
+      asm volatile(
+          "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(any_moved)
+          : "r"(moved), "r"(bar_id), "r"(bar_n)
+          : "memory");
+      if (!any_moved) {                      // |u_k - u_{k-1}| <= 2e-15 in every row
+        if (half == 0) uvec[row] = u_cur;
+        iter++;
+        break;
       }
-      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");
     }
     if (S.prof_on && t == 0) atomicAdd(&S.prof[11 + g], (unsigned long long)iter);   // steps per group
   }
