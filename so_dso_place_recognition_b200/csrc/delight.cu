@@ -7,13 +7,13 @@
 //
 // Matching is not a GEMM: per pair min over 4 row permutations of  mean over {a + b > 0} of 2 (a - b)^2 / (a + b).
 // A CTA owns a 16 x 16 tile of pairs (one pair per thread); per histogram row r it stages the 16 query rows r and,
-// for each of the 4 permutations, the 16 DB rows Mut[k][r] in shared memory as fp32 counts (exact below 2^24), with
-// their non-zero masks (8 words per row) and row sums.  The histograms are sparse, and a bin where only one of the two
-// counts is non-zero contributes exactly 2 x that count: per row  sum = 2 (S_a + S_b) - 2 sum_both (a + b)
-// + sum_both 2 (a - b)^2 / (a + b)  with the bins where BOTH are non-zero taken from the AND of the masks (the first two
-// terms are exact integers), and the number of bins with a + b > 0 is the popcount of the OR.  Only the both-non-zero
-// bins (about one in six) cost a reciprocal.  Terms in fp32 per row, row sums in fp64.  HBM traffic is the signatures
-// (16 KB each, L2 resident across tiles).
+// for each of the 4 permutations, the 16 DB rows Mut[k][r] in shared memory as fp32 counts (exact below 2^24) and
+// accumulates the terms in fp32 per row (256 terms), the row sums in fp64.  HBM traffic is the signatures (16 KB
+// each, L2 resident across tiles); the kernel is bound by the ~16 k divide-accumulate terms per pair.
+// Tried (tools/experiments/delight_match_sparse_masks.patch, parity green): only the bins where both counts are non-zero
+// need the reciprocal (one in seven at 37 % density; the others contribute 2 x the non-zero count, in closed form from row
+// sums), found from the AND of 256-bit non-zero masks.  38 ms instead of 32 for 2000 x 2000: the per-lane bit loops
+// diverge and their shared-memory reads hit random banks, where the dense loop broadcasts.
 // Compiled with -fmad=false (generation restates fp64 arithmetic operation by operation, see pca.cuh).
 #include <climits>
 
@@ -99,26 +99,10 @@ delight_generate_kernel(const double *__restrict__ xyz, const float *__restrict_
   }
 }
 
-// fp64 signature rows -> fp32 counts [scan][16][256], non-zero masks [scan][16][8] and row sums [scan][16]; one warp per
-// (scan, row)
-__global__ void __launch_bounds__(256)
-delight_prep_kernel(const double *__restrict__ hist, size_t rows, float *__restrict__ out, unsigned *__restrict__ mask,
-                    float *__restrict__ rowsum) {
-  const int lane = threadIdx.x & 31;
-  for (size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (size_t)gridDim.x * 8) {
-    float sum = 0.0f;
-#pragma unroll
-    for (int w = 0; w < DL_BINS / 32; w++) {
-      const float v = (float)hist[row * DL_BINS + 32 * w + lane];
-      out[row * DL_BINS + 32 * w + lane] = v;
-      const unsigned bits = __ballot_sync(0xffffffffu, v > 0.0f);
-      if (lane == 0) mask[row * (DL_BINS / 32) + w] = bits;
-      sum += v;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);   // integers below 2^24: exact
-    if (lane == 0) rowsum[row] = sum;
-  }
+// fp64 signature rows -> fp32 counts [scan][16][256]
+__global__ void delight_to_f32_kernel(const double *__restrict__ hist, size_t n, float *__restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = (float)hist[i];
 }
 
 __constant__ int c_mut[4][16] = {{0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15},           // processDELIGHT.m:2-5
@@ -128,23 +112,12 @@ __constant__ int c_mut[4][16] = {{0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 
 
 constexpr int DT = 16;              // pairs per tile edge
 constexpr int DPAD = DL_BINS + 1;   // row pitch in shared memory (bank-conflict free for the per-thread DB rows)
-constexpr int DW = DL_BINS / 32;    // mask words per row
-
-struct DlPrepped {
-  const float *cnt;        // [scan][16][256]
-  const unsigned *mask;    // [scan][16][8]
-  const float *rowsum;     // [scan][16]
-};
 
 __global__ void __launch_bounds__(DT * DT)
-delight_match_kernel(DlPrepped A, int m, DlPrepped B, int n, double *__restrict__ dist) {
+delight_match_kernel(const float *__restrict__ h1, int m, const float *__restrict__ h2, int n, double *__restrict__ dist) {
   extern __shared__ float sm[];
   float *sa = sm;                      // [DT][DPAD]     query rows r
   float *sb = sm + DT * DPAD;          // [4][DT][DPAD]  DB rows Mut[k][r]
-  unsigned *ma = reinterpret_cast<unsigned *>(sm + 5 * DT * DPAD);   // [DT][DW]
-  unsigned *mb = ma + DT * DW;                                       // [4][DT][DW]
-  float *ra = reinterpret_cast<float *>(mb + 4 * DT * DW);           // [DT]
-  float *rb = ra + DT;                                               // [4][DT]
   const int tx = threadIdx.x & (DT - 1), ty = threadIdx.x / DT;
   const int q0 = blockIdx.y * DT, j0 = blockIdx.x * DT;
   double ts[4] = {0.0, 0.0, 0.0, 0.0};
@@ -153,44 +126,27 @@ delight_match_kernel(DlPrepped A, int m, DlPrepped B, int n, double *__restrict_
     __syncthreads();
     for (int e = threadIdx.x; e < DT * DL_BINS; e += DT * DT) {
       const int s = e >> 8, c = e & 255;
-      sa[s * DPAD + c] = q0 + s < m ? A.cnt[((size_t)(q0 + s) * DL_ROWS + r) * DL_BINS + c] : 0.0f;
+      sa[s * DPAD + c] = q0 + s < m ? h1[((size_t)(q0 + s) * DL_ROWS + r) * DL_BINS + c] : 0.0f;
 #pragma unroll
       for (int k = 0; k < 4; k++)
-        sb[(k * DT + s) * DPAD + c] = j0 + s < n ? B.cnt[((size_t)(j0 + s) * DL_ROWS + c_mut[k][r]) * DL_BINS + c] : 0.0f;
-    }
-    if (threadIdx.x < DT * DW) {
-      const int s = threadIdx.x / DW, w = threadIdx.x % DW;
-      ma[s * DW + w] = q0 + s < m ? A.mask[((size_t)(q0 + s) * DL_ROWS + r) * DW + w] : 0u;
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        mb[(k * DT + s) * DW + w] = j0 + s < n ? B.mask[((size_t)(j0 + s) * DL_ROWS + c_mut[k][r]) * DW + w] : 0u;
-    } else if (threadIdx.x < DT * DW + DT) {
-      const int s = threadIdx.x - DT * DW;
-      ra[s] = q0 + s < m ? A.rowsum[(size_t)(q0 + s) * DL_ROWS + r] : 0.0f;
-#pragma unroll
-      for (int k = 0; k < 4; k++) rb[k * DT + s] = j0 + s < n ? B.rowsum[(size_t)(j0 + s) * DL_ROWS + c_mut[k][r]] : 0.0f;
+        sb[(k * DT + s) * DPAD + c] = j0 + s < n ? h2[((size_t)(j0 + s) * DL_ROWS + c_mut[k][r]) * DL_BINS + c] : 0.0f;
     }
     __syncthreads();
+    float rs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 4
+    for (int c = 0; c < DL_BINS; c++) {
+      const float a = sa[ty * DPAD + c];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      float s_ab = 0.0f, s_chi = 0.0f;   // over the bins where both counts are non-zero: sum (a + b), sum 2 (a-b)^2 / (a+b)
-      int cnt = 0;
-#pragma unroll 1
-      for (int w = 0; w < DW; w++) {
-        const unsigned wa = ma[ty * DW + w], wb = mb[(k * DT + tx) * DW + w];
-        cnt += __popc(wa | wb);                              // processDELIGHT.m:25: a + b > 0
-        for (unsigned both = wa & wb; both; both &= both - 1) {
-          const int c = 32 * w + __ffs((int)both) - 1;
-          const float a = sa[ty * DPAD + c], b = sb[(k * DT + tx) * DPAD + c];
-          const float ab = a + b, df = a - b;
-          s_ab += ab;                                        // (integer below 2^24: exact)
-          s_chi = __fmaf_rn(2.0f * df * df, __fdividef(1.0f, ab), s_chi);   // :26-27
-        }
+      for (int k = 0; k < 4; k++) {
+        const float b = sb[(k * DT + tx) * DPAD + c];
+        // processDELIGHT.m:25-29, branch-free: counts are >= 0, so a + b == 0 means a == b == 0 and the term vanishes
+        const float ab = a + b, df = a - b;
+        rs[k] = __fmaf_rn(2.0f * df * df, __fdividef(1.0f, fmaxf(ab, 1e-30f)), rs[k]);
+        tc[k] += ab > 0.0f;
       }
-      // bins where only one count is non-zero contribute 2 x that count: 2 (S_a + S_b) - 2 sum_both (a + b), exact
-      ts[k] += (double)(2.0f * ((ra[ty] + rb[k * DT + tx]) - s_ab)) + (double)s_chi;
-      tc[k] += cnt;
     }
+#pragma unroll
+    for (int k = 0; k < 4; k++) ts[k] += (double)rs[k];
   }
   const int qi = q0 + ty, dj = j0 + tx;
   if (qi < m && dj < n) {
@@ -254,31 +210,21 @@ cudaError_t launch_delight_generate(const double *xyz, const float *inten, const
   return cudaGetLastError();
 }
 
-static size_t dl_align(size_t x) { return (x + 255) & ~(size_t)255; }
-size_t delight_match_workspace_bytes(int m, int n) {
-  const size_t rows = ((size_t)m + (size_t)n) * DL_ROWS;
-  return dl_align(rows * DL_BINS * sizeof(float)) + dl_align(rows * DW * sizeof(unsigned)) + dl_align(rows * sizeof(float)) + 256;
-}
+size_t delight_match_workspace_bytes(int m, int n) { return ((size_t)m + (size_t)n) * DL_SIZE * sizeof(float) + 256; }
 
 cudaError_t launch_delight_match(const double *hist1, int m, const double *hist2, int n, double *dist, void *workspace,
                                  cudaStream_t st, int64_t *launches) {
   if (m <= 0 || n <= 0) return cudaSuccess;
-  const size_t rows1 = (size_t)m * DL_ROWS, rows2 = (size_t)n * DL_ROWS, rows = rows1 + rows2;
-  unsigned char *w = reinterpret_cast<unsigned char *>(workspace);
-  float *cnt = reinterpret_cast<float *>(w);
-  unsigned *mask = reinterpret_cast<unsigned *>(w + dl_align(rows * DL_BINS * sizeof(float)));
-  float *rowsum = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(mask) + dl_align(rows * DW * sizeof(unsigned)));
-  delight_prep_kernel<<<1024, 256, 0, st>>>(hist1, rows1, cnt, mask, rowsum);
-  delight_prep_kernel<<<1024, 256, 0, st>>>(hist2, rows2, cnt + rows1 * DL_BINS, mask + rows1 * DW, rowsum + rows1);
-  const DlPrepped A{cnt, mask, rowsum}, B{cnt + rows1 * DL_BINS, mask + rows1 * DW, rowsum + rows1};
-  const size_t smem = (size_t)5 * DT * DPAD * sizeof(float) + (size_t)5 * DT * DW * sizeof(unsigned) + (size_t)5 * DT * sizeof(float);
+  float *f1 = reinterpret_cast<float *>(workspace), *f2 = f1 + (size_t)m * DL_SIZE;
+  delight_to_f32_kernel<<<1024, 256, 0, st>>>(hist1, (size_t)m * DL_SIZE, f1);
+  delight_to_f32_kernel<<<1024, 256, 0, st>>>(hist2, (size_t)n * DL_SIZE, f2);
+  const size_t smem = (size_t)5 * DT * DPAD * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(delight_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   for (int qb = 0; qb < m; qb += 65535 * DT) {
     const int mq = m - qb < 65535 * DT ? m - qb : 65535 * DT;
     dim3 grid((n + DT - 1) / DT, (mq + DT - 1) / DT);
-    const DlPrepped Aq{A.cnt + (size_t)qb * DL_SIZE, A.mask + (size_t)qb * DL_ROWS * DW, A.rowsum + (size_t)qb * DL_ROWS};
-    delight_match_kernel<<<grid, DT * DT, smem, st>>>(Aq, mq, B, n, dist + (size_t)qb * n);
+    delight_match_kernel<<<grid, DT * DT, smem, st>>>(f1 + (size_t)qb * DL_SIZE, mq, f2, n, dist + (size_t)qb * n);
   }
   if (launches) *launches += 3;
   return cudaGetLastError();
