@@ -597,7 +597,7 @@ __device__ __forceinline__ int mirror15_sr(int sr) { return sr ^ 15; }
 template <int PQ0, int PQ1, bool EXACT, bool FULL>
 __device__ __forceinline__ void bin_block(M2Smem &S, const ScanRef &R, int var, int slot, int twin_var, float R_f,
                                           float iscale, unsigned long long degen_mask, int degen_sr_pos,
-                                          int degen_sr_neg, int i0, float coord_lim) {
+                                          int degen_sr_neg, int i0, float coord_lim, bool degen_twin) {
   const int lane = threadIdx.x & 31;
   unsigned *hcnt = S.cnt[slot];
   int *hisum = S.isum[slot];
@@ -625,10 +625,28 @@ __device__ __forceinline__ void bin_block(M2Smem &S, const ScanRef &R, int var, 
     const float r2_lim = fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz))) < coord_lim ? 1e10f : -1.0f;
     // planes whose projection vectors are exactly zero (p=2, q=0): xp = yp = -0 if all three
     // coordinates are negative, +0 otherwise, and every point lands in one of two bins -> warp-aggregated
+    // degen_twin (exact mode, first variant of a pair): the same for variant twin_var into slot 1, under its own signs
     for (unsigned long long dm = degen_mask; dm; dm &= dm - 1) {
       const int pq = __ffsll((long long)dm) - 1;
       // signs of the flipped fp64 coordinates (a flip of +-0 flips the sign bit too; identity: untouched)
       const bool neg = act && (signbit(ax) != (ddx < 0.0)) && (signbit(ay) != (ddy < 0.0)) && (signbit(az) != (ddz < 0.0));
+      if (EXACT && degen_twin) {
+        double tdx, tdy, tdz;
+        variant_signs(twin_var, tdx, tdy, tdz);
+        const bool tneg = act && (signbit(ax) != (tdx < 0.0)) && (signbit(ay) != (tdy < 0.0)) && (signbit(az) != (tdz < 0.0));
+#pragma unroll
+        for (int cls = 0; cls < 2; cls++) {
+          const bool mine = act && (tneg == (cls == 1));
+          const unsigned ball = __ballot_sync(0xffffffffu, mine);
+          const int sr = cls ? degen_sr_neg : degen_sr_pos;
+          if (ball == 0u || sr < 0) continue;
+          const int sum = __reduce_add_sync(0xffffffffu, mine ? iv : 0);
+          if (lane == 0) {
+            atomicAdd(&S.cnt[1][pq * M2DP_SR + sr], (unsigned)__popc(ball));
+            atomicAdd(&S.isum[1][pq * M2DP_SR + sr], sum);
+          }
+        }
+      }
 #pragma unroll
       for (int cls = 0; cls < 2; cls++) {
         const bool mine = act && (neg == (cls == 1));
@@ -715,14 +733,14 @@ __device__ __forceinline__ void bin_block(M2Smem &S, const ScanRef &R, int var, 
 template <int PQ0, int PQ1, bool EXACT>
 __device__ __forceinline__ void bin_pass(M2Smem &S, const ScanRef &R, int var, int slot, int twin_var, float R_f,
                                          float iscale, unsigned long long degen_mask, int degen_sr_pos,
-                                         int degen_sr_neg, float coord_lim = 128.0f) {
+                                         int degen_sr_neg, float coord_lim = 128.0f, bool degen_twin = false) {
   int i0 = 0;
   for (; i0 + M2_THREADS <= R.n; i0 += M2_THREADS)
     bin_block<PQ0, PQ1, EXACT, true>(S, R, var, slot, twin_var, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg, i0,
-                                     coord_lim);
+                                     coord_lim, degen_twin);
   if (i0 < R.n)
     bin_block<PQ0, PQ1, EXACT, false>(S, R, var, slot, twin_var, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg, i0,
-                                      coord_lim);
+                                      coord_lim, degen_twin);
 }
 
 // the deferred evaluations of the passes since the queue was reset, one entry per thread
@@ -939,7 +957,9 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
             S.cnt[slot][r] = __ldcg(stash + b);
             S.isum[slot][r] = (int)__ldcg(stash + 2 * P0_BINS + b);
           }
-          bin_pass<M2DP_NUM_Q, M2DP_PQ, true>(S, R, a, 0, a + 2, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
+          // (this pass also adds the degenerate planes of variant a + 2, which has no pass of its own any more)
+          bin_pass<M2DP_NUM_Q, M2DP_PQ, true>(S, R, a, 0, a + 2, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg, 128.0f,
+                                              true);
         } else {
           bin_pass<0, M2DP_PQ, true>(S, R, a, 0, a + 2, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg,
                                      a == 0 && stash ? 64.0f : 128.0f);
@@ -963,11 +983,9 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
         }
         __syncthreads();
         M2_PROF(2);
-        // the planes of variant a + 2 that have no twin in this pair (p = 0; seeded: none) and its degenerate planes
-        // (sign rule of its own)
-        if (a == 1 && seeded)
-          bin_pass<0, 0, true>(S, R, a + 2, 1, -1, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg);
-        else
+        // the planes of variant a + 2 that have no twin in this pair (p = 0) and its degenerate planes (sign rule of its
+        // own); seeded: nothing left to do
+        if (!(a == 1 && seeded))
           bin_pass<0, M2DP_NUM_Q, true>(S, R, a + 2, 1, -1, R_f, iscale, degen_mask, degen_sr_pos, degen_sr_neg,
                                         a == 0 && stash ? 64.0f : 128.0f);
         __syncthreads();
