@@ -199,15 +199,17 @@ __device__ __forceinline__ unsigned long long queue_entry(int i, int pq, int slo
   return ((unsigned long long)(unsigned)i << 8) | (unsigned)(pq | (slot << 6) | (twin ? 0x80 : 0));
 }
 // stash != nullptr (first pair of a scan): an entry of a p = 0 plane of variant v also stands for the same plane of
-// variant v ^ 1 (second pair), whose p = 0 rows are kept in the stash
+// variant v ^ 1 (second pair), whose p = 0 rows are kept in the stash.
+// An entry has up to three jobs -- role 0: its own variant, 1: the twin plane of the pair's other variant, 2: the
+// stash -- each one fp64 evaluation (a few thousand clocks of dependent latency); role < 0 runs all of them in turn.
 template <bool EXACT>
 __device__ __forceinline__ void run_entry(M2Smem &S, const ScanRef &R, unsigned long long w, int var_slot0,
-                                          int var_slot1, float iscale, unsigned *stash = nullptr) {
+                                          int var_slot1, float iscale, unsigned *stash = nullptr, int role = -1) {
   const int i = (int)(w >> 8), pq = (int)(w & 0x3fu), slot = (int)((w >> 6) & 1u);
   const int var = slot ? var_slot1 : var_slot0;
-  add_exact<EXACT>(S, R, i, pq, var, slot, iscale);
-  if (w & 0x80u) add_exact<EXACT>(S, R, i, twin_plane(pq), var_slot1, 1, iscale);
-  if (EXACT && stash && pq < M2DP_NUM_Q) {
+  if (role < 0 || role == 0) add_exact<EXACT>(S, R, i, pq, var, slot, iscale);
+  if ((role < 0 || role == 1) && (w & 0x80u)) add_exact<EXACT>(S, R, i, twin_plane(pq), var_slot1, 1, iscale);
+  if ((role < 0 || role == 2) && EXACT && stash && pq < M2DP_NUM_Q) {
     const int idx = m2dp_bin_exact(R, i, pq, var ^ 1);
     if (idx >= 0) {
       atomicAdd(&stash[slot * P0_BINS + idx], 1u);
@@ -749,8 +751,9 @@ __device__ __forceinline__ void replay_queue(M2Smem &S, const ScanRef &R, int va
                                              unsigned *stash = nullptr) {
   const unsigned long long *queue = reinterpret_cast<const unsigned long long *>(S.T);
   const int qn = S.qn < QCAP ? S.qn : QCAP;
-  for (int e = threadIdx.x; e < qn; e += M2_THREADS)
-    run_entry<EXACT>(S, R, queue[e], var_slot0, var_slot1, iscale, stash);
+  // one thread per (entry, role): the up to three evaluations of an entry run side by side
+  for (int e = threadIdx.x; e < 3 * qn; e += M2_THREADS)
+    run_entry<EXACT>(S, R, queue[e / 3], var_slot0, var_slot1, iscale, stash, e % 3);
 }
 
 // binarise the slots [slot0, slot0 + nslot) (M2DP.cpp:84-91) into 128-bit row masks, then per slot the two dominant
