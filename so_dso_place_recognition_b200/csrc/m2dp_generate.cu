@@ -98,8 +98,8 @@ __device__ __forceinline__ void group_sync(int g) {
   asm volatile("bar.sync %0, %1;" ::"r"(8 + g), "r"(g ? SVD_G1 : SVD_G0) : "memory");
 }
 
-// phases: 0 moments + eigen-solve, 1 main binning pass, 2 twin-row copy, 3 binning of the p = 0 planes of the twin,
-// 4 queue replay, 5 binarise, 6 Gram (counts), 10 Gram (binary), 7 squarings, 8 power iteration, 9 v = A^T u + output
+// phases: 10 moments pass, 0 eigen-solve, 1 main binning pass, 2 twin-row copy, 3 binning of the p = 0 planes of the twin,
+// 4 queue replay, 5 binarise, 6 Gram matrices, 7 squarings, 8 power iteration, 9 v = A^T u + output
 #define M2_PROF(k)                                            \
   do {                                                        \
     if (S.prof_on && threadIdx.x == 0) {                      \
@@ -878,6 +878,7 @@ m2dp_generate_kernel(const double *__restrict__ xyz, const float *__restrict__ i
     emin = S.ibc[0];
     // every partial sum of the sequential float loop (M2DP.cpp:77-80) is exact -> the float sum is the exact sum
     const bool exact = emin == (1 << 20) ? s11[10] == 0.0 : s11[10] < ldexp(1.0, 24 + emin);
+    M2_PROF(10);
     if (threadIdx.x == 0) {
       if (variants && n > 0) {  // test_m2dp.cpp:44-45
         const double dn = (double)n;

@@ -18,8 +18,8 @@ print("m2dp_generate_kernel ms (profiled)", ctx.last_kernel_ms)
 out = (C.c_ulonglong * 16)()
 L.sodso_debug_phase_profile(0, C.cast(out, C.c_void_p))
 v = list(out)
-names = {0: "moments+eigen", 1: "main bin pass", 2: "twin copy", 3: "p=0 bin pass", 4: "queue replay", 5: "binarise",
-         6: "Gram (counts)", 10: "Gram (binary)", 7: "squarings", 8: "power iteration", 9: "A^T u + output"}
+names = {10: "moments pass", 0: "eigen-solve (1 thread)", 1: "main bin pass", 2: "twin copy", 3: "p=0 bin pass", 4: "queue replay", 5: "binarise",
+         6: "Gram matrices", 7: "squarings", 8: "power iteration", 9: "A^T u + output"}
 tot = sum(v[:11])
 for k in sorted(names):
     print("%-18s %6.2f %%  %8.0f clk/scan" % (names[k], 100.0 * v[k] / tot, v[k] / n))
