@@ -121,3 +121,57 @@ def test_m2dp_points_in_the_guard_band(gpu_ctx, oracle):
     c, i = api.M2DP(45.0).getSignature(pts, inten)
     np.testing.assert_allclose(c, c_ref, rtol=0, atol=TOL_SIG)
     np.testing.assert_allclose(i, i_ref, rtol=0, atol=TOL_SIG)
+
+
+def _symmetric_cloud(rng, n_half, scale):
+    """points in +- pairs: the centroid is the origin to rounding, the principal axes are the coordinate axes"""
+    p = rng.normal(size=(n_half, 3)) * np.asarray(scale, dtype=np.float64)
+    return np.concatenate([p, -p])
+
+
+@pytest.mark.parametrize("n_centre", [40, 60, 600])
+def test_m2dp_variant_sharing_with_a_full_guard_band_queue(gpu_ctx, oracle, n_centre):
+    """The four variants share plane evaluations (pairs (0, 2), (1, 3) exactly; the p = 0 planes across the pairs to
+    within the guard band), and evaluations inside the guard band are queued and replayed in fp64 per variant.  Points
+    within 1e-5 m of the centroid are inside the guard band of EVERY plane: 40 of them nearly fill the queue (3 200 of
+    4 096 entries, all with twin and cross-pair duties), 60 overflow it in the pass over the second variant's p = 0
+    planes only (those entries are served on the spot and the second pair may not be seeded from the first), 600
+    overflow it in the main pass (the pair is redone variant by variant).  Either way: the oracle's signatures."""
+    rng = np.random.default_rng(100 + n_centre)
+    cloud = _symmetric_cloud(rng, 1800, (2.0, 9.0, 21.0))
+    centre = _symmetric_cloud(rng, n_centre // 2, (1e-5, 1e-5, 1e-5))
+    xyz = np.concatenate([cloud, centre])
+    xyz = xyz[rng.permutation(len(xyz))] + np.array([3.0, -7.0, 11.0])
+    inten = rng.integers(0, 256, len(xyz)).astype(np.float32)
+    off = np.array([0, len(xyz)], dtype=np.int64)
+    ref = oracle.m2dp_generate(xyz, inten, off)
+    np.testing.assert_allclose(api.m2dp_generate(xyz, inten, off), ref, rtol=0, atol=TOL_SIG)
+    # the same scan between ordinary ones (the per-CTA stash and the queue are reused from scan to scan)
+    a, ai, _ = synth.make_scan_set(1, 2048)
+    xyz3 = np.concatenate([a, xyz, a])
+    inten3 = np.concatenate([ai, inten, ai])
+    off3 = np.array([0, len(a), len(a) + len(xyz), 2 * len(a) + len(xyz)], dtype=np.int64)
+    h3 = api.m2dp_generate(xyz3, inten3, off3)
+    np.testing.assert_allclose(h3[4:8], ref, rtol=0, atol=TOL_SIG)
+    np.testing.assert_array_equal(h3[0:4], h3[8:12])
+
+
+def test_m2dp_far_points_and_large_range(gpu_ctx, oracle):
+    """lidarRange 200 m: points beyond 64 m (no cross-pair sharing for them) and beyond 128 m (no fp32 proposal at all)"""
+    rng = np.random.default_rng(7)
+    xyz = _symmetric_cloud(rng, 1500, (6.0, 35.0, 70.0)) + np.array([1.0, 2.0, 3.0])
+    assert (np.abs(xyz).max(axis=1) > 64).sum() > 300 and (np.abs(xyz).max(axis=1) > 128).sum() > 20
+    inten = rng.integers(0, 256, len(xyz)).astype(np.float32)
+    off = np.array([0, len(xyz)], dtype=np.int64)
+    np.testing.assert_allclose(api.m2dp_generate(xyz, inten, off, 200.0), oracle.m2dp_generate(xyz, inten, off, 200.0),
+                               rtol=0, atol=TOL_SIG)
+
+
+def test_m2dp_large_scan_64bit_gram(gpu_ctx, oracle):
+    """70 000 points: Gram entries can exceed 2^32 (64-bit integer path), bin counts exceed 2^12"""
+    rng = np.random.default_rng(8)
+    xyz = rng.normal(size=(70000, 3)) * np.array([1.5, 6.0, 14.0])
+    inten = rng.integers(0, 256, len(xyz)).astype(np.float32)
+    off = np.array([0, len(xyz)], dtype=np.int64)
+    np.testing.assert_allclose(api.m2dp_generate(xyz, inten, off), oracle.m2dp_generate(xyz, inten, off, nthreads=4),
+                               rtol=0, atol=TOL_SIG)
