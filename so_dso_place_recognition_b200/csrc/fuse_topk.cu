@@ -12,6 +12,7 @@ namespace sodso {
 namespace {
 
 constexpr int FUSE_THREADS = 256;
+constexpr int FUSE_UNROLL = 8;     // row elements a thread loads together in fuse_topk_kernel
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
@@ -235,26 +236,40 @@ fuse_topk_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, i
       lv[t] = 0.0;
       lj[t] = -1;
     }
-    for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
-      const long long jg = db_row0 + j;
-      long long dist = qg - jg;
-      if (dist < 0) dist = -dist;
-      if (dist < (long long)mask_width) continue;
-      const double fl = fma(a_p, (double)p[j], fma(a_i, (double)q[j], c0));
-      if (!isfinite(fl)) continue;
-      if (cand_less(fl, jg, lv[KLL - 1], lj[KLL - 1])) {
-        lv[KLL - 1] = fl;
-        lj[KLL - 1] = jg;
+    // (the loads of FUSE_UNROLL elements are issued together: a thread has only ~20 elements of a row, and one load
+    // in flight at a time made the row scan a chain of memory latencies)
+    for (int j0 = threadIdx.x; j0 < n; j0 += FUSE_THREADS * FUSE_UNROLL) {
+      float pv[FUSE_UNROLL], qv[FUSE_UNROLL];
 #pragma unroll
-        for (int t = KLL - 1; t > 0; t--)
-          if (cand_less(lv[t], lj[t], lv[t - 1], lj[t - 1])) {
-            const double tv = lv[t];
-            const long long tj = lj[t];
-            lv[t] = lv[t - 1];
-            lj[t] = lj[t - 1];
-            lv[t - 1] = tv;
-            lj[t - 1] = tj;
-          }
+      for (int u = 0; u < FUSE_UNROLL; u++) {
+        const int j = j0 + u * FUSE_THREADS;
+        pv[u] = j < n ? p[j] : 0.0f;
+        qv[u] = j < n ? q[j] : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < FUSE_UNROLL; u++) {
+        const int j = j0 + u * FUSE_THREADS;
+        if (j >= n) break;
+        const long long jg = db_row0 + j;
+        long long dist = qg - jg;
+        if (dist < 0) dist = -dist;
+        if (dist < (long long)mask_width) continue;
+        const double fl = fma(a_p, (double)pv[u], fma(a_i, (double)qv[u], c0));
+        if (!isfinite(fl)) continue;
+        if (cand_less(fl, jg, lv[KLL - 1], lj[KLL - 1])) {
+          lv[KLL - 1] = fl;
+          lj[KLL - 1] = jg;
+#pragma unroll
+          for (int t = KLL - 1; t > 0; t--)
+            if (cand_less(lv[t], lj[t], lv[t - 1], lj[t - 1])) {
+              const double tv = lv[t];
+              const long long tj = lj[t];
+              lv[t] = lv[t - 1];
+              lj[t] = lj[t - 1];
+              lv[t - 1] = tv;
+              lj[t - 1] = tj;
+            }
+        }
       }
     }
     double sel_s = 0.0;
@@ -282,18 +297,30 @@ fuse_topk_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, i
       // second scan: the (typically exactly k) entries at or below the bound, evaluated exactly and sorted by one thread
       if (threadIdx.x == 0) cand_n = 0;
       __syncthreads();
-      for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
-        const long long jg = db_row0 + j;
-        long long dist = qg - jg;
-        if (dist < 0) dist = -dist;
-        if (dist < (long long)mask_width) continue;
-        if (!(fma(a_p, (double)p[j], fma(a_i, (double)q[j], c0)) <= bound)) continue;
-        const double f = p_weight * (((double)p[j] - mu_p) / sd_p) + ((double)q[j] - mu_i) / sd_i;   // run_test.m:40
-        if (f != f) continue;
-        const int slot = atomicAdd(&cand_n, 1);
-        if (slot < TOPK_CAND_CAP) {
-          cand_f[slot] = f;
-          cand_j[slot] = jg;
+      for (int j0 = threadIdx.x; j0 < n; j0 += FUSE_THREADS * FUSE_UNROLL) {
+        float pv[FUSE_UNROLL], qv[FUSE_UNROLL];
+#pragma unroll
+        for (int u = 0; u < FUSE_UNROLL; u++) {
+          const int j = j0 + u * FUSE_THREADS;
+          pv[u] = j < n ? p[j] : 0.0f;
+          qv[u] = j < n ? q[j] : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < FUSE_UNROLL; u++) {
+          const int j = j0 + u * FUSE_THREADS;
+          if (j >= n) break;
+          const long long jg = db_row0 + j;
+          long long dist = qg - jg;
+          if (dist < 0) dist = -dist;
+          if (dist < (long long)mask_width) continue;
+          if (!(fma(a_p, (double)pv[u], fma(a_i, (double)qv[u], c0)) <= bound)) continue;
+          const double f = p_weight * (((double)pv[u] - mu_p) / sd_p) + ((double)qv[u] - mu_i) / sd_i;   // run_test.m:40
+          if (f != f) continue;
+          const int slot = atomicAdd(&cand_n, 1);
+          if (slot < TOPK_CAND_CAP) {
+            cand_f[slot] = f;
+            cand_j[slot] = jg;
+          }
         }
       }
       __syncthreads();
