@@ -175,3 +175,20 @@ def test_m2dp_large_scan_64bit_gram(gpu_ctx, oracle):
     off = np.array([0, len(xyz)], dtype=np.int64)
     np.testing.assert_allclose(api.m2dp_generate(xyz, inten, off), oracle.m2dp_generate(xyz, inten, off, nthreads=4),
                                rtol=0, atol=TOL_SIG)
+
+
+def test_m2dp_empty_and_tiny_scans(gpu_ctx, oracle):
+    """0 points (zero matrices: u = e_0, v = 0), 1 point (it sits at the centroid: signed zeros through the sign flips
+    of the four variants, M2DP.cpp:59 at (+-0, +-0)) and a 40-point scan.  Scans of 2 or 3 points are left out on
+    purpose: their scatter matrix is rank deficient, the eigenvectors of the repeated zero eigenvalue are an
+    arbitrary basis (pts_align.h:31-34 takes whatever Eigen returns), and the 1e-16 coordinates along them decide
+    sectors -- the oracle and the kernels disagree there, and so would two Eigen versions."""
+    rng = np.random.default_rng(5)
+    sizes = [0, 1, 0, 40]
+    xyz = rng.normal(size=(sum(sizes), 3)) * np.array([3.0, 8.0, 15.0])
+    inten = rng.integers(0, 256, sum(sizes)).astype(np.float32)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    h = api.m2dp_generate(xyz, inten, off)
+    ref = oracle.m2dp_generate(xyz, inten, off)
+    assert h.shape == (16, 384)
+    np.testing.assert_allclose(h, ref, rtol=0, atol=TOL_SIG)
