@@ -8,7 +8,8 @@
 // Matching is not a GEMM: per pair min over 4 row permutations of  mean over {a + b > 0} of 2 (a - b)^2 / (a + b).
 // A CTA owns a 16 x 16 tile of pairs (one pair per thread); per histogram row r it stages the 16 query rows r and,
 // for each of the 4 permutations, the 16 DB rows Mut[k][r] in shared memory as fp32 counts (exact below 2^24) and
-// accumulates the terms in fp32 per row (256 terms), the row sums in fp64.  HBM traffic is the signatures (16 KB
+// accumulates the terms in fp32 per row (256 terms), the row sums in fp64; the number of contributing bins comes from
+// the popcount of the OR of 256-bit non-zero masks.  HBM traffic is the signatures (16 KB
 // each, L2 resident across tiles); the kernel is bound by the ~16 k divide-accumulate terms per pair.
 // Tried (tools/experiments/delight_match_sparse_masks.patch, parity green): only the bins where both counts are non-zero
 // need the reciprocal (one in seven at 37 % density; the others contribute 2 x the non-zero count, in closed form from row
@@ -99,10 +100,19 @@ delight_generate_kernel(const double *__restrict__ xyz, const float *__restrict_
   }
 }
 
-// fp64 signature rows -> fp32 counts [scan][16][256]
-__global__ void delight_to_f32_kernel(const double *__restrict__ hist, size_t n, float *__restrict__ out) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    out[i] = (float)hist[i];
+// fp64 signature rows -> fp32 counts [scan][16][256] and their non-zero masks [scan][16][8]; one warp per (scan, row)
+__global__ void __launch_bounds__(256)
+delight_prep_kernel(const double *__restrict__ hist, size_t rows, float *__restrict__ out, unsigned *__restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  for (size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (size_t)gridDim.x * 8) {
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      const float v = (float)hist[row * 256 + 32 * w + lane];
+      out[row * 256 + 32 * w + lane] = v;
+      const unsigned bits = __ballot_sync(0xffffffffu, v > 0.0f);
+      if (lane == 0) mask[row * 8 + w] = bits;
+    }
+  }
 }
 
 __constant__ int c_mut[4][16] = {{0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15},           // processDELIGHT.m:2-5
@@ -113,11 +123,16 @@ __constant__ int c_mut[4][16] = {{0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 
 constexpr int DT = 16;              // pairs per tile edge
 constexpr int DPAD = DL_BINS + 1;   // row pitch in shared memory (bank-conflict free for the per-thread DB rows)
 
+constexpr int DW = DL_BINS / 32;    // mask words per row
+
 __global__ void __launch_bounds__(DT * DT)
-delight_match_kernel(const float *__restrict__ h1, int m, const float *__restrict__ h2, int n, double *__restrict__ dist) {
+delight_match_kernel(const float *__restrict__ h1, const unsigned *__restrict__ m1, int m, const float *__restrict__ h2,
+                     const unsigned *__restrict__ m2, int n, double *__restrict__ dist) {
   extern __shared__ float sm[];
   float *sa = sm;                      // [DT][DPAD]     query rows r
   float *sb = sm + DT * DPAD;          // [4][DT][DPAD]  DB rows Mut[k][r]
+  unsigned *ma = reinterpret_cast<unsigned *>(sm + 5 * DT * DPAD);   // [DT][DW]     non-zero masks of the query rows
+  unsigned *mb = ma + DT * DW;                                       // [4][DT][DW]  ... of the DB rows
   const int tx = threadIdx.x & (DT - 1), ty = threadIdx.x / DT;
   const int q0 = blockIdx.y * DT, j0 = blockIdx.x * DT;
   double ts[4] = {0.0, 0.0, 0.0, 0.0};
@@ -131,7 +146,19 @@ delight_match_kernel(const float *__restrict__ h1, int m, const float *__restric
       for (int k = 0; k < 4; k++)
         sb[(k * DT + s) * DPAD + c] = j0 + s < n ? h2[((size_t)(j0 + s) * DL_ROWS + c_mut[k][r]) * DL_BINS + c] : 0.0f;
     }
+    if (threadIdx.x < DT * DW) {
+      const int s = threadIdx.x / DW, w = threadIdx.x % DW;
+      ma[s * DW + w] = q0 + s < m ? m1[((size_t)(q0 + s) * DL_ROWS + r) * DW + w] : 0u;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        mb[(k * DT + s) * DW + w] = j0 + s < n ? m2[((size_t)(j0 + s) * DL_ROWS + c_mut[k][r]) * DW + w] : 0u;
+    }
     __syncthreads();
+    // processDELIGHT.m:25: the number of bins with a + b > 0 (counts are >= 0) from the masks, not term by term
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+      for (int w = 0; w < DW; w++) tc[k] += __popc(ma[ty * DW + w] | mb[(k * DT + tx) * DW + w]);
     float rs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 4
     for (int c = 0; c < DL_BINS; c++) {
@@ -139,14 +166,14 @@ delight_match_kernel(const float *__restrict__ h1, int m, const float *__restric
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const float b = sb[(k * DT + tx) * DPAD + c];
-        // processDELIGHT.m:25-29, branch-free: counts are >= 0, so a + b == 0 means a == b == 0 and the term vanishes
+        // processDELIGHT.m:25-29, branch-free: a + b == 0 means a == b == 0 and the term vanishes; the factor 2 of
+        // :26 is applied to the row sum (exact)
         const float ab = a + b, df = a - b;
-        rs[k] = __fmaf_rn(2.0f * df * df, __fdividef(1.0f, fmaxf(ab, 1e-30f)), rs[k]);
-        tc[k] += ab > 0.0f;
+        rs[k] = __fmaf_rn(df * df, __fdividef(1.0f, fmaxf(ab, 1e-30f)), rs[k]);
       }
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) ts[k] += (double)rs[k];
+    for (int k = 0; k < 4; k++) ts[k] += (double)(2.0f * rs[k]);
   }
   const int qi = q0 + ty, dj = j0 + tx;
   if (qi < m && dj < n) {
@@ -210,21 +237,29 @@ cudaError_t launch_delight_generate(const double *xyz, const float *inten, const
   return cudaGetLastError();
 }
 
-size_t delight_match_workspace_bytes(int m, int n) { return ((size_t)m + (size_t)n) * DL_SIZE * sizeof(float) + 256; }
+static size_t dl_align(size_t x) { return (x + 255) & ~(size_t)255; }
+size_t delight_match_workspace_bytes(int m, int n) {
+  const size_t rows = ((size_t)m + (size_t)n) * DL_ROWS;
+  return dl_align(rows * DL_BINS * sizeof(float)) + dl_align(rows * DW * sizeof(unsigned)) + 256;
+}
 
 cudaError_t launch_delight_match(const double *hist1, int m, const double *hist2, int n, double *dist, void *workspace,
                                  cudaStream_t st, int64_t *launches) {
   if (m <= 0 || n <= 0) return cudaSuccess;
-  float *f1 = reinterpret_cast<float *>(workspace), *f2 = f1 + (size_t)m * DL_SIZE;
-  delight_to_f32_kernel<<<1024, 256, 0, st>>>(hist1, (size_t)m * DL_SIZE, f1);
-  delight_to_f32_kernel<<<1024, 256, 0, st>>>(hist2, (size_t)n * DL_SIZE, f2);
-  const size_t smem = (size_t)5 * DT * DPAD * sizeof(float);
+  const size_t rows1 = (size_t)m * DL_ROWS, rows2 = (size_t)n * DL_ROWS, rows = rows1 + rows2;
+  float *f1 = reinterpret_cast<float *>(workspace), *f2 = f1 + rows1 * DL_BINS;
+  unsigned *k1 = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(workspace) + dl_align(rows * DL_BINS * sizeof(float)));
+  unsigned *k2 = k1 + rows1 * DW;
+  delight_prep_kernel<<<1024, 256, 0, st>>>(hist1, rows1, f1, k1);
+  delight_prep_kernel<<<1024, 256, 0, st>>>(hist2, rows2, f2, k2);
+  const size_t smem = (size_t)5 * DT * DPAD * sizeof(float) + (size_t)5 * DT * DW * sizeof(unsigned);
   cudaError_t e = cudaFuncSetAttribute(delight_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   for (int qb = 0; qb < m; qb += 65535 * DT) {
     const int mq = m - qb < 65535 * DT ? m - qb : 65535 * DT;
     dim3 grid((n + DT - 1) / DT, (mq + DT - 1) / DT);
-    delight_match_kernel<<<grid, DT * DT, smem, st>>>(f1 + (size_t)qb * DL_SIZE, mq, f2, n, dist + (size_t)qb * n);
+    delight_match_kernel<<<grid, DT * DT, smem, st>>>(f1 + (size_t)qb * DL_SIZE, k1 + (size_t)qb * DL_ROWS * DW, mq, f2, k2, n,
+                                                      dist + (size_t)qb * n);
   }
   if (launches) *launches += 3;
   return cudaGetLastError();
