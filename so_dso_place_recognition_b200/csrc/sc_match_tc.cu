@@ -140,68 +140,94 @@ struct __align__(16) RowImg {
 };
 static_assert(sizeof(RowImg) % 128 == 96, "bank staggering of consecutive images: b * 96 mod 128 = 0, 96, 64, 32");
 
-// builds the image of channel ch of one signature row (nsect = 30 for the DB operand, 60 for queries)
-__device__ inline void build_img(const double *h, bool valid, int ch, bool is_db, int nsect, RowImg &S) {
-  const double *hc = h + ch * SC_SIZE;
-  double ss = 0.0;
-  int nb = 0;
-  if (valid)
-    for (int k = threadIdx.x; k < SC_SIZE; k += blockDim.x) {
-      const double v = hc[k];
-      ss += v * v;
-      if (v != 0.0 && v != 1.0) nb = 1;
-    }
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_down_sync(0xffffffffu, ss, o);
-  if (threadIdx.x == 0) S.nonbin = 0;
-  if ((threadIdx.x & 31) == 0) S.red[threadIdx.x >> 5] = ss;
-  __syncthreads();
-  if (nb) atomicOr(&S.nonbin, 1);
-  double s = 0.0;
-  for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += S.red[w];
-  const double nrm = sqrt(s);  // processSC.m:16,19
-  // h / |h| as h * (1 / |h|): one fp64 division per thread instead of four per work item; the operand is rounded to
-  // 22 bits (fp16 hi + lo) right after, so the last-bit difference from the quotient is invisible
-  const double scale = (double)VAL_SCALE / nrm;
-  const __half2 zero2 = __floats2half2_rn(0.0f, 0.0f);
-  // one work item = rings 2t, 2t + 1 of sequence position u
-  for (int it = threadIdx.x; it < nsect * (SC_NUM_R / 2); it += blockDim.x) {
-    const int u = it / (SC_NUM_R / 2), t = it - u * (SC_NUM_R / 2);
-    const int u2 = u < HALF_S ? u + HALF_S : u - HALF_S;      // sector (u + 30) mod 60
-    __half2 hi[NCOMP], lo[NCOMP];
-    unsigned nib[NCOMP] = {0u, 0u};
-    if (valid) {
-      __half h_hi[NCOMP][2], h_lo[NCOMP][2];
+// builds the images of channel ch of NB signature rows at once (nsect = 30 for the DB operand, 60 for queries): the
+// loads of all rows are in flight together and there is one reduction / two barriers for the NB rows, not per row
+template <int NB>
+__device__ inline void build_imgs(const double *h0, int row0, int nrows, int ch, bool is_db, int nsect, RowImg *S) {
+  double ss[NB];
+  int nb[NB];
 #pragma unroll
-      for (int q = 0; q < 2; q++) {
-        const double r1 = hc[u * SC_NUM_R + 2 * t + q], r2 = hc[u2 * SC_NUM_R + 2 * t + q];
-        const double v1 = r1 * scale, v2 = r2 * scale;
-        split_fp16(v1 + v2, h_hi[0][q], h_lo[0][q]);
-        split_fp16(v1 - v2, h_hi[1][q], h_lo[1][q]);
-        const int b1 = r1 == 1.0, b2 = r2 == 1.0;
-        nib[0] |= (b1 + b2 == 2 ? 0x4u : (b1 + b2 == 1 ? 0x2u : 0x0u)) << (4 * q);   // e2m1 2.0 / 1.0 / 0
-        nib[1] |= (b1 == b2 ? 0x0u : (b1 ? 0x2u : 0xAu)) << (4 * q);                 // 0 / +1.0 / -1.0
+  for (int b = 0; b < NB; b++) {
+    ss[b] = 0.0;
+    nb[b] = 0;
+  }
+  for (int k = threadIdx.x; k < SC_SIZE; k += blockDim.x) {
+    double v[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) v[b] = row0 + b < nrows ? h0[(size_t)b * 2 * SC_SIZE + ch * SC_SIZE + k] : 0.0;
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+      ss[b] += v[b] * v[b];
+      if (v[b] != 0.0 && v[b] != 1.0) nb[b] = 1;
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    for (int o = 16; o > 0; o >>= 1) ss[b] += __shfl_down_sync(0xffffffffu, ss[b], o);
+    if (threadIdx.x == 0) S[b].nonbin = 0;
+    if ((threadIdx.x & 31) == 0) S[b].red[threadIdx.x >> 5] = ss[b];
+  }
+  __syncthreads();
+  double scale[NB], nrm[NB];
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    if (nb[b]) atomicOr(&S[b].nonbin, 1);
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += S[b].red[w];
+    nrm[b] = sqrt(s);  // processSC.m:16,19
+    // h / |h| as h * (1 / |h|): one fp64 division per thread instead of four per work item; the operand is rounded to
+    // 22 bits (fp16 hi + lo) right after, so the last-bit difference from the quotient is invisible
+    scale[b] = (double)VAL_SCALE / nrm[b];
+  }
+  const __half2 zero2 = __floats2half2_rn(0.0f, 0.0f);
+  const int per_row = nsect * (SC_NUM_R / 2);
+  // one work item = rings 2t, 2t + 1 of sequence position u of row b
+  for (int it0 = threadIdx.x; it0 < per_row; it0 += blockDim.x) {
+    const int u = it0 / (SC_NUM_R / 2), t = it0 - u * (SC_NUM_R / 2);
+    const int u2 = u < HALF_S ? u + HALF_S : u - HALF_S;      // sector (u + 30) mod 60
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+      const bool valid = row0 + b < nrows;
+      const double *hc = h0 + (size_t)b * 2 * SC_SIZE + ch * SC_SIZE;
+      __half2 hi[NCOMP], lo[NCOMP];
+      unsigned nib[NCOMP] = {0u, 0u};
+      if (valid) {
+        __half h_hi[NCOMP][2], h_lo[NCOMP][2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const double r1 = hc[u * SC_NUM_R + 2 * t + q], r2 = hc[u2 * SC_NUM_R + 2 * t + q];
+          const double v1 = r1 * scale[b], v2 = r2 * scale[b];
+          split_fp16(v1 + v2, h_hi[0][q], h_lo[0][q]);
+          split_fp16(v1 - v2, h_hi[1][q], h_lo[1][q]);
+          const int b1 = r1 == 1.0, b2 = r2 == 1.0;
+          nib[0] |= (b1 + b2 == 2 ? 0x4u : (b1 + b2 == 1 ? 0x2u : 0x0u)) << (4 * q);   // e2m1 2.0 / 1.0 / 0
+          nib[1] |= (b1 == b2 ? 0x0u : (b1 ? 0x2u : 0xAu)) << (4 * q);                 // 0 / +1.0 / -1.0
+        }
+#pragma unroll
+        for (int comp = 0; comp < NCOMP; comp++) {
+          hi[comp] = __halves2half2(h_hi[comp][0], h_hi[comp][1]);
+          lo[comp] = __halves2half2(h_lo[comp][0], h_lo[comp][1]);
+        }
+      } else {
+#pragma unroll
+        for (int comp = 0; comp < NCOMP; comp++) hi[comp] = lo[comp] = zero2;
       }
 #pragma unroll
       for (int comp = 0; comp < NCOMP; comp++) {
-        hi[comp] = __halves2half2(h_hi[comp][0], h_hi[comp][1]);
-        lo[comp] = __halves2half2(h_lo[comp][0], h_lo[comp][1]);
+        __half2 *dst = reinterpret_cast<__half2 *>(&S[b].f16[comp][u][0]);
+        dst[t] = is_db ? hi[comp] : lo[comp];
+        dst[10 + t] = is_db ? lo[comp] : hi[comp];
+        dst[20 + t] = hi[comp];
+        if (t < 2) dst[30 + t] = zero2;                          // slots 60..63
+        S[b].f4[comp][u][t] = (unsigned char)nib[comp];
+        if (t < 6) S[b].f4[comp][u][10 + t] = 0;                 // rings 20..31: padding
       }
-    } else {
-#pragma unroll
-      for (int comp = 0; comp < NCOMP; comp++) hi[comp] = lo[comp] = zero2;
-    }
-#pragma unroll
-    for (int comp = 0; comp < NCOMP; comp++) {
-      __half2 *dst = reinterpret_cast<__half2 *>(&S.f16[comp][u][0]);
-      dst[t] = is_db ? hi[comp] : lo[comp];
-      dst[10 + t] = is_db ? lo[comp] : hi[comp];
-      dst[20 + t] = hi[comp];
-      if (t < 2) dst[30 + t] = zero2;                          // slots 60..63
-      S.f4[comp][u][t] = (unsigned char)nib[comp];
-      if (t < 6) S.f4[comp][u][10 + t] = 0;                    // rings 20..31: padding
     }
   }
-  if (threadIdx.x == 0) S.inv_norm = valid ? (float)(1.0 / nrm) : 0.0f;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int b = 0; b < NB; b++) S[b].inv_norm = row0 + b < nrows ? (float)(1.0 / nrm[b]) : 0.0f;
+  }
   __syncthreads();
 }
 
@@ -211,7 +237,7 @@ sc_tc_prep_db_kernel(const double *__restrict__ hist, int n, int n_pad, unsigned
                      size_t off_f16, size_t off_f4, size_t off_norm, int row0) {
   __shared__ RowImg S;
   const int row = row0 + blockIdx.x, ch = blockIdx.y;
-  build_img(hist + (size_t)row * 2 * SC_SIZE, row < n, ch, true, HALF_S, S);
+  build_imgs<1>(hist + (size_t)row * 2 * SC_SIZE, row, n, ch, true, HALF_S, &S);
   if (threadIdx.x == 0) {
     if (S.nonbin) atomicOr(reinterpret_cast<int *>(buf) + ch, 1);
     reinterpret_cast<float *>(buf + off_norm)[(size_t)ch * n_pad + row] = S.inv_norm;
@@ -241,13 +267,11 @@ sc_tc_prep_query_kernel(const double *__restrict__ hist, int m, int m_pad, unsig
   extern __shared__ __align__(16) unsigned char prep_smem[];
   RowImg *S = reinterpret_cast<RowImg *>(prep_smem);
   const int group = group0 + blockIdx.x, ngroups = m_pad / QG, ch = blockIdx.y;
-  for (int b = 0; b < QG; b++) {
-    const int row = QG * group + b;
-    build_img(hist + (size_t)row * 2 * SC_SIZE, row < m, ch, false, SC_NUM_S, S[b]);
-    if (threadIdx.x == 0) {
-      if (S[b].nonbin) atomicOr(reinterpret_cast<int *>(buf) + ch, 1);
-      reinterpret_cast<float *>(buf + off_norm)[(size_t)ch * m_pad + row] = S[b].inv_norm;
-    }
+  build_imgs<QG>(hist + (size_t)QG * group * 2 * SC_SIZE, QG * group, m, ch, false, SC_NUM_S, S);
+  if (threadIdx.x < QG) {
+    const int b = threadIdx.x, row = QG * group + b;
+    if (S[b].nonbin) atomicOr(reinterpret_cast<int *>(buf) + ch, 1);
+    reinterpret_cast<float *>(buf + off_norm)[(size_t)ch * m_pad + row] = S[b].inv_norm;
   }
   for (int base = 0; base < 2; base++) {
     const size_t gb = ((size_t)ch * 2 + base) * ngroups + group;
