@@ -13,6 +13,7 @@ namespace {
 
 constexpr int FUSE_THREADS = 256;
 constexpr int FUSE_UNROLL = 8;     // row elements a thread loads together in fuse_topk_kernel
+constexpr int STATS_UNROLL = 10;   // ... and in row_stats_kernel
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
@@ -127,18 +128,30 @@ row_stats_kernel(const float *__restrict__ d_p, const float *__restrict__ d_i, i
   const int row = blockIdx.x;
   const float *p = d_p + (size_t)row * ldd, *q = d_i + (size_t)row * ldd;
   double v[STATS_W] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  for (int j = threadIdx.x; j < n; j += FUSE_THREADS) {
-    const float pf = p[j], qf = q[j];
-    const double a = (double)pf - STAT_SHIFT, b = (double)qf - STAT_SHIFT;
-    if (pf == pf) {
-      v[0] += a;
-      v[1] += a * a;
-      v[2] += 1.0;
+  // (the loads of STATS_UNROLL elements per channel are issued together; the sums run in the same order as a plain loop)
+  for (int j0 = threadIdx.x; j0 < n; j0 += FUSE_THREADS * STATS_UNROLL) {
+    float pv[STATS_UNROLL], qv[STATS_UNROLL];
+#pragma unroll
+    for (int u = 0; u < STATS_UNROLL; u++) {
+      const int j = j0 + u * FUSE_THREADS;
+      pv[u] = j < n ? p[j] : 0.0f;
+      qv[u] = j < n ? q[j] : 0.0f;
     }
-    if (qf == qf) {
-      v[3] += b;
-      v[4] += b * b;
-      v[5] += 1.0;
+#pragma unroll
+    for (int u = 0; u < STATS_UNROLL; u++) {
+      if (j0 + u * FUSE_THREADS >= n) break;
+      const float pf = pv[u], qf = qv[u];
+      const double a = (double)pf - STAT_SHIFT, b = (double)qf - STAT_SHIFT;
+      if (pf == pf) {
+        v[0] += a;
+        v[1] += a * a;
+        v[2] += 1.0;
+      }
+      if (qf == qf) {
+        v[3] += b;
+        v[4] += b * b;
+        v[5] += 1.0;
+      }
     }
   }
   block_sum_d<STATS_W>(v, scratch);
